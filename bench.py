@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the ggml block codec hot path on B200 (see BASELINE.json).
+
+Workload (N=1): BASELINE.json configs[1] — Llama-3-8B-shaped synthetic tensors (4096x14336 FFN,
+4096x4096 attention), dequantize Q4_0 / Q8_0 / Q4_K / Q6_K -> f16.  One *step* = one pass of
+`dequantize_slice` over all 8 (type, shape) tensors.  Metric: algorithmic GB/s
+(bytes = packed bytes read + f16 bytes written), whole job.
+
+  value     device-resident: inputs already in HBM, kernels launched through the C ABI
+            (`ggq_dequantize_slice_device`) on torch's current stream, CUDA-event timed.
+  e2e       the same step through the host C ABI (`ggq_dequantize_slice`, the drop-in for
+            QuantExt::dequantize_slice) with pinned HOST buffers: H2D + kernel + D2H inside the timing.
+  roofline  the dominant kernel (largest share of the step): algorithmic bytes per launch / average
+            launch duration from CUDA events recorded around that launch inside the timed region.
+  cpu_baseline  the CPU oracle port (oracle/, the reference's algorithm restated in C; the Rust
+            reference cannot be built in this image) on the host cores, bounded sample.
+
+`--impl reference` times that CPU port on the same workload config (bounded sample per step).
+Multi-GPU (`torchrun ... bench.py --gpus N`): tensors are independent, each rank processes its own
+copy of the workload on its own GPU, no collective on the data path => "scaling": "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+F32, F16, BF16 = 0, 1, 30
+Q4_0, Q8_0, Q4K, Q6K = 2, 8, 12, 14
+NAMES = {2: "Q4_0", 8: "Q8_0", 12: "Q4_K", 14: "Q6_K"}
+BLOCK = {2: (32, 18), 8: (32, 34), 12: (256, 144), 14: (256, 210)}
+SHAPES = {"ffn": (4096, 14336), "attn": (4096, 4096)}
+TYPES = [Q4_0, Q8_0, Q4K, Q6K]
+WORKLOAD = "llama3-8b-shaped dequant Q4_0/Q8_0/Q4_K/Q6_K->f16: 4096x14336 + 4096x4096 per type (BASELINE configs[1])"
+METRIC = "dequant_GBps_algorithmic"
+UNIT = "GB/s"
+
+
+def algo_bytes(ty, n_elems):
+    e, b = BLOCK[ty]
+    return n_elems // e * b + n_elems * 2
+
+
+def tensors():
+    out = []
+    for ty in TYPES:
+        for sname, (r, c) in SHAPES.items():
+            out.append((ty, sname, r * c))
+    return out
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+def run_cpu_port(steps, warmup, sample_elems, threads):
+    """The oracle port on host cores: dequantize `sample_elems` elements of every type per step."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    packed = {}
+    for ty in TYPES:
+        e, b = BLOCK[ty]
+        x = (rng.standard_normal(sample_elems) * 0.02).astype(np.float32).astype(np.float16)
+        packed[ty] = O.quantize(ty, O.F16, x, threads=threads)
+    outs = {ty: np.empty(sample_elems, np.uint16) for ty in TYPES}
+    L = O.lib()
+
+    def step():
+        for ty in TYPES:
+            e, b = BLOCK[ty]
+            rc = L.ggo_dequantize_slice(ty, O.F16, outs[ty].ctypes.data, sample_elems, packed[ty].ctypes.data, sample_elems // e, threads)
+            assert rc == 0
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    nbytes = sum(algo_bytes(ty, sample_elems) for ty in TYPES)
+    return nbytes * steps / dt / 1e9, dt / steps * 1e3
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 4096 * 4096
+    gbs, ms = run_cpu_port(args.steps, max(args.warmup, 1), sample, threads)
+    sample_desc = f"4096x4096 elements per type x {len(TYPES)} types per step (attention-shaped slice of the workload), {threads} pthreads over contiguous block ranges"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/f32->f16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU port of the reference algorithm (oracle/ggq_oracle.c); the Rust reference cannot be compiled here (no cargo/rustc)"},
+        "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import gguf_b200 as g
+    from gguf_b200._lib import lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = lib()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- synthetic tensors: Gaussian f16 weights, quantised ON THE GPU by this library ----
+    work = []
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1 + rank)
+    for ty, sname, n in tensors():
+        e, b = BLOCK[ty]
+        x = (torch.randn(n, device=dev, generator=gen, dtype=torch.float32) * 0.02).to(torch.float16)
+        packed = torch.empty(n // e * b, dtype=torch.uint8, device=dev)
+        g.quantize_slice_device(ty, F16, packed, n // e, x, n, stream)
+        out = torch.empty(n, dtype=torch.float16, device=dev)
+        work.append({"ty": ty, "shape": sname, "n": n, "nb": n // e, "packed": packed, "out": out, "bytes": algo_bytes(ty, n)})
+        del x
+    torch.cuda.synchronize()
+    step_bytes = sum(w["bytes"] for w in work)
+
+    def step(events=None):
+        for i, w in enumerate(work):
+            if events is not None:
+                events[i][0].record()
+            g.dequantize_slice_device(w["ty"], F16, w["out"], w["n"], w["packed"], w["nb"], stream)
+            if events is not None:
+                events[i][1].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    # ---- timed region: K steps, events around every launch (per-kernel durations) ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in work] for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = L.ggq_launch_count()
+    barrier()
+    t_start.record()
+    for k in range(args.steps):
+        step(ev[k])
+    t_end.record()
+    barrier()
+    launches = L.ggq_launch_count() - launches0
+    clocks = sampler.stop()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = step_bytes * args.steps * world / (elapsed_ms * 1e-3) / 1e9
+
+    per_kernel = []
+    for i, w in enumerate(work):
+        ms = float(np.mean([ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(args.steps)]))
+        per_kernel.append({"kernel": f"dequant_kernel<{NAMES[w['ty']]},f16>", "shape": w["shape"], "us": ms * 1e3,
+                           "GBps": w["bytes"] / (ms * 1e-3) / 1e9, "bytes": w["bytes"]})
+    dom = max(per_kernel, key=lambda r: r["us"])
+    peak, peak_src = measured_peak()
+    roofline = {"bound": "hbm", "kernel": f"{dom['kernel']} {dom['shape']}", "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": dom["GBps"] / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"],
+                "avg_launch_us": dom["us"]}
+
+    # ---- e2e: host C ABI with pinned host buffers (H2D + kernel + D2H in the timing) ----
+    e2e = None
+    if not args.no_e2e:
+        host = []
+        for w in work:
+            pin_in, pin_out = g.PinnedBuffer(w["packed"].numel()), g.PinnedBuffer(w["n"] * 2)
+            pin_in.array[:] = w["packed"].cpu().numpy()
+            host.append((w, pin_in, pin_out))
+
+        def host_step():
+            for w, pi, po in host:
+                g.dequantize_slice(w["ty"], po.view(np.uint16), pi.array, F16)
+        for _ in range(max(1, min(args.warmup, 2))):
+            host_step()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        # spot check: the host path and the device path agree byte for byte
+        w, pi, po = host[0]
+        assert np.array_equal(po.view(np.uint16), w["out"].cpu().numpy().view(np.uint16)), "host/device path mismatch"
+        e2e = {"value": step_bytes * e2e_steps * world / dt / 1e9, "unit": UNIT, "steps": e2e_steps,
+               "h2d_bytes_per_step": int(sum(w["packed"].numel() for w in work)), "d2h_bytes_per_step": int(sum(w["n"] * 2 for w in work)),
+               "api": "ggq_dequantize_slice (host pointers, pinned)", "ms_per_step": dt / e2e_steps * 1e3}
+        for _, pi, po in host:
+            pi.free(); po.free()
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        sample = 4096 * 4096
+        gbs, _ = run_cpu_port(3, 1, sample, threads)
+        cpu = {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"4096x4096 elements per type x {len(TYPES)} types, 3 passes, oracle/ggq_oracle.c with {threads} pthreads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/f32->f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "bytes_per_step_per_gpu": step_bytes,
+                       "l2": "per-step footprint (packed+f16 of 8 tensors = %.0f MB) exceeds the 126 MB L2; no flush needed" % (step_bytes / 1e6),
+                       "sharding": "by tensor, one replica of the workload per GPU, no collective"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "frac_of_peak_whole_step": value / world / peak, "per_kernel": per_kernel,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:])
+    ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,48 @@
+"""ctypes loader for libggq.so (the C ABI declared in include/ggq.h).
+
+There is deliberately no fallback: if the shared library has not been built (run
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C gguf_b200/csrc``) importing a
+compute entry point raises, and every compute call fails with GGQ_ERR_CUDA when no GPU is present.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libggq.so")
+
+# every symbol include/ggq.h declares: (name, restype, argtypes)
+_c = ctypes
+SYMBOLS = [
+    ("ggq_block_info", _c.c_int, [_c.c_uint32, _c.POINTER(_c.c_uint32), _c.POINTER(_c.c_uint32)]),
+    ("ggq_last_error", _c.c_char_p, []),
+    ("ggq_device_count", _c.c_int, []),
+    ("ggq_set_device", _c.c_int, [_c.c_int]),
+    ("ggq_quantize_slice", _c.c_int, [_c.c_uint32, _c.c_uint32, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_size_t]),
+    ("ggq_dequantize_slice", _c.c_int, [_c.c_uint32, _c.c_uint32, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_size_t]),
+    ("ggq_quantize_slice_device", _c.c_int,
+     [_c.c_uint32, _c.c_uint32, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    ("ggq_dequantize_slice_device", _c.c_int,
+     [_c.c_uint32, _c.c_uint32, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    ("ggq_host_alloc", _c.c_void_p, [_c.c_size_t]),
+    ("ggq_host_free", None, [_c.c_void_p]),
+    ("ggq_launch_count", _c.c_uint64, []),
+    ("ggq_version", _c.c_char_p, []),
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(
+                f"{SO_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "gguf_b200 has no CPU fallback.")
+        L = ctypes.CDLL(SO_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)  # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib

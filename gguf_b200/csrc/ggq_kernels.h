@@ -1,0 +1,43 @@
+// ggq_kernels.h — internal launch entry points shared by the kernel TUs and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ggq {
+
+constexpr int MAX_DEVICES = 32;
+
+struct DevInfo {
+    int device;    // CUDA ordinal the launch targets (current device of the caller)
+    int sm_count;  // multiProcessorCount
+};
+
+// packed blocks -> float side.  `type` is a block type (legacy / K / Q8K).
+cudaError_t dequant_blocks(uint32_t type, uint32_t fdt, const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev);
+// float side -> packed blocks, legacy 32-element blocks and Q8K.
+cudaError_t quant_blocks_legacy(uint32_t type, uint32_t fdt, const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev);
+// float side -> packed blocks, K-quants (Q2K..Q6K).
+cudaError_t quant_blocks_k(uint32_t type, uint32_t fdt, const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev);
+// element casts between f32 / f16 / bf16 (the 1-element "blocks" of structs/half.rs).
+cudaError_t cast_elems(uint32_t src_dt, uint32_t dst_dt, const void *src, void *dst, size_t n, cudaStream_t stream, DevInfo dev);
+
+// occupancy cache helper: resident CTAs per SM for `kern`, after raising its dynamic smem limit.
+template <class K>
+static inline cudaError_t cached_occupancy(K kern, int threads, int smem, int device, int *cache, int *out) {
+    int v = cache[device];
+    if (v == 0) {
+        cudaError_t e = cudaSuccess;
+        if (smem > 0) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
+        if (e != cudaSuccess) return e;
+        v = n > 0 ? n : 1;
+        cache[device] = v;
+    }
+    *out = v;
+    return cudaSuccess;
+}
+
+}  // namespace ggq

@@ -1,0 +1,555 @@
+// quant_k.cu — f32 / f16 / bf16 -> Q2K Q3K Q4K Q5K Q6K (256-element super-blocks), sm_100a.
+// Compiled with -fmad=false -prec-div=true -prec-sqrt=true -ftz=false: every expression below is
+// evaluated exactly as written, one IEEE rounding per operator, left to right — the same way the
+// CPU oracle (oracle/ggq_oracle.c, built with -ffp-contract=off) evaluates it.
+//
+// The reference only declares these layouts (/root/reference/ggml-quants/src/structs/q{2..6}_k.rs;
+// quantize is `todo!()`), so the arithmetic is upstream ggml's `quantize_row_qN_K_ref`, whose scale
+// search is *sequentially dependent across candidates* (an accepted candidate changes `min` for the
+// next one).  It therefore cannot be split across lanes without changing results.  Mapping used:
+//   * ONE LANE PER SUB-BLOCK (32 elements for Q4K/Q5K, 16 for Q2K/Q3K/Q6K): a warp owns 4 (resp. 2)
+//     consecutive super-blocks; each lane keeps its sub-block in registers and runs the search in
+//     the oracle's exact order — no redundant work, no cross-lane float reduction;
+//   * the 8/16 per-sub-block results of a super-block are combined by xor-shuffles (max is
+//     order-independent; "first with greatest |.|" uses a lowest-lane-wins arg-max);
+//   * codes go through a per-warp shared-memory scratch and are assembled bytewise into the packed
+//     layout, then copied to global memory.
+// This path is COMPUTE-bound (~400 dependent flops per element for Q4K), not HBM-bound; see DESIGN.md.
+#include "ggq_common.cuh"
+#include "ggq_kernels.h"
+
+namespace ggq {
+
+constexpr unsigned KFULL = 0xFFFFFFFFu;
+constexpr int KQ_WARPS = 4;
+constexpr int KQ_THREADS = KQ_WARPS * 32;
+#define GROUP_MAX_EPS 1e-15f
+
+__device__ __forceinline__ int nearest_int(float v) {
+    const float t = v + 12582912.f;
+    return (__float_as_int(t) & 0x007fffff) - 0x00400000;
+}
+// exact (float)l for a small integer l in [-64, 2^22)
+__device__ __forceinline__ float i2f_small(int l) { return u2f_biased((uint32_t)(l + 64), 64.0f); }
+
+template <int NW> __device__ __forceinline__ void set_code(uint32_t (&w)[NW], int i, int l) { w[i >> 2] |= (uint32_t)(l & 0xFF) << (8 * (i & 3)); }
+template <int NW> __device__ __forceinline__ int get_code(const uint32_t (&w)[NW], int i) { return (int)((w[i >> 2] >> (8 * (i & 3))) & 0xFF); }
+
+// ---- upstream make_qkx2_quants ------------------------------------------------------------------
+template <int N, bool USE_MAD>
+__device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const float (&w)[N], const int nmax, uint32_t (&L)[N / 4],
+                                                  float &the_min, const float rmin, const float rdelta, const int nstep) {
+    float mn = x[0], mx = x[0];
+    float sum_w = w[0];
+    float sum_x = sum_w * x[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) {
+        if (x[i] < mn) mn = x[i];
+        if (x[i] > mx) mx = x[i];
+        sum_w += w[i];
+        sum_x += w[i] * x[i];
+    }
+#pragma unroll
+    for (int k = 0; k < N / 4; k++) L[k] = 0;
+    if (mn > 0) mn = 0;
+    if (mx == mn) {
+        the_min = -mn;
+        return 0.f;
+    }
+    float iscale = (float)nmax / (mx - mn);
+    float scale = 1 / iscale;
+    float best_mad = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        int l = nearest_int(iscale * (x[i] - mn));
+        l = max(0, min(nmax, l));
+        set_code(L, i, l);
+        float diff = scale * i2f_small(l) + mn - x[i];
+        diff = USE_MAD ? fabsf(diff) : diff * diff;
+        best_mad += w[i] * diff;
+    }
+    for (int is = 0; is <= nstep; ++is) {
+        iscale = (rmin + rdelta * (float)is + (float)nmax) / (mx - mn);
+        float sum_l = 0, sum_l2 = 0, sum_xl = 0;
+        uint32_t Laux[N / 4];
+#pragma unroll
+        for (int k = 0; k < N / 4; k++) Laux[k] = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            int l = nearest_int(iscale * (x[i] - mn));
+            l = max(0, min(nmax, l));
+            set_code(Laux, i, l);
+            const float wl = w[i] * i2f_small(l);
+            sum_l += wl;
+            sum_l2 += wl * i2f_small(l);
+            sum_xl += wl * x[i];
+        }
+        const float D = sum_w * sum_l2 - sum_l * sum_l;
+        if (D > 0) {
+            float this_scale = (sum_w * sum_xl - sum_x * sum_l) / D;
+            float this_min = (sum_l2 * sum_x - sum_l * sum_xl) / D;
+            if (this_min > 0) {
+                this_min = 0;
+                this_scale = sum_xl / sum_l2;
+            }
+            float mad = 0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                float diff = this_scale * i2f_small(get_code(Laux, i)) + this_min - x[i];
+                diff = USE_MAD ? fabsf(diff) : diff * diff;
+                mad += w[i] * diff;
+            }
+            if (mad < best_mad) {
+#pragma unroll
+                for (int k = 0; k < N / 4; k++) L[k] = Laux[k];
+                best_mad = mad;
+                scale = this_scale;
+                mn = this_min;
+            }
+        }
+    }
+    the_min = -mn;
+    return scale;
+}
+
+// ---- upstream make_qx_quants(n=16, nmax, rmse_type=1, qw=NULL); codes stored as l + nmax -----------
+__device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const int nmax, uint32_t (&L)[4]) {
+    float mx = 0, amax = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float ax = fabsf(x[i]);
+        if (ax > amax) { amax = ax; mx = x[i]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) L[k] = 0;
+    if (amax < GROUP_MAX_EPS) return 0.f;
+    float iscale = (float)(-nmax) / mx;
+    float sumlx = 0, suml2 = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        int l = nearest_int(iscale * x[i]);
+        l = max(-nmax, min(nmax - 1, l));
+        set_code(L, i, l + nmax);
+        const float w = x[i] * x[i];
+        sumlx += w * x[i] * i2f_small(l);
+        suml2 += w * i2f_small(l) * i2f_small(l);
+    }
+    float scale = suml2 ? sumlx / suml2 : 0.0f;
+    float best = scale * sumlx;
+    for (int is = -9; is <= 9; ++is) {
+        if (is == 0) continue;
+        iscale = -((float)nmax + 0.1f * (float)is) / mx;
+        sumlx = suml2 = 0;
+        uint32_t Laux[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            int l = nearest_int(iscale * x[i]);
+            l = max(-nmax, min(nmax - 1, l));
+            set_code(Laux, i, l + nmax);
+            const float w = x[i] * x[i];
+            sumlx += w * x[i] * i2f_small(l);
+            suml2 += w * i2f_small(l) * i2f_small(l);
+        }
+        if (suml2 > 0 && sumlx * sumlx > best * suml2) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) L[k] = Laux[k];
+            scale = sumlx / suml2;
+            best = scale * sumlx;
+        }
+    }
+    return scale;
+}
+
+// ---- upstream make_q3_quants(n=16, nmax=4, do_rmse=true); codes stored as l + nmax ----------------
+__device__ __forceinline__ float make_q3_quants16(const float (&x)[16], const int nmax, uint32_t (&Lout)[4]) {
+    float mx = 0, amax = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float ax = fabsf(x[i]);
+        if (ax > amax) { amax = ax; mx = x[i]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) Lout[k] = 0;
+    if (amax < GROUP_MAX_EPS) return 0.f;
+    const float iscale = (float)(-nmax) / mx;
+    float sumlx = 0, suml2 = 0;
+    int L[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        int l = nearest_int(iscale * x[i]);
+        l = max(-nmax, min(nmax - 1, l));
+        L[i] = l;
+        const float w = x[i] * x[i];
+        sumlx += w * x[i] * i2f_small(l);
+        suml2 += w * i2f_small(l) * i2f_small(l);
+    }
+    for (int itry = 0; itry < 5; ++itry) {
+        int n_changed = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float w = x[i] * x[i];
+            float slx = sumlx - w * x[i] * i2f_small(L[i]);
+            if (slx > 0) {
+                float sl2 = suml2 - w * i2f_small(L[i]) * i2f_small(L[i]);
+                int new_l = nearest_int(x[i] * sl2 / slx);
+                new_l = max(-nmax, min(nmax - 1, new_l));
+                if (new_l != L[i]) {
+                    slx += w * x[i] * i2f_small(new_l);
+                    sl2 += w * i2f_small(new_l) * i2f_small(new_l);
+                    if (sl2 > 0 && slx * slx * suml2 > sumlx * sumlx * sl2) {
+                        L[i] = new_l;
+                        sumlx = slx;
+                        suml2 = sl2;
+                        ++n_changed;
+                    }
+                }
+            }
+        }
+        if (!n_changed) break;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) set_code(Lout, i, L[i] + nmax);
+    return sumlx / suml2;
+}
+
+// ---- group reductions over the G lanes of one super-block ------------------------------------------
+template <int G> __device__ __forceinline__ float group_max_from_zero(float v) {  // max_x = 0; if (v > max_x) max_x = v
+    float m = v > 0.f ? v : 0.f;
+#pragma unroll
+    for (int s = 1; s < G; s <<= 1) { const float o = __shfl_xor_sync(KFULL, m, s); m = o > m ? o : m; }
+    return m;
+}
+// first value (lowest lane) with strictly greatest |v|, starting from 0
+template <int G> __device__ __forceinline__ float group_max_by_abs(float v, int lane) {
+    float acc = fabsf(v) > 0.f ? v : 0.f;
+#pragma unroll
+    for (int s = 1; s < G; s <<= 1) {
+        const float o = __shfl_xor_sync(KFULL, acc, s);
+        const bool lower = (lane & s) == 0;
+        const float first = lower ? acc : o, second = lower ? o : acc;
+        acc = fabsf(second) > fabsf(first) ? second : first;
+    }
+    return acc;
+}
+
+// ---- per-type quantizers ---------------------------------------------------------------------------
+// Scratch written by the lanes of one super-block, read by the bytewise assembler.
+struct KScratch {
+    uint8_t L[256];   // final codes, one byte per element
+    uint8_t a[16];    // per-sub-block code A (scale)
+    uint8_t b[16];    // per-sub-block code B (min)
+    uint16_t d16, dmin16;
+    uint32_t zero;    // whole block is zero bytes
+};
+
+template <uint32_t T> struct KQuant;
+
+template <int SUB> __device__ __forceinline__ void put_codes(KScratch &s, int j, const uint32_t (&L)[SUB / 4]) {
+#pragma unroll
+    for (int k = 0; k < SUB / 4; k++) *reinterpret_cast<uint32_t *>(&s.L[j * SUB + 4 * k]) = L[k];
+}
+
+// Q4K and Q5K share everything but nmax / search range / final layout.
+template <int NMAX> __device__ __forceinline__ void k45_lane(const float (&x)[32], int j, KScratch &s, float rmin, int nstep) {
+    float sum_x2 = 0;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) sum_x2 += x[l] * x[l];
+    const float av_x = sqrtf(sum_x2 / 32);
+    float w[32];
+#pragma unroll
+    for (int l = 0; l < 32; ++l) w[l] = av_x + fabsf(x[l]);
+    uint32_t L[8];
+    float the_min;
+    const float scale = make_qkx2_quants<32, false>(x, w, NMAX, L, the_min, rmin, 0.1f, nstep);
+    const float max_scale = group_max_from_zero<8>(scale), max_min = group_max_from_zero<8>(the_min);
+    const float inv_scale = max_scale > 0 ? 63.f / max_scale : 0.f;
+    const float inv_min = max_min > 0 ? 63.f / max_min : 0.f;
+    uint32_t ls = (uint32_t)nearest_int(inv_scale * scale) & 0xFFu;
+    uint32_t lm = (uint32_t)nearest_int(inv_min * the_min) & 0xFFu;
+    ls = min(ls, 63u);
+    lm = min(lm, 63u);
+    const uint16_t d16 = f2h(max_scale / 63.f), dmin16 = f2h(max_min / 63.f);
+    const float d = h2f(d16) * (float)ls;
+    if (d != 0.f) {
+        const float dm = h2f(dmin16) * (float)lm;
+#pragma unroll
+        for (int k = 0; k < 8; k++) L[k] = 0;
+#pragma unroll
+        for (int ii = 0; ii < 32; ++ii) {
+            int l = nearest_int((x[ii] + dm) / d);
+            l = max(0, min(NMAX, l));
+            set_code(L, ii, l);
+        }
+    }
+    put_codes<32>(s, j, L);
+    s.a[j] = (uint8_t)ls;
+    s.b[j] = (uint8_t)lm;
+    if (j == 0) { s.d16 = d16; s.dmin16 = dmin16; s.zero = 0; }
+}
+// header bytes 0..15 of Q4K / Q5K: delta, min, 12 bytes of 6-bit scales/mins
+__device__ __forceinline__ uint32_t k45_header_byte(const KScratch &s, int o) {
+    if (o < 2) return (s.d16 >> (8 * o)) & 0xFF;
+    if (o < 4) return (s.dmin16 >> (8 * (o - 2))) & 0xFF;
+    const int k = o - 4;
+    if (k < 4) return s.a[k] | ((s.a[k + 4] >> 4) << 6);
+    if (k < 8) return s.b[k - 4] | ((s.b[k] >> 4) << 6);
+    return (s.a[k - 4] & 0xF) | ((s.b[k - 4] & 0xF) << 4);
+}
+
+template <> struct KQuant<T_Q4K> {
+    static constexpr int SUB = 32;
+    static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s) { k45_lane<15>(x, j, s, -1.f, 20); }
+    static __device__ __forceinline__ uint32_t byte(const KScratch &s, int o) {
+        if (o < 16) return k45_header_byte(s, o);
+        const int t = o - 16, p = t >> 5, l = t & 31;
+        return s.L[64 * p + l] | (s.L[64 * p + 32 + l] << 4);
+    }
+};
+template <> struct KQuant<T_Q5K> {
+    static constexpr int SUB = 32;
+    static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s) { k45_lane<31>(x, j, s, -0.5f, 15); }
+    static __device__ __forceinline__ uint32_t byte(const KScratch &s, int o) {
+        if (o < 16) return k45_header_byte(s, o);
+        if (o < 48) {
+            const int l = o - 16;
+            uint32_t h = 0;
+#pragma unroll
+            for (int p = 0; p < 4; p++) h |= ((s.L[64 * p + l] >> 4) << (2 * p)) | ((s.L[64 * p + 32 + l] >> 4) << (2 * p + 1));
+            return h;
+        }
+        const int t = o - 48, p = t >> 5, l = t & 31;
+        return (s.L[64 * p + l] & 15) | ((s.L[64 * p + 32 + l] & 15) << 4);
+    }
+};
+
+template <> struct KQuant<T_Q6K> {
+    static constexpr int SUB = 16;
+    static __device__ __forceinline__ void lane(const float (&x)[16], int j, int lane_id, KScratch &s) {
+        uint32_t L[4];
+        const float scale = make_qx_quants16(x, 32, L);
+        const float max_scale = group_max_by_abs<16>(scale, lane_id);
+        const bool zero = fabsf(max_scale) < GROUP_MAX_EPS;
+        int sc = 0;
+        uint16_t d16 = 0;
+        if (!zero) {
+            const float iscale = -128.f / max_scale;
+            d16 = f2h(1 / iscale);
+            sc = min(127, nearest_int(iscale * scale));
+            const float d = h2f(d16) * (float)(int)(int8_t)sc;
+            if (d != 0.f) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) L[k] = 0;
+#pragma unroll
+                for (int ii = 0; ii < 16; ++ii) {
+                    int l = nearest_int(x[ii] / d);
+                    l = max(-32, min(31, l));
+                    set_code(L, ii, l + 32);
+                }
+            }
+        }
+        put_codes<16>(s, j, L);
+        s.a[j] = (uint8_t)(int8_t)sc;
+        if (j == 0) { s.d16 = d16; s.dmin16 = 0; s.zero = zero ? 1u : 0u; }
+    }
+    static __device__ __forceinline__ uint32_t byte(const KScratch &s, int o) {
+        if (s.zero) return 0;
+        if (o < 128) {  // ql
+            const int n = o >> 6, r = o & 63, l = r & 31, e = 128 * n + l + (r >= 32 ? 32 : 0);
+            return (s.L[e] & 15) | ((s.L[e + 64] & 15) << 4);
+        }
+        if (o < 192) {  // qh
+            const int t = o - 128, n = t >> 5, l = t & 31, e = 128 * n + l;
+            return (s.L[e] >> 4) | ((s.L[e + 32] >> 4) << 2) | ((s.L[e + 64] >> 4) << 4) | ((s.L[e + 96] >> 4) << 6);
+        }
+        if (o < 208) return s.a[o - 192];
+        return (s.d16 >> (8 * (o - 208))) & 0xFF;
+    }
+};
+
+template <> struct KQuant<T_Q2K> {
+    static constexpr int SUB = 16;
+    static __device__ __forceinline__ void lane(const float (&x)[16], int j, int, KScratch &s) {
+        float w[16];
+#pragma unroll
+        for (int l = 0; l < 16; ++l) w[l] = fabsf(x[l]);
+        uint32_t L[4];
+        float the_min;
+        const float scale = make_qkx2_quants<16, true>(x, w, 3, L, the_min, -0.5f, 0.1f, 15);
+        const float max_scale = group_max_from_zero<16>(scale), max_min = group_max_from_zero<16>(the_min);
+        uint32_t b = 0;
+        uint16_t d16 = 0, dmin16 = 0;
+        if (max_scale > 0) {
+            const float iscale = 15.f / max_scale;
+            b = (uint32_t)nearest_int(iscale * scale) & 0xFFu;
+            d16 = f2h(max_scale / 15.f);
+        }
+        if (max_min > 0) {
+            const float iscale = 15.f / max_min;
+            b |= ((uint32_t)nearest_int(iscale * the_min) << 4) & 0xFFu;
+            dmin16 = f2h(max_min / 15.f);
+        }
+        const float d = h2f(d16) * (float)(b & 0xFu);
+        if (d != 0.f) {
+            const float dm = h2f(dmin16) * (float)(b >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) L[k] = 0;
+#pragma unroll
+            for (int ii = 0; ii < 16; ++ii) {
+                int l = nearest_int((x[ii] + dm) / d);
+                l = max(0, min(3, l));
+                set_code(L, ii, l);
+            }
+        }
+        put_codes<16>(s, j, L);
+        s.a[j] = (uint8_t)b;
+        if (j == 0) { s.d16 = d16; s.dmin16 = dmin16; s.zero = 0; }
+    }
+    static __device__ __forceinline__ uint32_t byte(const KScratch &s, int o) {
+        if (o < 16) return s.a[o];
+        if (o < 80) {
+            const int t = o - 16, n = t >> 5, l = t & 31, e = 128 * n + l;
+            return s.L[e] | (s.L[e + 32] << 2) | (s.L[e + 64] << 4) | (s.L[e + 96] << 6);
+        }
+        if (o < 82) return (s.d16 >> (8 * (o - 80))) & 0xFF;
+        return (s.dmin16 >> (8 * (o - 82))) & 0xFF;
+    }
+};
+
+template <> struct KQuant<T_Q3K> {
+    static constexpr int SUB = 16;
+    static __device__ __forceinline__ void lane(const float (&x)[16], int j, int lane_id, KScratch &s) {
+        uint32_t L[4];
+        const float scale = make_q3_quants16(x, 4, L);
+        const float max_scale = group_max_by_abs<16>(scale, lane_id);
+        int c = 0;
+        uint16_t d16 = 0;
+        if (max_scale != 0.f) {
+            const float iscale = -32.f / max_scale;
+            int l = (int)(int8_t)nearest_int(iscale * scale);
+            c = max(-32, min(31, l)) + 32;
+            d16 = f2h(1 / iscale);
+        }
+        const float d = h2f(d16) * (float)(c - 32);
+        if (d != 0.f) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) L[k] = 0;
+#pragma unroll
+            for (int ii = 0; ii < 16; ++ii) {
+                int l = nearest_int(x[ii] / d);
+                l = max(-4, min(3, l));
+                set_code(L, ii, l + 4);
+            }
+        }
+        put_codes<16>(s, j, L);
+        s.a[j] = (uint8_t)c;
+        if (j == 0) { s.d16 = d16; s.dmin16 = 0; s.zero = 0; }
+    }
+    static __device__ __forceinline__ uint32_t byte(const KScratch &s, int o) {
+        if (o < 32) {  // hmask
+            uint32_t h = 0;
+#pragma unroll
+            for (int bq = 0; bq < 8; bq++) h |= (uint32_t)(s.L[32 * bq + o] > 3) << bq;
+            return h;
+        }
+        if (o < 96) {
+            const int t = o - 32, n = t >> 5, l = t & 31, e = 128 * n + l;
+            return (s.L[e] & 3) | ((s.L[e + 32] & 3) << 2) | ((s.L[e + 64] & 3) << 4) | ((s.L[e + 96] & 3) << 6);
+        }
+        if (o < 108) {
+            const int k = o - 96;
+            if (k < 8) return (s.a[k] & 0xF) | ((s.a[k + 8] & 0xF) << 4);
+            const int r = k - 8;
+            return (s.a[r] >> 4) | ((s.a[r + 4] >> 4) << 2) | ((s.a[r + 8] >> 4) << 4) | ((s.a[r + 12] >> 4) << 6);
+        }
+        return (s.d16 >> (8 * (o - 108))) & 0xFF;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+template <uint32_t T, class FT>
+__global__ void __launch_bounds__(KQ_THREADS, 4)
+quant_k_kernel(const typename FT::raw *__restrict__ src, uint8_t *__restrict__ dst, size_t nblocks) {
+    using KQ = KQuant<T>;
+    constexpr int SUB = KQ::SUB, NSUB = 256 / SUB, SBW = 32 / NSUB;  // super-blocks per warp pass
+    constexpr int BYTES = BlockTraits<T>::BYTES;
+    constexpr int OUT_BYTES = (SBW * BYTES + 15) & ~15;
+
+    __shared__ float xs[KQ_WARPS][32][SUB + 1];
+    __shared__ KScratch scratch[KQ_WARPS][SBW];
+    __shared__ __align__(16) uint8_t outb[KQ_WARPS][OUT_BYTES];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sbi = lane / NSUB, j = lane % NSUB;
+    const size_t ngroups = (nblocks + SBW - 1) / SBW;
+    const bool vec_in = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+
+    for (size_t g = (size_t)blockIdx.x * KQ_WARPS + warp; g < ngroups; g += (size_t)gridDim.x * KQ_WARPS) {
+        const size_t sb0 = g * SBW;
+        const int nsb = (int)min((size_t)SBW, nblocks - sb0);
+        const typename FT::raw *in = src + sb0 * 256;
+        // cooperative coalesced load of SBW*256 elements -> xs[row = sub-block][col]
+#pragma unroll
+        for (int it = 0; it < SBW * 256 / (32 * 8); it++) {
+            const int e0 = (it * 32 + lane) * 8;
+            float v[8];
+            if (e0 / 256 < nsb) {
+                load8<FT>(in + e0, v, vec_in);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = 0.f;
+            }
+            const int row = e0 / SUB, col = e0 % SUB;
+#pragma unroll
+            for (int k = 0; k < 8; k++) xs[warp][row][col + k] = v[k];
+        }
+        __syncwarp();
+        float x[SUB];
+#pragma unroll
+        for (int i = 0; i < SUB; i++) x[i] = xs[warp][lane][i];
+        KQ::lane(x, j, lane, scratch[warp][sbi]);
+        __syncwarp();
+        for (int o = lane; o < nsb * BYTES; o += 32) outb[warp][o] = (uint8_t)KQ::byte(scratch[warp][o / BYTES], o % BYTES);
+        __syncwarp();
+        cta_copy_s2g(dst + sb0 * BYTES, outb[warp], (uint32_t)(nsb * BYTES), lane, 32);
+        __syncwarp();
+    }
+}
+
+template <uint32_t T, class FT>
+static cudaError_t launch_quant_k(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
+    constexpr int SBW = 32 / (256 / KQuant<T>::SUB);
+    auto kern = quant_k_kernel<T, FT>;
+    static int occ_cache[MAX_DEVICES];
+    int ctas_per_sm = 0;
+    cudaError_t e = cached_occupancy(kern, KQ_THREADS, 0, dev.device, occ_cache, &ctas_per_sm);
+    if (e != cudaSuccess) return e;
+    const size_t ngroups = (nblocks + SBW - 1) / SBW;
+    const size_t want = (ngroups + KQ_WARPS - 1) / KQ_WARPS;
+    size_t grid = (size_t)dev.sm_count * ctas_per_sm;
+    if (grid > want) grid = want;
+    kern<<<(unsigned)grid, KQ_THREADS, 0, stream>>>(static_cast<const typename FT::raw *>(src), static_cast<uint8_t *>(dst), nblocks);
+    return cudaGetLastError();
+}
+template <uint32_t T>
+static cudaError_t launch_quant_k_fdt(uint32_t fdt, const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
+    switch (fdt) {
+        case T_F32: return launch_quant_k<T, F32>(src, dst, nblocks, stream, dev);
+        case T_F16: return launch_quant_k<T, F16>(src, dst, nblocks, stream, dev);
+        case T_BF16: return launch_quant_k<T, BF16>(src, dst, nblocks, stream, dev);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t quant_blocks_k(uint32_t type, uint32_t fdt, const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
+    if (nblocks == 0) return cudaSuccess;
+    switch (type) {
+        case T_Q2K: return launch_quant_k_fdt<T_Q2K>(fdt, src, dst, nblocks, stream, dev);
+        case T_Q3K: return launch_quant_k_fdt<T_Q3K>(fdt, src, dst, nblocks, stream, dev);
+        case T_Q4K: return launch_quant_k_fdt<T_Q4K>(fdt, src, dst, nblocks, stream, dev);
+        case T_Q5K: return launch_quant_k_fdt<T_Q5K>(fdt, src, dst, nblocks, stream, dev);
+        case T_Q6K: return launch_quant_k_fdt<T_Q6K>(fdt, src, dst, nblocks, stream, dev);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace ggq

@@ -1,0 +1,112 @@
+/*
+ * ggq.h — C ABI of libggq.so: the B200-native (sm_100a) ggml block quantize / dequantize path.
+ *
+ * This is the drop-in boundary for the reference's `ggml-quants` slice API.  Each entry point
+ * cites the reference interface it replaces (paths under /root/reference/).  Plain pointers and
+ * sizes only; no torch / C++ types.  The Rust-side binding a maintainer would add is shown in
+ * INTEGRATION.md.
+ *
+ * Semantics common to every call
+ *   - `type` is a GGmlType discriminant (ggus/src/tensor.rs:15-50): the packed/block side.
+ *   - `fdt` is the float-side element type T of `Quantize<T, N>` (ggml-quants/src/lib.rs:53-90):
+ *     GGQ_F32, GGQ_F16 or GGQ_BF16.
+ *   - Lengths are in the units of the reference slices: `[Blk]` lengths in blocks, `[T]` lengths in
+ *     elements.  The check ORDER is the reference's (lib.rs:122-127, 136-141): divisibility first
+ *     -> GGQ_ERR_INDIVISIBLE, then length equality -> GGQ_ERR_LENGTH_MISMATCH.
+ *   - Results are bit-identical to the reference's per-block functions (see DESIGN.md "Parity").
+ *   - There is NO CPU fallback: without a CUDA device every compute call returns GGQ_ERR_CUDA.
+ *   - All entry points are thread-safe and re-entrant (the reference is entered concurrently from
+ *     one writer thread per output shard, xtask/src/utils/write.rs:64-99).
+ */
+#ifndef GGQ_H
+#define GGQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* GGmlType discriminants — ggus/src/tensor.rs:15-50 (only the types with a codec here) */
+enum ggq_type {
+    GGQ_F32 = 0,
+    GGQ_F16 = 1,   /* 1-element "block": structs/half.rs:8-22  */
+    GGQ_Q4_0 = 2,  /* structs/q4_0.rs  18 B / 32 */
+    GGQ_Q4_1 = 3,  /* structs/q4_1.rs  20 B / 32 */
+    GGQ_Q5_0 = 6,  /* structs/q5_0.rs  22 B / 32 */
+    GGQ_Q5_1 = 7,  /* structs/q5_1.rs  24 B / 32 */
+    GGQ_Q8_0 = 8,  /* structs/q8_0.rs  34 B / 32 */
+    GGQ_Q8_1 = 9,  /* structs/q8_1.rs  36 B / 32 */
+    GGQ_Q2K = 10,  /* structs/q2_k.rs  84 B / 256 */
+    GGQ_Q3K = 11,  /* structs/q3_k.rs 110 B / 256 */
+    GGQ_Q4K = 12,  /* structs/q4_k.rs 144 B / 256 */
+    GGQ_Q5K = 13,  /* structs/q5_k.rs 176 B / 256 */
+    GGQ_Q6K = 14,  /* structs/q6_k.rs 210 B / 256 */
+    GGQ_Q8K = 15,  /* structs/q8_k.rs 290 B / 256 (reference layout: f16 delta) */
+    GGQ_BF16 = 30  /* 1-element "block": structs/half.rs:24-38 */
+};
+
+/* Return codes.  1 and 2 are `QuantizeError::{Indivisible, LengthMismatch}` (lib.rs:107-113). */
+enum ggq_status {
+    GGQ_OK = 0,
+    GGQ_ERR_INDIVISIBLE = 1,
+    GGQ_ERR_LENGTH_MISMATCH = 2,
+    GGQ_ERR_UNSUPPORTED = -1, /* unknown type / fdt */
+    GGQ_ERR_CUDA = -2,        /* CUDA runtime failure or no device; see ggq_last_error() */
+    GGQ_ERR_INVALID = -3      /* null pointer with non-zero length, bad device index, ... */
+};
+
+/* `DataBlock::COUNT` and `size_of::<Blk>()` (lib.rs:11-21; ggus/src/tensor.rs:74-79). */
+int ggq_block_info(uint32_t type, uint32_t *elems, uint32_t *bytes);
+
+/* Human-readable description of the calling thread's last non-OK return. */
+const char *ggq_last_error(void);
+
+/* Number of CUDA devices visible (0 when none); and the device the calling thread's *_slice
+ * calls run on (default: the current CUDA device of the thread). */
+int ggq_device_count(void);
+int ggq_set_device(int device);
+
+/* ---- host-pointer slice API (the drop-in) ------------------------------------------------- */
+
+/* `QuantExt::<T, N>::quantize_slice(dst: &mut [Blk], src: &[T])` — lib.rs:121-133; called from
+ * xtask/src/utils/operator/cast.rs:140-148.  Host pointers, synchronous: on return every byte of
+ * dst[0 .. dst_blocks*block_bytes) has been written.  Pageable or pinned memory accepted; only
+ * the Rust alignment (align_of::<T>/<Blk>, i.e. 2 or 4) is assumed. */
+int ggq_quantize_slice(uint32_t type, uint32_t fdt, void *dst, size_t dst_blocks,
+                       const void *src, size_t src_elems);
+
+/* `QuantExt::<T, N>::dequantize_slice(dst: &mut [T], src: &[Blk])` — lib.rs:135-147; called from
+ * cast.rs:150-156. */
+int ggq_dequantize_slice(uint32_t type, uint32_t fdt, void *dst, size_t dst_elems,
+                         const void *src, size_t src_blocks);
+
+/* ---- device-pointer slice API (device-resident chains, pipelining, kernel timing) ---------- */
+
+/* Same contracts, but `dst`/`src` are device pointers on the current device and the work is
+ * enqueued on `stream` (a cudaStream_t; NULL = legacy default stream) without synchronising.
+ * Pointers need only the Rust alignment; 16-byte aligned buffers take the fast (TMA) path. */
+int ggq_quantize_slice_device(uint32_t type, uint32_t fdt, void *dst, size_t dst_blocks,
+                              const void *src, size_t src_elems, void *stream);
+int ggq_dequantize_slice_device(uint32_t type, uint32_t fdt, void *dst, size_t dst_elems,
+                                const void *src, size_t src_blocks, void *stream);
+
+/* ---- memory helpers ------------------------------------------------------------------------ */
+
+/* Page-locked host memory (stands in for cast.rs:158-161 `MmapMut::map_anon` when the caller
+ * wants DMA-able buffers).  The host slice API detects pinned pointers and skips its bounce
+ * buffers for them. */
+void *ggq_host_alloc(size_t bytes);
+void ggq_host_free(void *p);
+
+/* Number of kernel launches issued by this library since load (all threads); for harnesses. */
+uint64_t ggq_launch_count(void);
+
+/* Library version string, e.g. "ggq-b200 0.1 (sm_100a)". */
+const char *ggq_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGQ_H */

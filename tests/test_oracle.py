@@ -1,0 +1,108 @@
+"""CPU tests: pin the oracle (oracle/ggq_oracle.c) against vectors that do not come from it."""
+import os
+
+import numpy as np
+import pytest
+
+from data import edge_blocks, gaussian, to_fdt
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+LEGACY = {"q4_0": 2, "q4_1": 3, "q5_0": 6, "q5_1": 7, "q8_0": 8}
+
+
+def test_readme_block_known_answers(oracle):
+    """ggml-quants/README.md:32-37 example block -> exact packed bytes."""
+    k = np.load(os.path.join(G, "readme_block.npz"))
+    for name, ty in [("q8_0", 8), ("q4_0", 2), ("q4_1", 3), ("q5_0", 6), ("q8_1", 9)]:
+        assert oracle.quantize(ty, oracle.F32, k["x"]).tobytes() == k[name].tobytes(), name
+
+
+@pytest.mark.parametrize("name", sorted(LEGACY))
+def test_legacy_matches_gguf_py_golden(oracle, name):
+    g = np.load(os.path.join(G, "gguf_py_legacy.npz"))
+    ty = LEGACY[name]
+    q = oracle.quantize(ty, oracle.F32, g["x"])
+    assert np.array_equal(q, g[name])
+    d = oracle.dequantize(ty, oracle.F32, g[name])
+    assert np.array_equal(d.view(np.uint32), g[name + "_deq"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name,ty", [("q2k", 10), ("q3k", 11), ("q4k", 12), ("q5k", 13), ("q6k", 14)])
+def test_kquant_dequant_matches_gguf_py_golden(oracle, name, ty):
+    g = np.load(os.path.join(G, "gguf_py_kdequant.npz"))
+    d = oracle.dequantize(ty, oracle.F32, g[name])
+    assert np.array_equal(d.view(np.uint32), g[name + "_deq"].view(np.uint32))
+
+
+def test_live_gguf_py_crosscheck(oracle):
+    """Same cross-check on fresh seeds when gguf-py is importable (it is in this image)."""
+    gq = pytest.importorskip("gguf.quants")
+    from gguf import GGMLQuantizationType as T
+    x = np.concatenate([gaussian(32 * 500, 11, s) for s in (1e-3, 0.02, 5.0)])
+    for ty, gt in [(2, T.Q4_0), (3, T.Q4_1), (6, T.Q5_0), (7, T.Q5_1), (8, T.Q8_0)]:
+        assert np.array_equal(oracle.quantize(ty, 0, x), gq.quantize(x.reshape(-1, 32), gt).reshape(-1))
+
+
+def test_zero_block_is_all_zero_bytes(oracle):
+    """the reference returns Self::ZEROS (diverges from ggml)."""
+    for ty in (2, 3, 6, 7, 8, 9, 15):
+        n, b = oracle.block_info(ty)
+        assert not oracle.quantize(ty, 0, np.zeros(n, np.float32)).any()
+    # dequantising a zero Q4_0 block gives -0.0 (sign bit set): (0 - 8) * +0.0
+    y = oracle.dequantize(2, 0, np.zeros(18, np.uint8))
+    assert (y.view(np.uint32) == 0x80000000).all()
+
+
+def test_error_order(oracle):
+    """lib.rs:293-331 known answers."""
+    assert oracle.quantize_rc(8, 0, 1, 31) == oracle.INDIVISIBLE
+    assert oracle.quantize_rc(8, 0, 3, 64) == oracle.LENGTH_MISMATCH
+    assert oracle.dequantize_rc(8, 0, 31, 1) == oracle.INDIVISIBLE
+    assert oracle.dequantize_rc(8, 0, 64, 3) == oracle.LENGTH_MISMATCH
+    assert oracle.quantize_rc(8, 0, 2, 64) == oracle.OK
+
+
+@pytest.mark.parametrize("ty,tol", [(1, 4e-3), (30, 8e-3), (2, 8e-2), (3, 4e-2), (6, 4e-2), (7, 2e-2), (8, 4.5e-3), (9, 4.5e-3), (15, 4.5e-3)])
+def test_reference_tolerances(oracle, ty, tol):
+    """the reference's own round-trip thresholds on [0,1) inputs."""
+    n, _ = oracle.block_info(ty)
+    x = np.random.default_rng(ty).random(n * 64, dtype=np.float32)
+    y = oracle.dequantize(ty, 0, oracle.quantize(ty, 0, x))
+    assert np.abs(x - y).max() <= tol
+
+
+@pytest.mark.parametrize("ty,rel", [(10, 0.35), (11, 0.2), (12, 0.09), (13, 0.05), (14, 0.025)])
+def test_kquant_roundtrip_quality(oracle, ty, rel):
+    """K-quant quantize is unpinned by the reference; sanity: rmse/sigma in the range upstream ggml shows."""
+    x = gaussian(256 * 200, 5)
+    y = oracle.dequantize(ty, 0, oracle.quantize(ty, 0, x))
+    assert np.sqrt(np.mean((x - y) ** 2)) / 0.02 < rel
+
+
+def test_half_conversions_exhaustive(oracle):
+    """f16 -> f32 -> f16 is the identity on every non-NaN pattern and matches numpy on a float sweep."""
+    L = oracle.lib()
+    allh = np.arange(65536, dtype=np.uint16)
+    wide = oracle.dequantize(1, 0, allh.view(np.uint8))
+    back = oracle.quantize(1, 0, wide).view(np.uint16)
+    nan = (allh & 0x7FFF) > 0x7C00
+    assert np.array_equal(back[~nan], allh[~nan])
+    assert np.array_equal(wide[~nan].view(np.uint32), allh[~nan].view(np.float16).astype(np.float32).view(np.uint32))
+    assert np.array_equal(back[nan], allh[nan] | 0x0200)  # quieted, payload kept
+    x = (np.random.default_rng(1).standard_normal(200000) * 10.0 ** np.random.default_rng(2).integers(-9, 6, 200000)).astype(np.float32)
+    with np.errstate(over="ignore"):
+        assert np.array_equal(oracle.quantize(1, 0, x).view(np.uint16), x.astype(np.float16).view(np.uint16))
+    assert L.ggo_f32_to_bf16(1.0) == 0x3F80 and L.ggo_f32_to_bf16(np.float32(1.00390625)) == 0x3F80  # tie -> even
+
+
+def test_threaded_driver_is_deterministic(oracle):
+    x = to_fdt(gaussian(32 * 4096, 3), 1)
+    assert np.array_equal(oracle.quantize(8, 1, x, threads=1), oracle.quantize(8, 1, x, threads=7))
+
+
+def test_edge_blocks_do_not_crash(oracle):
+    for ty in (2, 3, 6, 7, 8, 9, 15, 10, 11, 12, 13, 14):
+        n, _ = oracle.block_info(ty)
+        x = edge_blocks(n)
+        q = oracle.quantize(ty, 0, x)
+        oracle.dequantize(ty, 0, q)

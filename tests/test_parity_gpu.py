@@ -1,0 +1,213 @@
+"""GPU parity tests: every call goes through the C ABI (libggq.so) and is compared, bit for bit,
+with the CPU oracle on the same seeded inputs.  NaNs produced by arithmetic compare as NaN ~ NaN
+(their payload is platform-defined in the reference too)."""
+import threading
+
+import numpy as np
+import pytest
+
+from data import (BF16, F16, F32, edge_blocks, gaussian, random_packed, same_blocks, same_floats, to_fdt)
+
+pytestmark = pytest.mark.gpu
+
+LEGACY = [2, 3, 6, 7, 8, 9]
+KQ = [10, 11, 12, 13, 14]
+ALLQ = LEGACY + [15] + KQ
+FDTS = [F32, F16, BF16]
+
+
+def _inputs(n_elems_block, seed):
+    """Gaussian + heavy-tailed + edge-case blocks, a ragged (non multiple-of-tile) count."""
+    nb = 1200 if n_elems_block == 32 else 150
+    rng = np.random.default_rng(seed)
+    x = np.concatenate([
+        gaussian(n_elems_block * nb, seed),
+        (rng.standard_t(3, n_elems_block * 37) * 0.02).astype(np.float32),
+        rng.random(n_elems_block * 13, dtype=np.float32),
+        edge_blocks(n_elems_block),
+    ])
+    return x
+
+
+@pytest.mark.parametrize("fdt", FDTS)
+@pytest.mark.parametrize("ty", ALLQ)
+def test_quantize_bit_exact(ggq, oracle, ty, fdt):
+    n, b = oracle.block_info(ty)
+    src = to_fdt(_inputs(n, 100 + ty), fdt)
+    got = ggq.quantize(ty, src, fdt)
+    want = oracle.quantize(ty, fdt, src, threads=8)
+    assert same_blocks(got, want, ty, b)
+
+
+@pytest.mark.parametrize("fdt", FDTS)
+@pytest.mark.parametrize("ty", ALLQ)
+@pytest.mark.parametrize("wild", [False, True])
+def test_dequantize_bit_exact(ggq, oracle, ty, fdt, wild):
+    n, b = oracle.block_info(ty)
+    nb = 2051 if n == 32 else 259  # ragged: not a multiple of the tile or of 8 blocks
+    blocks = random_packed(ty, nb, b, 200 + ty, wild=wild)
+    got = ggq.dequantize(ty, blocks, fdt)
+    want = oracle.dequantize(ty, fdt, blocks, threads=8)
+    assert same_floats(got, want)
+
+
+@pytest.mark.parametrize("ty", ALLQ)
+def test_dequantize_of_quantized_realistic(ggq, oracle, ty):
+    """Packed inputs with realistic scales (oracle-quantised Gaussians), f16 output."""
+    n, b = oracle.block_info(ty)
+    blocks = oracle.quantize(ty, F32, gaussian(n * (4096 if n == 32 else 512), 300 + ty), threads=8)
+    assert same_floats(ggq.dequantize(ty, blocks, F16), oracle.dequantize(ty, F16, blocks, threads=8))
+
+
+@pytest.mark.parametrize("src_dt,dst_dt", [(a, b) for a in FDTS for b in FDTS])
+def test_casts_bit_exact_including_nan_payloads(ggq, oracle, src_dt, dst_dt):
+    """f16/bf16 as 1-element blocks (structs/half.rs): every cast is mediated by f32, NaNs quieted."""
+    if src_dt == F32:
+        bits = np.random.default_rng(5).integers(0, 2**32, 300001, dtype=np.uint32)
+        bits[:5] = [0x7F800001, 0xFFC12345, 0x7F800000, 0x00000001, 0x80000000]
+        src = bits.view(np.float32)
+    else:
+        src = np.concatenate([np.arange(65536, dtype=np.uint16), np.random.default_rng(6).integers(0, 65536, 7, dtype=np.uint16)])
+    if dst_dt == F32:  # "dequantize::<src, f32, 1>"
+        if src_dt == F32:
+            pytest.skip("f32 is not a block type")
+        got = ggq.dequantize(src_dt, src.view(np.uint8), F32)
+        want = oracle.dequantize(src_dt, F32, src.view(np.uint8))
+    else:              # "quantize::<dst, src, 1>"
+        got = ggq.quantize(dst_dt, src, src_dt).view(np.uint16)
+        want = oracle.quantize(dst_dt, src_dt, src).view(np.uint16)
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
+def test_readme_block(ggq):
+    import os
+    k = np.load(os.path.join(os.path.dirname(__file__), "golden", "readme_block.npz"))
+    for name, ty in [("q8_0", 8), ("q4_0", 2), ("q4_1", 3), ("q5_0", 6), ("q8_1", 9)]:
+        assert ggq.quantize(ty, k["x"]).tobytes() == k[name].tobytes(), name
+
+
+def test_golden_gguf_py(ggq):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gguf_py_legacy.npz"))
+    for name, ty in [("q4_0", 2), ("q4_1", 3), ("q5_0", 6), ("q5_1", 7), ("q8_0", 8)]:
+        assert np.array_equal(ggq.quantize(ty, g["x"]), g[name]), name
+        assert np.array_equal(ggq.dequantize(ty, g[name]).view(np.uint32), g[name + "_deq"].view(np.uint32)), name
+    k = np.load(os.path.join(os.path.dirname(__file__), "golden", "gguf_py_kdequant.npz"))
+    for name, ty in [("q2k", 10), ("q3k", 11), ("q4k", 12), ("q5k", 13), ("q6k", 14)]:
+        assert np.array_equal(ggq.dequantize(ty, k[name]).view(np.uint32), k[name + "_deq"].view(np.uint32)), name
+
+
+def test_zero_blocks_and_negative_zero(ggq):
+    for ty in (2, 3, 6, 7, 8, 9, 15):
+        n, b = ggq.block_info(ty)
+        assert not ggq.quantize(ty, np.zeros(n * 3, np.float32)).any()
+    assert (ggq.dequantize(2, np.zeros(18 * 5, np.uint8)).view(np.uint32) == 0x80000000).all()
+    assert (ggq.dequantize(6, np.zeros(22 * 5, np.uint8), F16) == 0x8000).all()
+
+
+@pytest.mark.parametrize("ty", [2, 8, 12, 14, 15])
+def test_single_block_and_tiny_sizes(ggq, oracle, ty):
+    n, b = oracle.block_info(ty)
+    for nb in (1, 2, 7, 9):
+        x = gaussian(n * nb, 400 + nb)
+        q = ggq.quantize(ty, x)
+        assert same_blocks(q, oracle.quantize(ty, F32, x), ty, b)
+        assert same_floats(ggq.dequantize(ty, q, F16), oracle.dequantize(ty, F16, q))
+
+
+def test_multi_chunk_host_pipeline_pageable_and_pinned(ggq, oracle):
+    """> 2 chunks of 8 Mi elements through the H2D/kernel/D2H ring, pageable and pinned buffers."""
+    n = (1 << 23) * 2 + 32 * 12345
+    x = to_fdt(gaussian(n, 9), F16)
+    want = oracle.quantize(8, F16, x, threads=8)
+    assert np.array_equal(ggq.quantize(8, x, F16), want)
+    pin_in, pin_out = ggq.PinnedBuffer(x.nbytes), ggq.PinnedBuffer(want.nbytes)
+    pin_in.view(np.uint16)[:] = x
+    ggq.quantize_slice(8, pin_out.array, pin_in.view(np.uint16), F16)
+    assert np.array_equal(pin_out.array, want)
+    # and back: Q8_0 -> f16 over the same ring
+    back = oracle.dequantize(8, F16, want, threads=8)
+    pin_f = ggq.PinnedBuffer(back.nbytes)
+    ggq.dequantize_slice(8, pin_f.view(np.uint16), pin_out.array, F16)
+    assert np.array_equal(pin_f.view(np.uint16), back)
+    assert np.array_equal(ggq.dequantize(8, want, F16), back)
+
+
+def test_concurrent_callers(ggq, oracle):
+    """The reference is entered from one writer thread per shard (xtask/src/utils/write.rs:64-99)."""
+    xs = [to_fdt(gaussian(32 * 50000 + 32 * i, 20 + i), F16) for i in range(6)]
+    types = [2, 3, 6, 7, 8, 9]
+    out = [None] * 6
+
+    def work(i):
+        out[i] = ggq.quantize(types[i], xs[i], F16)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(6):
+        assert np.array_equal(out[i], oracle.quantize(types[i], F16, xs[i], threads=4))
+
+
+@pytest.mark.parametrize("ty", [2, 8, 12, 14])
+def test_device_api_alignment_independence(ggq, oracle, ty):
+    """Device pointers at odd 2-byte offsets take the byte-exact paths; results must not change."""
+    import torch
+    n, b = oracle.block_info(ty)
+    nb = 777
+    x = to_fdt(gaussian(n * nb, 50 + ty), F16)
+    want_q = oracle.quantize(ty, F16, x, threads=4)
+    want_d = oracle.dequantize(ty, F16, want_q, threads=4)
+    for off_in, off_out in [(0, 0), (2, 0), (0, 2), (6, 10)]:
+        src = torch.zeros(x.nbytes + 64, dtype=torch.uint8, device="cuda")
+        src[off_in:off_in + x.nbytes] = torch.from_numpy(x.view(np.uint8)).cuda()
+        dst = torch.zeros(want_q.nbytes + 64, dtype=torch.uint8, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        ggq.quantize_slice_device(ty, F16, dst.data_ptr() + off_out, nb, src.data_ptr() + off_in, n * nb, st)
+        torch.cuda.synchronize()
+        got = dst.cpu().numpy()
+        assert same_blocks(got[off_out:off_out + want_q.nbytes], want_q, ty, b)
+        assert not got[:off_out].any() and not got[off_out + want_q.nbytes:].any()  # no stray writes
+        # dequantize from the misaligned packed buffer into a misaligned float buffer
+        fl = torch.zeros(want_d.nbytes + 64, dtype=torch.uint8, device="cuda")
+        ggq.dequantize_slice_device(ty, F16, fl.data_ptr() + off_in, n * nb, dst.data_ptr() + off_out, nb, st)
+        torch.cuda.synchronize()
+        gf = fl.cpu().numpy()
+        assert np.array_equal(gf[off_in:off_in + want_d.nbytes].view(np.uint16), want_d)
+        assert not gf[:off_in].any() and not gf[off_in + want_d.nbytes:].any()
+
+
+def test_full_size_properties(ggq):
+    """BASELINE.json config 2 size (4096x14336): properties that need no oracle pass.
+    (i) determinism across two runs, (ii) Q8_0 quantize -> dequantize -> quantize is a fixed point
+    on the codes, (iii) block independence: a shuffled block order gives the shuffled result."""
+    n = 4096 * 14336
+    x = to_fdt(gaussian(n, 77), F16)
+    q1 = ggq.quantize(8, x, F16)
+    q2 = ggq.quantize(8, x, F16)
+    assert np.array_equal(q1, q2)
+    y = ggq.dequantize(8, q1, F16)
+    q3 = ggq.quantize(8, y, F16)
+    assert np.array_equal(q3.reshape(-1, 34)[:, 2:], q1.reshape(-1, 34)[:, 2:])
+    perm = np.random.default_rng(1).permutation(n // 32)
+    qp = ggq.quantize(8, np.ascontiguousarray(x.reshape(-1, 32)[perm]).reshape(-1), F16)
+    assert np.array_equal(qp.reshape(-1, 34), q1.reshape(-1, 34)[perm])
+    # every K / legacy decoder at the same size: deterministic and finite
+    for ty in (2, 12, 14):
+        nn, b = ggq.block_info(ty)
+        blk = random_packed(ty, n // nn, b, ty)
+        a = ggq.dequantize(ty, blk, F16)
+        assert np.array_equal(a, ggq.dequantize(ty, blk, F16))
+        assert ((a & 0x7C00) != 0x7C00).all()
+
+
+@pytest.mark.parametrize("ty", [12, 14])
+def test_kquant_full_tensor_sample_vs_oracle(ggq, oracle, ty):
+    """4096x4096 F16 -> Q4K / Q6K on the GPU; a strided sample of super-blocks is re-quantised by the oracle."""
+    n = 4096 * 4096
+    x = to_fdt(gaussian(n, 88), F16)
+    q = ggq.quantize(ty, x, F16)
+    _, b = oracle.block_info(ty)
+    idx = np.arange(0, n // 256, 97)
+    xs = np.ascontiguousarray(x.reshape(-1, 256)[idx]).reshape(-1)
+    assert same_blocks(q.reshape(-1, b)[idx].reshape(-1), oracle.quantize(ty, F16, xs, threads=8), ty, b)
