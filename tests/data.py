@@ -30,8 +30,13 @@ def gaussian(n, seed, sigma=0.02):
     return (np.random.default_rng(seed).standard_normal(n) * sigma).astype(np.float32)
 
 
-def edge_blocks(block):
-    """A battery of nasty `block`-element inputs (f32): zeros, ties, NaN/inf, denormals, signed zeros."""
+def edge_blocks(block, kquant_domain=False):
+    """A battery of nasty `block`-element inputs (f32): zeros, ties, NaN/inf, denormals, signed zeros.
+
+    `kquant_domain=True` keeps only rows inside upstream ggml's K-quant domain: finite values whose
+    scale search never divides to inf/NaN (its `nearest_int` asserts |v| <= 4194303; NaN bits that
+    reach it are platform-defined, so there is nothing to be bit-exact with).  The legacy quantizers
+    are total functions in the reference and take every row."""
     rng = np.random.default_rng(7)
     rows = []
     z = np.zeros(block, np.float32)
@@ -60,6 +65,13 @@ def edge_blocks(block):
     rows.append(np.linspace(-1, 1, block, dtype=np.float32))                           # exact .5 rounding cases
     rows.append((np.arange(block, dtype=np.float32) - block / 2) * np.float32(0.5))
     rows.append(np.arange(1, block + 1, dtype=np.float32) * np.float32(0.1))
+    if kquant_domain:
+        keep = []
+        for r in rows:
+            nz = np.abs(r[r != 0]) if np.isfinite(r).all() else None
+            if nz is not None and (nz.size == 0 or (nz.min() > 1e-30 and nz.max() < 1e4)):
+                keep.append(r)
+        rows = keep
     return np.concatenate(rows)
 
 

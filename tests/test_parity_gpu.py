@@ -16,7 +16,7 @@ ALLQ = LEGACY + [15] + KQ
 FDTS = [F32, F16, BF16]
 
 
-def _inputs(n_elems_block, seed):
+def _inputs(n_elems_block, seed, kquant=False):
     """Gaussian + heavy-tailed + edge-case blocks, a ragged (non multiple-of-tile) count."""
     nb = 1200 if n_elems_block == 32 else 150
     rng = np.random.default_rng(seed)
@@ -24,7 +24,7 @@ def _inputs(n_elems_block, seed):
         gaussian(n_elems_block * nb, seed),
         (rng.standard_t(3, n_elems_block * 37) * 0.02).astype(np.float32),
         rng.random(n_elems_block * 13, dtype=np.float32),
-        edge_blocks(n_elems_block),
+        edge_blocks(n_elems_block, kquant_domain=kquant),
     ])
     return x
 
@@ -33,7 +33,7 @@ def _inputs(n_elems_block, seed):
 @pytest.mark.parametrize("ty", ALLQ)
 def test_quantize_bit_exact(ggq, oracle, ty, fdt):
     n, b = oracle.block_info(ty)
-    src = to_fdt(_inputs(n, 100 + ty), fdt)
+    src = to_fdt(_inputs(n, 100 + ty, kquant=ty in KQ), fdt)
     got = ggq.quantize(ty, src, fdt)
     want = oracle.quantize(ty, fdt, src, threads=8)
     assert same_blocks(got, want, ty, b)
