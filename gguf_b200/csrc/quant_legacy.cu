@@ -1,17 +1,19 @@
 // quant_legacy.cu — f32 / f16 / bf16 -> Q4_0 Q4_1 Q5_0 Q5_1 Q8_0 Q8_1 (32-element blocks) and Q8K
-// (256-element block, reference layout), sm_100a.  Compiled with -fmad=false: the reference's Rust
-// never fuses `x * recip + 8.5`, so neither may this file.
+// (256-element block, reference layout), plus the f32/f16/bf16 element casts; sm_100a.
+// Compiled with -fmad=false: the reference's Rust never fuses `x * recip + 8.5`, so neither may this.
 //
 // Replaces the per-block `Quantize::quantize` bodies behind `QuantExt::quantize_slice`
 // (/root/reference/ggml-quants/src/lib.rs:121-133; per-type bodies cited at each encoder).
 //
-// Shape of the kernel (HBM-bound, input-dominated):
-//   * each thread owns 8 consecutive input elements (one 16-byte load for f16/bf16, two for f32) of
-//     QROWS independent rows, all loads issued before any use;
-//   * 4 lanes own a 32-element block (32 lanes own a Q8K super-block); the per-block folds of
-//     structs.rs:91-107 become xor-shuffle reductions whose tie-break is "lowest index wins", which
-//     is exactly what the reference's left-to-right strict-compare folds produce;
-//   * delta / recip are computed redundantly per lane with IEEE div.rn (identical bits in every lane);
+// Shape of the kernel (input-dominated stream; the first version with 4 lanes per block spent ~21
+// instructions per element on shuffles / redundant divides and was issue-bound at 38 % of HBM peak):
+//   * ONE THREAD PER 32-ELEMENT ROW (a legacy block, or 1/8 of a Q8K super-block): the folds of
+//     structs.rs:91-107 are register-local, delta/recip cost two divides per 32 elements;
+//   * rows are staged global -> shared with 16-byte cp.async (coalesced, no registers), into rows
+//     padded by 16 bytes so that every thread's LDS.128 of its own row is bank-conflict free,
+//     QS stages deep;
+//   * f16 input folds with packed HMNMX2; codes are produced with full-rate float ops (clamp, then a
+//     round-toward-zero add of 2^23 leaves floor(v) in the mantissa) instead of F2I on the XU pipe;
 //   * packed blocks are assembled in a shared-memory tile and leave the SM as ONE 1-D bulk async
 //     store per tile (`cp.async.bulk.global.shared::cta`, SASS UBLKCP), double buffered.
 #include "ggq_common.cuh"
@@ -19,288 +21,475 @@
 
 namespace ggq {
 
-constexpr int Q_THREADS = 256;
-constexpr int Q_ROWS = 4;                                  // independent 8-element chunks per thread
-constexpr int Q_TILE_ELEMS = Q_THREADS * 8 * Q_ROWS;       // 8192
-
+constexpr int QL_THREADS = 128;   // rows per tile
 constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr float F32_MAX = 3.40282347e+38f;
 
-// ---- folds of structs.rs:91-107 over 8 lane-local elements, then across `LANES` lanes ----------
-// max_abs: fold acc.max(|x|) from 0, NaN ignored.
-template <int LANES> __device__ __forceinline__ float block_max_abs(const float *x) {
-    float acc = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { const float a = fabsf(x[i]); acc = a > acc ? a : acc; }
-#pragma unroll
-    for (int m = 1; m < LANES; m <<= 1) { const float o = __shfl_xor_sync(FULL, acc, m); acc = o > acc ? o : acc; }
-    return acc;
+__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
 }
-// max_by_abs: the FIRST x with strictly greatest |x| (sign kept); NaN never selected.
-template <int LANES> __device__ __forceinline__ float block_max_by_abs(const float *x, int lane) {
-    float acc = 0.0f;
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- a row of 32 elements, widened to f32 (lib.rs:66-69, 82-84); `raw` keeps the f16 pairs --------
+template <class FT> struct Row;
+template <> struct Row<F32> {
+    float x[32];
+    __device__ __forceinline__ void zero() {
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc = fabsf(x[i]) > fabsf(acc) ? x[i] : acc;
-#pragma unroll
-    for (int m = 1; m < LANES; m <<= 1) {
-        const float o = __shfl_xor_sync(FULL, acc, m);
-        // the partner with the lower lane id covers lower element indices and wins ties
-        const bool lower = (lane & m) == 0;
-        const float first = lower ? acc : o, second = lower ? o : acc;
-        acc = fabsf(second) > fabsf(first) ? second : first;
+        for (int k = 0; k < 32; k++) x[k] = 0.0f;
     }
-    return acc;
-}
-// min_max: strict-compare folds from (f32::MAX, f32::MIN); first seen wins ties (keeps the sign of
-// the first zero, as the reference's x86 lowering does — see oracle/ggq_oracle.c min_max()).
-template <int LANES> __device__ __forceinline__ void block_min_max(const float *x, int lane, float &mn, float &mx) {
-    float lo = 3.40282347e+38f, hi = -3.40282347e+38f;
+    __device__ __forceinline__ void load(const uint8_t *s) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) { lo = x[i] < lo ? x[i] : lo; hi = x[i] > hi ? x[i] : hi; }
-#pragma unroll
-    for (int m = 1; m < LANES; m <<= 1) {
-        const float ol = __shfl_xor_sync(FULL, lo, m), oh = __shfl_xor_sync(FULL, hi, m);
-        const bool lower = (lane & m) == 0;
-        const float fl = lower ? lo : ol, sl = lower ? ol : lo;
-        const float fh = lower ? hi : oh, sh = lower ? oh : hi;
-        lo = sl < fl ? sl : fl;
-        hi = sh > fh ? sh : fh;
+        for (int i = 0; i < 8; i++) {
+            const float4 v = *reinterpret_cast<const float4 *>(s + 16 * i);
+            x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+        }
     }
-    mn = lo;
-    mx = hi;
+};
+template <> struct Row<BF16> {
+    float x[32];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int k = 0; k < 32; k++) x[k] = 0.0f;
+    }
+    __device__ __forceinline__ void load(const uint8_t *s) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(s + 16 * i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                x[8 * i + 2 * k] = __uint_as_float(w[k] << 16);
+                x[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+            }
+        }
+    }
+};
+template <> struct Row<F16> {
+    float x[32];
+    uint32_t raw[16];  // half2 pairs (x[2k], x[2k+1])
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int k = 0; k < 32; k++) x[k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 16; k++) raw[k] = 0u;
+    }
+    __device__ __forceinline__ void load(const uint8_t *s) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(s + 16 * i);
+            raw[4 * i] = v.x; raw[4 * i + 1] = v.y; raw[4 * i + 2] = v.z; raw[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&raw[k]));
+            x[2 * k] = f.x; x[2 * k + 1] = f.y;
+        }
+    }
+};
+
+// ---- folds of structs.rs:91-107 over the 32 elements of one row -----------------------------------
+// All three are max/min folds that ignore NaN; max and min are exact, so evaluating them on packed f16
+// pairs gives the same value as the reference's f32 fold.
+// max_abs (structs.rs:91-94): fold acc.max(|x|) from 0
+template <class FT> __device__ __forceinline__ float row_max_abs(const Row<FT> &r) {
+    float a = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) a = fmaxf(a, fabsf(r.x[i]));
+    return a;
+}
+template <> __device__ __forceinline__ float row_max_abs<F16>(const Row<F16> &r) {
+    __half2 a = __floats2half2_rn(0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint32_t m = r.raw[k] & 0x7FFF7FFFu;
+        a = __hmax2(a, *reinterpret_cast<const __half2 *>(&m));
+    }
+    return fmaxf(__low2float(a), __high2float(a));
+}
+// largest and smallest element with a virtual 0 (the fold's start value): P >= 0 >= N
+template <class FT> __device__ __forceinline__ void row_pos_neg(const Row<FT> &r, float &P, float &N) {
+    float p = 0.0f, n = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) { p = fmaxf(p, r.x[i]); n = fminf(n, r.x[i]); }
+    P = p; N = n;
+}
+template <> __device__ __forceinline__ void row_pos_neg<F16>(const Row<F16> &r, float &P, float &N) {
+    __half2 p = __floats2half2_rn(0.0f, 0.0f), n = p;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const __half2 v = *reinterpret_cast<const __half2 *>(&r.raw[k]);
+        p = __hmax2(p, v);
+        n = __hmin2(n, v);
+    }
+    P = fmaxf(__low2float(p), __high2float(p));
+    N = fminf(__low2float(n), __high2float(n));
+}
+// min_max (structs.rs:102-107): folds from (f32::MAX, f32::MIN); NaN dropped
+template <class FT> __device__ __forceinline__ void row_min_max(const Row<FT> &r, float &mn, float &mx) {
+    float lo = F32_MAX, hi = -F32_MAX;
+#pragma unroll
+    for (int i = 0; i < 32; i++) { lo = fminf(lo, r.x[i]); hi = fmaxf(hi, r.x[i]); }
+    mn = lo; mx = hi;
+}
+template <> __device__ __forceinline__ void row_min_max<F16>(const Row<F16> &r, float &mn, float &mx) {
+    const uint32_t pinf = 0x7C007C00u, ninf = 0xFC00FC00u;
+    __half2 lo = *reinterpret_cast<const __half2 *>(&pinf), hi = *reinterpret_cast<const __half2 *>(&ninf);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const __half2 v = *reinterpret_cast<const __half2 *>(&r.raw[k]);
+        lo = __hmin2(lo, v);
+        hi = __hmax2(hi, v);
+    }
+    mn = fminf(F32_MAX, fminf(__low2float(lo), __high2float(lo)));
+    mx = fmaxf(-F32_MAX, fmaxf(__low2float(hi), __high2float(hi)));
 }
 
-// Rust `v as u8` for v already known <= 255 on the high side by the caller's clamp order
-__device__ __forceinline__ uint32_t as_u8(float v) { return min(__float2uint_rz(v), 255u); }  // NaN -> 0, neg -> 0
-// Rust `v.round() as i8`: half away from zero, saturating, NaN -> 0
-__device__ __forceinline__ int round_as_i8(float v) {
-    // floor(|v| + 0.5) == trunc(RZ(|v| + 0.5)); RZ keeps the sum from rounding up across an integer
-    const float r = __fadd_rz(v, copysignf(0.5f, v));
-    return max(-128, min(127, __float2int_rz(r)));
+// max_by_abs (structs.rs:96-100) over G lanes x 32 elements: the FIRST x with strictly greatest |x|.
+// With P = max(0, x...) and N = min(0, x...) the winner is P if P > -N, N if -N > P; only when both
+// +a and -a occur (P == -N != 0) does the order matter, and then the first of them wins.
+template <int G, class FT> __device__ __forceinline__ float block_max_by_abs(const Row<FT> &r, int j) {
+    float P, N;
+    row_pos_neg<FT>(r, P, N);
+#pragma unroll
+    for (int m = 1; m < G; m <<= 1) {
+        P = fmaxf(P, __shfl_xor_sync(FULL, P, m));
+        N = fminf(N, __shfl_xor_sync(FULL, N, m));
+    }
+    const float a = -N;
+    float res = (P > a) ? P : ((a > P) ? N : 0.0f);
+    // tie between +P and -P somewhere in the block: the first |x| == P in index order decides the sign
+    const bool tie = (P == a) && (P != 0.0f);
+    if (G == 1 ? tie : __any_sync(FULL, tie)) {  // G > 1: every lane of the warp runs the shuffles
+        int first = 32 * G;
+#pragma unroll
+        for (int i = 31; i >= 0; i--) first = (fabsf(r.x[i]) == P) ? (32 * j + i) : first;
+        float val = 0.0f;
+#pragma unroll
+        for (int i = 31; i >= 0; i--) val = (32 * j + i == first) ? r.x[i] : val;
+#pragma unroll
+        for (int m = 1; m < G; m <<= 1) {
+            const int of = __shfl_xor_sync(FULL, first, m);
+            const float ov = __shfl_xor_sync(FULL, val, m);
+            if (of < first) { first = of; val = ov; }
+        }
+        if (tie) res = val;
+    }
+    return res;
 }
 
-// ---- encoders: `x` = this lane's 8 elements, `j` = lane index inside the block group ------------
+// min of the row as the reference's strict-compare fold reports it: when the minimum is a zero, the
+// FIRST zero in index order keeps its sign (oracle/ggq_oracle.c min_max()).
+template <class FT> __device__ __forceinline__ float fix_zero_min(const Row<FT> &r, float mn) {
+    if (mn != 0.0f) return mn;
+    float z = mn;
+#pragma unroll
+    for (int i = 31; i >= 0; i--) z = (r.x[i] == 0.0f) ? r.x[i] : z;
+    return z;
+}
+
+// floor(v) for 0 <= v < 2^23 left in the low mantissa bits (RZ add never rounds up across an integer)
+__device__ __forceinline__ uint32_t floor_bits(float v) { return __float_as_uint(__fadd_rz(v, 8388608.0f)); }
+// Rust `v.round() as i8` as an int: half away from zero, NaN -> 0, +-inf saturate at int range
+__device__ __forceinline__ int round_half_away(float v) {
+    const float h = __uint_as_float((__float_as_uint(v) & 0x80000000u) | 0x3F000000u);  // copysign(0.5, v)
+    return __float2int_rz(__fadd_rz(v, h));
+}
+// bytes [sat8(a), sat8(b), sat8(c), sat8(d)] (little-endian) from four ints
+__device__ __forceinline__ uint32_t pack_sat_s8(int a, int b, int c, int d) {
+    uint32_t t, w;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(d), "r"(c), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(b), "r"(a), "r"(t));
+    return w;
+}
+// low bytes of four registers -> one word
+__device__ __forceinline__ uint32_t gather_b0(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+__device__ __forceinline__ void sts16(uint8_t *p, uint32_t v) { *reinterpret_cast<uint16_t *>(p) = (uint16_t)v; }
+// store NW words at a 2-byte aligned shared address
+template <int NW> __device__ __forceinline__ void sts_words2(uint8_t *p, const uint32_t *w) {
+#pragma unroll
+    for (int i = 0; i < NW; i++) { sts16(p + 4 * i, w[i] & 0xFFFFu); sts16(p + 4 * i + 2, w[i] >> 16); }
+}
+template <int NW> __device__ __forceinline__ void sts_words4(uint8_t *p, const uint32_t *w) {
+#pragma unroll
+    for (int i = 0; i < NW; i++) *reinterpret_cast<uint32_t *>(p + 4 * i) = w[i];
+}
+
+// 16 payload bytes of Q4_x / low nibbles of Q5_x: byte i = code[i] | code[i+16] << 4, codes < 16 in
+// the low byte of c[] (upper bits of c[] are don't-care: only byte 0 of the sum is gathered)
+__device__ __forceinline__ void nibble_bytes(const uint32_t *c, uint32_t *w) {
+    uint32_t b[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) b[i] = c[i] + (c[i + 16] << 4);
+#pragma unroll
+    for (int k = 0; k < 4; k++) w[k] = gather_b0(b[4 * k], b[4 * k + 1], b[4 * k + 2], b[4 * k + 3]);
+}
+
+// ---- encoders: one thread, one 32-element row -------------------------------------------------------
 template <uint32_t T> struct Encoder;
-
-// pack 8 nibble codes c[k] (k-th element of this lane) into two words, one code per byte
-__device__ __forceinline__ void bytes8(const uint32_t *c, uint32_t &w0, uint32_t &w1) {
-    w0 = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
-    w1 = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
-}
-// 4-bit payload shared by Q4_x / Q5_x: lanes j=0,1 hold elements 0..15 (low nibbles), lanes 2,3 hold
-// 16..31 (high nibbles) of the same 16 bytes.  After the exchange lane j writes 4 of the bytes.
-template <int QOFF, int ALIGN> __device__ __forceinline__ void store_nibbles(uint8_t *blk, int j, uint32_t w0, uint32_t w1) {
-    const uint32_t o0 = __shfl_xor_sync(FULL, w0, 2), o1 = __shfl_xor_sync(FULL, w1, 2);
-    if (j < 2) sts32<ALIGN>(blk + QOFF + 8 * j, w0 | (o0 << 4));           // bytes 8j .. 8j+3
-    else       sts32<ALIGN>(blk + QOFF + 8 * (j - 2) + 4, o1 | (w1 << 4)); // bytes 8(j-2)+4 .. +7
-}
 
 // q4_0.rs:23-44
 template <> struct Encoder<T_Q4_0> {
-    static constexpr int LANES = 4;
-    static __device__ __forceinline__ void run(const float *x, int j, int lane, uint8_t *blk) {
-        const float mx = block_max_by_abs<4>(x, lane);
-        uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        uint16_t d16 = 0;
+    static constexpr int G = 1;
+    template <class FT> static __device__ __forceinline__ void run(const Row<FT> &r, int, uint8_t *blk) {
+        const float mx = block_max_by_abs<1, FT>(r, 0);
+        uint32_t w[4] = {0, 0, 0, 0};
+        uint32_t d16 = 0;
         if (mx != 0.0f) {
-            const float d = __fdiv_rn(mx, -8.0f), r = __fdiv_rn(1.0f, d);
+            const float d = __fmul_rn(mx, -0.125f);  // == mx / -8 (power of two: same real value, same rounding)
+            const float rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
+            uint32_t c[32];
 #pragma unroll
-            for (int k = 0; k < 8; k++) c[k] = as_u8(fminf(__fadd_rn(__fmul_rn(x[k], r), 8.5f), 15.0f));
+            for (int i = 0; i < 32; i++) {
+                // (x*recip + 8.5).min(15.) as u8 : NaN -> 15 (fminf drops it), negatives -> 0
+                const float v = fminf(__fadd_rn(__fmul_rn(r.x[i], rc), 8.5f), 15.0f);
+                c[i] = floor_bits(fmaxf(v, 0.0f));
+            }
+            nibble_bytes(c, w);
         }
-        uint32_t w0, w1;
-        bytes8(c, w0, w1);
-        store_nibbles<2, 2>(blk, j, w0, w1);
-        if (j == 0) *reinterpret_cast<uint16_t *>(blk) = d16;
+        sts16(blk, d16);
+        sts_words2<4>(blk + 2, w);
     }
 };
 
 // q4_1.rs:23-47
 template <> struct Encoder<T_Q4_1> {
-    static constexpr int LANES = 4;
-    static __device__ __forceinline__ void run(const float *x, int j, int lane, uint8_t *blk) {
+    static constexpr int G = 1;
+    template <class FT> static __device__ __forceinline__ void run(const Row<FT> &r, int, uint8_t *blk) {
         float mn, mx;
-        block_min_max<4>(x, lane, mn, mx);
-        uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        uint16_t d16 = 0;
+        row_min_max<FT>(r, mn, mx);
+        mn = fix_zero_min<FT>(r, mn);
+        uint32_t w[4] = {0, 0, 0, 0};
+        uint32_t d16 = 0;
         if (mn != mx) {
-            const float d = __fdiv_rn(__fsub_rn(mx, mn), 15.0f), r = __fdiv_rn(1.0f, d);
+            const float d = __fdiv_rn(__fsub_rn(mx, mn), 15.0f), rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
+            uint32_t c[32];
 #pragma unroll
-            for (int k = 0; k < 8; k++) c[k] = min(as_u8(__fadd_rn(__fmul_rn(__fsub_rn(x[k], mn), r), 0.5f)), 15u);
+            for (int i = 0; i < 32; i++) {
+                // (((x - min)*recip + 0.5) as u8).min(15) : NaN -> 0
+                const float v = __fadd_rn(__fmul_rn(__fsub_rn(r.x[i], mn), rc), 0.5f);
+                c[i] = floor_bits(fminf(fmaxf(v, 0.0f), 15.0f));
+            }
+            nibble_bytes(c, w);
         }
-        uint32_t w0, w1;
-        bytes8(c, w0, w1);
-        store_nibbles<4, 4>(blk, j, w0, w1);
-        if (j == 0) *reinterpret_cast<uint32_t *>(blk) = (uint32_t)d16 | ((uint32_t)f2h(mn) << 16);
+        *reinterpret_cast<uint32_t *>(blk) = d16 | ((uint32_t)f2h(mn) << 16);
+        sts_words4<4>(blk + 4, w);
     }
 };
 
-// q5_0.rs:26-58  (qh bit i = bit 4 of element i's code, for all 32 elements)
+// 5-bit codes (< 32, low byte of c[]) -> qh (bit i = bit 4 of code i) and the 16 nibble bytes
+__device__ __forceinline__ void pack5(const uint32_t *c, uint32_t &qh, uint32_t *w) {
+    uint32_t n[32];
+    qh = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        qh |= ((c[i] >> 4) & 1u) << i;
+        n[i] = c[i] & 15u;
+    }
+    nibble_bytes(n, w);
+}
+
+// q5_0.rs:26-58
 template <> struct Encoder<T_Q5_0> {
-    static constexpr int LANES = 4;
-    static __device__ __forceinline__ void run(const float *x, int j, int lane, uint8_t *blk) {
-        const float mx = block_max_by_abs<4>(x, lane);
-        uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        uint16_t d16 = 0;
+    static constexpr int G = 1;
+    template <class FT> static __device__ __forceinline__ void run(const Row<FT> &r, int, uint8_t *blk) {
+        const float mx = block_max_by_abs<1, FT>(r, 0);
+        uint32_t w[4] = {0, 0, 0, 0};
+        uint32_t d16 = 0, qh = 0;
         if (mx != 0.0f) {
-            const float d = __fdiv_rn(mx, -16.0f), r = __fdiv_rn(1.0f, d);
+            const float d = __fmul_rn(mx, -0.0625f);  // == mx / -16
+            const float rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
+            uint32_t c[32];
 #pragma unroll
-            for (int k = 0; k < 8; k++) c[k] = min(as_u8(__fadd_rn(__fmul_rn(x[k], r), 16.5f)), 31u);
+            for (int i = 0; i < 32; i++) {
+                // ((x*recip + 16.5) as u8).min(31) : NaN -> 0
+                const float v = __fadd_rn(__fmul_rn(r.x[i], rc), 16.5f);
+                c[i] = floor_bits(fminf(fmaxf(v, 0.0f), 31.0f));
+            }
+            pack5(c, qh, w);
         }
-        uint32_t hb = 0, n[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) { hb |= (c[k] >> 4) << k; n[k] = c[k] & 15u; }
-        uint32_t w0, w1;
-        bytes8(n, w0, w1);
-        store_nibbles<6, 2>(blk, j, w0, w1);
-        blk[2 + j] = (uint8_t)hb;
-        if (j == 0) *reinterpret_cast<uint16_t *>(blk) = d16;
+        sts16(blk, d16);
+        sts16(blk + 2, qh & 0xFFFFu);
+        sts16(blk + 4, qh >> 16);
+        sts_words2<4>(blk + 6, w);
     }
 };
 
 // q5_1.rs:26-62
 template <> struct Encoder<T_Q5_1> {
-    static constexpr int LANES = 4;
-    static __device__ __forceinline__ void run(const float *x, int j, int lane, uint8_t *blk) {
+    static constexpr int G = 1;
+    template <class FT> static __device__ __forceinline__ void run(const Row<FT> &r, int, uint8_t *blk) {
         float mn, mx;
-        block_min_max<4>(x, lane, mn, mx);
-        uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        uint16_t d16 = 0;
+        row_min_max<FT>(r, mn, mx);
+        mn = fix_zero_min<FT>(r, mn);
+        uint32_t w[4] = {0, 0, 0, 0};
+        uint32_t d16 = 0, qh = 0;
         if (mn != mx) {
-            const float d = __fdiv_rn(__fsub_rn(mx, mn), 31.0f), r = __fdiv_rn(1.0f, d);
+            const float d = __fdiv_rn(__fsub_rn(mx, mn), 31.0f), rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
+            uint32_t c[32];
 #pragma unroll
-            for (int k = 0; k < 8; k++) c[k] = min(as_u8(__fadd_rn(__fmul_rn(__fsub_rn(x[k], mn), r), 0.5f)), 31u);
+            for (int i = 0; i < 32; i++) {
+                const float v = __fadd_rn(__fmul_rn(__fsub_rn(r.x[i], mn), rc), 0.5f);
+                c[i] = floor_bits(fminf(fmaxf(v, 0.0f), 31.0f));
+            }
+            pack5(c, qh, w);
         }
-        uint32_t hb = 0, n[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) { hb |= (c[k] >> 4) << k; n[k] = c[k] & 15u; }
-        uint32_t w0, w1;
-        bytes8(n, w0, w1);
-        store_nibbles<8, 4>(blk, j, w0, w1);
-        blk[4 + j] = (uint8_t)hb;
-        if (j == 0) *reinterpret_cast<uint32_t *>(blk) = (uint32_t)d16 | ((uint32_t)f2h(mn) << 16);
+        *reinterpret_cast<uint32_t *>(blk) = d16 | ((uint32_t)f2h(mn) << 16);
+        *reinterpret_cast<uint32_t *>(blk + 4) = qh;
+        sts_words4<4>(blk + 8, w);
     }
 };
 
 // q8_0.rs:23-41 and q8_1.rs:28-55 (Q8_1 adds sum = f16(Σq as f32 * delta), delta unrounded)
-template <uint32_t T, int QOFF, bool WITH_SUM> struct Encoder8 {
-    static constexpr int LANES = 4;
-    static __device__ __forceinline__ void run(const float *x, int j, int /*lane*/, uint8_t *blk) {
-        const float amax = block_max_abs<4>(x);
-        int q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        float d = 0.0f;
-        uint16_t d16 = 0;
+template <uint32_t T, bool WITH_SUM> struct Encoder8 {
+    static constexpr int G = 1;
+    template <class FT> static __device__ __forceinline__ void run(const Row<FT> &r, int, uint8_t *blk) {
+        const float amax = row_max_abs<FT>(r);
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t d16 = 0, s16 = 0;
         if (amax != 0.0f) {
-            d = __fdiv_rn(amax, 127.0f);
-            const float r = __fdiv_rn(1.0f, d);
+            const float d = __fdiv_rn(amax, 127.0f), rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
 #pragma unroll
-            for (int k = 0; k < 8; k++) q[k] = round_as_i8(__fmul_rn(x[k], r));
-        }
-        const uint32_t w0 = (q[0] & 0xFF) | ((q[1] & 0xFF) << 8) | ((q[2] & 0xFF) << 16) | ((uint32_t)q[3] << 24);
-        const uint32_t w1 = (q[4] & 0xFF) | ((q[5] & 0xFF) << 8) | ((q[6] & 0xFF) << 16) | ((uint32_t)q[7] << 24);
-        constexpr int AL = (QOFF % 4 == 0 && BlockTraits<T>::BYTES % 4 == 0) ? 4 : 2;
-        sts32<AL>(blk + QOFF + 8 * j, w0);
-        sts32<AL>(blk + QOFF + 8 * j + 4, w1);
-        if constexpr (WITH_SUM) {
-            int s = q[0] + q[1] + q[2] + q[3] + q[4] + q[5] + q[6] + q[7];
-            s += __shfl_xor_sync(FULL, s, 1);
-            s += __shfl_xor_sync(FULL, s, 2);
-            if (j == 0) {
-                const uint16_t s16 = amax != 0.0f ? f2h(__fmul_rn((float)s, d)) : (uint16_t)0;
-                *reinterpret_cast<uint32_t *>(blk) = (uint32_t)d16 | ((uint32_t)s16 << 16);
+            for (int k = 0; k < 8; k++)
+                w[k] = pack_sat_s8(round_half_away(__fmul_rn(r.x[4 * k], rc)), round_half_away(__fmul_rn(r.x[4 * k + 1], rc)),
+                                   round_half_away(__fmul_rn(r.x[4 * k + 2], rc)), round_half_away(__fmul_rn(r.x[4 * k + 3], rc)));
+            if constexpr (WITH_SUM) {
+                int s = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) s = __dp4a((int)w[k], 0x01010101, s);
+                s16 = f2h(__fmul_rn((float)s, d));
             }
+        }
+        if constexpr (WITH_SUM) {
+            *reinterpret_cast<uint32_t *>(blk) = d16 | (s16 << 16);
+            sts_words4<8>(blk + 4, w);
         } else {
-            if (j == 0) *reinterpret_cast<uint16_t *>(blk) = d16;
+            sts16(blk, d16);
+            sts_words2<8>(blk + 2, w);
         }
     }
 };
-template <> struct Encoder<T_Q8_0> : Encoder8<T_Q8_0, 2, false> {};
-template <> struct Encoder<T_Q8_1> : Encoder8<T_Q8_1, 4, true> {};
+template <> struct Encoder<T_Q8_0> : Encoder8<T_Q8_0, false> {};
+template <> struct Encoder<T_Q8_1> : Encoder8<T_Q8_1, true> {};
 
-// q8_k.rs:27-54 — reference layout {delta: f16, quants: [i8;256], sums: [i16;16]}, 290 bytes
+// q8_k.rs:27-54 — reference layout {delta: f16, quants: [i8;256], sums: [i16;16]}, 290 bytes.
+// 8 consecutive lanes own one super-block; lane j holds elements 32j .. 32j+31.
 template <> struct Encoder<T_Q8K> {
-    static constexpr int LANES = 32;
-    static __device__ __forceinline__ void run(const float *x, int j, int lane, uint8_t *blk) {
-        const float mx = block_max_by_abs<32>(x, lane);
-        int q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        uint16_t d16 = 0;
+    static constexpr int G = 8;
+    template <class FT> static __device__ __forceinline__ void run(const Row<FT> &r, int j, uint8_t *blk) {
+        const float mx = block_max_by_abs<8, FT>(r, j);
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t d16 = 0;
+        int s0 = 0, s1 = 0;
         if (mx != 0.0f) {
-            const float d = __fdiv_rn(mx, -127.0f), r = __fdiv_rn(1.0f, d);
+            const float d = __fdiv_rn(mx, -127.0f), rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
+            int q[32];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                // (x*recip).round().min(127.) as i8 : NaN.round() is NaN, NaN.min(127.) is 127
-                const float p = __fmul_rn(x[k], r);
-                q[k] = (p != p) ? 127 : min(round_as_i8(p), 127);
+            for (int i = 0; i < 32; i++) {
+                // (x*recip).round().min(127.) as i8 : NaN.round() is NaN and NaN.min(127.) is 127
+                const float p = __fmul_rn(r.x[i], rc);
+                q[i] = (p != p) ? 127 : min(round_half_away(p), 127);
             }
+#pragma unroll
+            for (int k = 0; k < 8; k++) w[k] = pack_sat_s8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { s0 = __dp4a((int)w[k], 0x01010101, s0); s1 = __dp4a((int)w[k + 4], 0x01010101, s1); }
         }
-        const uint32_t w0 = (q[0] & 0xFF) | ((q[1] & 0xFF) << 8) | ((q[2] & 0xFF) << 16) | ((uint32_t)q[3] << 24);
-        const uint32_t w1 = (q[4] & 0xFF) | ((q[5] & 0xFF) << 8) | ((q[6] & 0xFF) << 16) | ((uint32_t)q[7] << 24);
-        sts32<2>(blk + 2 + 8 * j, w0);
-        sts32<2>(blk + 2 + 8 * j + 4, w1);
-        int s = q[0] + q[1] + q[2] + q[3] + q[4] + q[5] + q[6] + q[7];
-        s += __shfl_xor_sync(FULL, s, 1);
-        if ((j & 1) == 0) *reinterpret_cast<uint16_t *>(blk + 258 + (j >> 1) * 2) = (uint16_t)(int16_t)s;
-        if (j == 0) *reinterpret_cast<uint16_t *>(blk) = d16;
+        sts_words2<8>(blk + 2 + 32 * j, w);
+        sts16(blk + 258 + 4 * j, (uint32_t)s0 & 0xFFFFu);
+        sts16(blk + 258 + 4 * j + 2, (uint32_t)s1 & 0xFFFFu);
+        if (j == 0) sts16(blk, d16);
     }
 };
 
 // ---------------------------------------------------------------------------------------------
-template <uint32_t T, class FT>
-__global__ void __launch_bounds__(Q_THREADS, 3)
-quant_legacy_kernel(const typename FT::raw *__restrict__ src, uint8_t *__restrict__ dst, size_t nblocks) {
+template <uint32_t T, class FT, int QS>
+__global__ void __launch_bounds__(QL_THREADS)
+quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t nblocks) {
     using TR = BlockTraits<T>;
     using E = Encoder<T>;
-    constexpr int TILE_BLOCKS = Q_TILE_ELEMS / TR::ELEMS;
-    constexpr int TILE_BYTES = TILE_BLOCKS * TR::BYTES;
-    static_assert(TILE_BYTES % 16 == 0, "tile must be a whole number of 16-byte chunks");
-    __shared__ __align__(128) uint8_t stage[2][TILE_BYTES];
+    constexpr int RPB = TR::ELEMS / 32;                 // rows per block (1, or 8 for Q8K)
+    constexpr int TILE_BLOCKS = QL_THREADS / RPB;
+    constexpr int ROW_BYTES = 32 * FT::SIZE, ROW_STRIDE = ROW_BYTES + 16, CPR = ROW_BYTES / 16;
+    constexpr int IN_STAGE = QL_THREADS * ROW_STRIDE;
+    constexpr int OUT_STAGE = (TILE_BLOCKS * TR::BYTES + 15) & ~15;
+    static_assert((TILE_BLOCKS * TR::BYTES) % 16 == 0, "tile must be a whole number of 16-byte chunks");
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *in_st = smem;
+    uint8_t *out_st = smem + QS * IN_STAGE;
 
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int j = tid % E::LANES;
-    const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
+    const int tid = threadIdx.x;
+    const size_t nrows = nblocks * RPB;
+    const size_t ntiles = (nrows + QL_THREADS - 1) / QL_THREADS;
     const bool vec_in = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
     const bool bulk_out = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
 
-    int it = 0;
-    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const size_t blk0 = t * (size_t)TILE_BLOCKS;
-        const int nb = (int)min((size_t)TILE_BLOCKS, nblocks - blk0);
-        const typename FT::raw *in = src + blk0 * TR::ELEMS;
-        uint8_t *st = stage[it & 1];
-
-        float x[Q_ROWS][8];
+    // stage the rows of this CTA's i-th tile (all threads; 16-byte chunks, coalesced)
+    auto issue = [&](size_t i) {
+        const size_t t = blockIdx.x + i * (size_t)gridDim.x;
+        if (t < ntiles) {
+            const size_t row0 = t * QL_THREADS;
+            const int rows = (int)min((size_t)QL_THREADS, nrows - row0);
+            uint8_t *st = in_st + (i % QS) * IN_STAGE;
+            const uint8_t *g = src + row0 * ROW_BYTES;
+            if (vec_in) {
 #pragma unroll
-        for (int r = 0; r < Q_ROWS; r++) {
-            const int e0 = (r * Q_THREADS + tid) * 8;
-            if (e0 / TR::ELEMS < nb) {
-                load8<FT>(in + e0, x[r], vec_in);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; k++) x[r][k] = 0.0f;
+                for (int k = 0; k < CPR; k++) {
+                    const int c = tid + k * QL_THREADS, row = c / CPR, ch = c % CPR;
+                    if (row < rows) cp_async16(st + row * ROW_STRIDE + ch * 16, g + (size_t)c * 16);
+                }
+            } else {  // source not 16-byte aligned: element-granular synchronous staging
+                using RAW = typename FT::raw;
+                const RAW *ge = reinterpret_cast<const RAW *>(g);
+                for (int e = tid; e < rows * 32; e += QL_THREADS)
+                    *reinterpret_cast<RAW *>(st + (e / 32) * ROW_STRIDE + (e % 32) * FT::SIZE) = ge[e];
             }
         }
-        // stage[it&1] was handed to the bulk store two iterations ago; thread 0 confirmed that
-        // store had finished READING shared memory before last iteration's barrier (see below).
+        cp_async_commit();
+    };
 #pragma unroll
-        for (int r = 0; r < Q_ROWS; r++) {
-            const int b = ((r * Q_THREADS + tid) * 8) / TR::ELEMS;
-            E::run(x[r], j, lane, st + b * TR::BYTES);   // shuffles inside: all lanes participate
+    for (int i = 0; i < QS; i++) issue(i);
+    cp_async_wait<QS - 1>();
+    __syncthreads();
+
+    size_t i = 0;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+        const size_t row0 = t * QL_THREADS;
+        const int rows = (int)min((size_t)QL_THREADS, nrows - row0);
+        const int nb = rows / RPB;
+        uint8_t *ost = out_st + (i & 1) * OUT_STAGE;
+        // out_st[i&1] was handed to the bulk store of iteration i-2; thread 0 confirmed that store had
+        // finished READING shared memory before the barrier of iteration i-1.
+        if (RPB > 1 || tid < rows) {  // G > 1 encoders shuffle: every lane of the warp takes part
+            Row<FT> r;
+            if (tid < rows) {
+                r.load(in_st + (i % QS) * IN_STAGE + tid * ROW_STRIDE);
+            } else {
+                r.zero();
+            }
+            E::template run<FT>(r, tid % RPB, ost + (tid / RPB) * TR::BYTES);
         }
-        // generic-proxy writes -> async-proxy (bulk store) reads
-        fence_proxy_async_smem();
-        if (tid == 0) bulk_wait_read<0>();  // every earlier bulk store has released its stage
-        __syncthreads();
-        uint8_t *out = dst + blk0 * TR::BYTES;
+        fence_proxy_async_smem();          // generic-proxy writes -> async-proxy (bulk store) reads
+        cp_async_wait<QS - 2 < 0 ? 0 : QS - 2>();  // this thread's copies of the next tile have landed
+        if (tid == 0) bulk_wait_read<0>(); // every earlier bulk store has released its stage
+        __syncthreads();                   // out tile complete, next in tile visible, this in stage free
+        uint8_t *out = dst + (row0 / RPB) * TR::BYTES;
         if (bulk_out && nb == TILE_BLOCKS) {
-            if (tid == 0) { bulk_s2g(out, st, TILE_BYTES); bulk_commit(); }
+            if (tid == 0) { bulk_s2g(out, ost, TILE_BLOCKS * TR::BYTES); bulk_commit(); }
         } else {
-            cta_copy_s2g(out, st, (uint32_t)nb * TR::BYTES, tid, Q_THREADS);
-            __syncthreads();
+            cta_copy_s2g(out, ost, (uint32_t)nb * TR::BYTES, tid, QL_THREADS);
         }
+        issue(i + QS);
     }
     if (tid == 0) bulk_wait_all<0>();
 }
@@ -308,16 +497,18 @@ quant_legacy_kernel(const typename FT::raw *__restrict__ src, uint8_t *__restric
 template <uint32_t T, class FT>
 static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
     using TR = BlockTraits<T>;
-    constexpr int TILE_BLOCKS = Q_TILE_ELEMS / TR::ELEMS;
-    auto kern = quant_legacy_kernel<T, FT>;
+    constexpr int QS = FT::SIZE == 4 ? 2 : 3;
+    constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = QL_THREADS / RPB;
+    constexpr int SMEM = QS * QL_THREADS * (32 * FT::SIZE + 16) + 2 * ((TILE_BLOCKS * TR::BYTES + 15) & ~15);
+    auto kern = quant_rows_kernel<T, FT, QS>;
     static int occ_cache[MAX_DEVICES];
     int ctas_per_sm = 0;
-    cudaError_t e = cached_occupancy(kern, Q_THREADS, 0, dev.device, occ_cache, &ctas_per_sm);
+    cudaError_t e = cached_occupancy(kern, QL_THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
     if (e != cudaSuccess) return e;
     const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
     size_t grid = (size_t)dev.sm_count * ctas_per_sm;
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, Q_THREADS, 0, stream>>>(static_cast<const typename FT::raw *>(src), static_cast<uint8_t *>(dst), nblocks);
+    kern<<<(unsigned)grid, QL_THREADS, SMEM, stream>>>(static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
     return cudaGetLastError();
 }
 
