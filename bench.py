@@ -244,8 +244,16 @@ def ours(args, rank, world, local_rank):
     clocks = sampler.stop()
     dom = max(per_kernel, key=lambda r: r["us"])
     peak, peak_src = measured_peak()
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        dom_ty = [w["ty"] for w in work if f"dequant_kernel<{NAMES[w['ty']]},f16>" == dom["kernel"]][0]
+        if dom["shape"] == "ffn":
+            traffic = tj["dequant_ffn_f16"].get(str(dom_ty))
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": f"{dom['kernel']} {dom['shape']}", "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": dom["GBps"] / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"],
+                "frac": dom["GBps"] / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"],
                 "avg_launch_us": dom["us"], "method": f"{R} back-to-back launches between two CUDA events on the launch stream, {NSETS} rotating buffer sets"}
 
     # ---- e2e: host C ABI with pinned host buffers (H2D + kernel + D2H in the timing) ----

@@ -433,63 +433,79 @@ quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, si
     const size_t ntiles = (nrows + QL_THREADS - 1) / QL_THREADS;
     const bool vec_in = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
     const bool bulk_out = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+    constexpr size_t TILE_IN = (size_t)QL_THREADS * ROW_BYTES, TILE_OUT = (size_t)TILE_BLOCKS * TR::BYTES;
+    constexpr int ROWS_PER_PASS = QL_THREADS / CPR;  // chunk k of thread tid lands in row tid/CPR + k*ROWS_PER_PASS
 
-    // stage the rows of this CTA's i-th tile (all threads; 16-byte chunks, coalesced)
-    auto issue = [&](size_t i) {
-        const size_t t = blockIdx.x + i * (size_t)gridDim.x;
-        if (t < ntiles) {
-            const size_t row0 = t * QL_THREADS;
-            const int rows = (int)min((size_t)QL_THREADS, nrows - row0);
-            uint8_t *st = in_st + (i % QS) * IN_STAGE;
-            const uint8_t *g = src + row0 * ROW_BYTES;
+    // ---- producer state: tile i of this CTA goes to stage i % QS (running pointers, no div/mod) ----
+    size_t t_issue = blockIdx.x;
+    const uint8_t *g_issue = src + t_issue * TILE_IN + (size_t)tid * 16;
+    const size_t g_step = (size_t)gridDim.x * TILE_IN;
+    const uint32_t s_chunk0 = (uint32_t)(tid / CPR) * ROW_STRIDE + (uint32_t)(tid % CPR) * 16;
+    int s_issue = 0;
+    auto issue = [&]() {  // all threads; 16-byte chunks, coalesced
+        if (t_issue < ntiles) {
+            uint8_t *st = in_st + s_issue * IN_STAGE;
+            const size_t rem = nrows - t_issue * QL_THREADS;
             if (vec_in) {
+                if (rem >= (size_t)QL_THREADS) {
 #pragma unroll
-                for (int k = 0; k < CPR; k++) {
-                    const int c = tid + k * QL_THREADS, row = c / CPR, ch = c % CPR;
-                    if (row < rows) cp_async16(st + row * ROW_STRIDE + ch * 16, g + (size_t)c * 16);
+                    for (int k = 0; k < CPR; k++) cp_async16(st + s_chunk0 + k * ROWS_PER_PASS * ROW_STRIDE, g_issue + (size_t)k * QL_THREADS * 16);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CPR; k++)
+                        if ((size_t)(tid / CPR + k * ROWS_PER_PASS) < rem)
+                            cp_async16(st + s_chunk0 + k * ROWS_PER_PASS * ROW_STRIDE, g_issue + (size_t)k * QL_THREADS * 16);
                 }
             } else {  // source not 16-byte aligned: element-granular synchronous staging
                 using RAW = typename FT::raw;
-                const RAW *ge = reinterpret_cast<const RAW *>(g);
+                const RAW *ge = reinterpret_cast<const RAW *>(g_issue - (size_t)tid * 16);
+                const int rows = (int)min((size_t)QL_THREADS, rem);
                 for (int e = tid; e < rows * 32; e += QL_THREADS)
                     *reinterpret_cast<RAW *>(st + (e / 32) * ROW_STRIDE + (e % 32) * FT::SIZE) = ge[e];
             }
         }
         cp_async_commit();
+        t_issue += gridDim.x;
+        g_issue += g_step;
+        s_issue = (s_issue + 1 == QS) ? 0 : s_issue + 1;
     };
 #pragma unroll
-    for (int i = 0; i < QS; i++) issue(i);
+    for (int i = 0; i < QS; i++) issue();
     cp_async_wait<QS - 1>();
     __syncthreads();
 
-    size_t i = 0;
-    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
-        const size_t row0 = t * QL_THREADS;
-        const int rows = (int)min((size_t)QL_THREADS, nrows - row0);
-        const int nb = rows / RPB;
-        uint8_t *ost = out_st + (i & 1) * OUT_STAGE;
-        // out_st[i&1] was handed to the bulk store of iteration i-2; thread 0 confirmed that store had
-        // finished READING shared memory before the barrier of iteration i-1.
+    // ---- consumer state ----
+    const uint8_t *my_row = in_st + tid * ROW_STRIDE;
+    const int my_j = tid % RPB;
+    const uint32_t my_out = (uint32_t)(tid / RPB) * TR::BYTES;
+    uint8_t *o_ptr = dst + (size_t)blockIdx.x * TILE_OUT;
+    const size_t o_step = (size_t)gridDim.x * TILE_OUT;
+    int s_cons = 0, o_cons = 0;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const size_t rem = nrows - t * QL_THREADS;
+        const int rows = (int)min((size_t)QL_THREADS, rem);
+        uint8_t *ost = out_st + o_cons * OUT_STAGE;
+        // out_st[o_cons] was handed to the bulk store two iterations ago; thread 0 confirmed that store
+        // had finished READING shared memory before the barrier of the previous iteration.
         if (RPB > 1 || tid < rows) {  // G > 1 encoders shuffle: every lane of the warp takes part
             Row<FT> r;
-            if (tid < rows) {
-                r.load(in_st + (i % QS) * IN_STAGE + tid * ROW_STRIDE);
-            } else {
-                r.zero();
-            }
-            E::template run<FT>(r, tid % RPB, ost + (tid / RPB) * TR::BYTES);
+            if (tid < rows) r.load(my_row + s_cons * IN_STAGE);
+            else r.zero();
+            E::template run<FT>(r, my_j, ost + my_out);
         }
-        fence_proxy_async_smem();          // generic-proxy writes -> async-proxy (bulk store) reads
-        cp_async_wait<QS - 2 < 0 ? 0 : QS - 2>();  // this thread's copies of the next tile have landed
-        if (tid == 0) bulk_wait_read<0>(); // every earlier bulk store has released its stage
-        __syncthreads();                   // out tile complete, next in tile visible, this in stage free
-        uint8_t *out = dst + (row0 / RPB) * TR::BYTES;
-        if (bulk_out && nb == TILE_BLOCKS) {
-            if (tid == 0) { bulk_s2g(out, ost, TILE_BLOCKS * TR::BYTES); bulk_commit(); }
+        fence_proxy_async_smem();                  // generic-proxy writes -> async-proxy (bulk store) reads
+        cp_async_wait<(QS >= 2) ? QS - 2 : 0>();   // this thread's copies of the next tile have landed
+        if (tid == 0) bulk_wait_read<0>();         // every earlier bulk store has released its stage
+        __syncthreads();                           // out tile complete, next in tile visible, this in stage free
+        if (bulk_out && rows == QL_THREADS) {
+            if (tid == 0) { bulk_s2g(o_ptr, ost, (uint32_t)TILE_OUT); bulk_commit(); }
         } else {
-            cta_copy_s2g(out, ost, (uint32_t)nb * TR::BYTES, tid, QL_THREADS);
+            cta_copy_s2g(o_ptr, ost, (uint32_t)(rows / RPB) * TR::BYTES, tid, QL_THREADS);
         }
-        issue(i + QS);
+        issue();
+        o_ptr += o_step;
+        s_cons = (s_cons + 1 == QS) ? 0 : s_cons + 1;
+        o_cons ^= 1;
     }
     if (tid == 0) bulk_wait_all<0>();
 }

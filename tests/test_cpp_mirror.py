@@ -1,0 +1,27 @@
+"""Builds and runs tests/cpp/test_quant_ext.cpp (the reference's unit tests against the C++ mirror)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "test_quant_ext")
+
+
+def build(ggq):
+    so_dir = os.path.join(ROOT, "gguf_b200")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", EXE, os.path.join(ROOT, "tests", "cpp", "test_quant_ext.cpp"),
+                           "-L" + so_dir, "-l:libggq.so", "-Wl,-rpath," + so_dir])
+
+
+def test_cpp_mirror_error_order_no_gpu(ggq):
+    build(ggq)
+    r = subprocess.run([EXE, "--no-gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_reference_unit_tests(ggq):
+    build(ggq)
+    r = subprocess.run([EXE], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
