@@ -1,7 +1,7 @@
 /*
  * ggq_oracle.c — CPU ORACLE (test infrastructure only; see ggq_oracle.h for the parity status).
  *
- * Build: gcc -O2 -std=c11 -ffp-contract=off -fno-fast-math -fPIC -shared -pthread
+ * Build: gcc -O3 -std=gnu11 -ffp-contract=off -fno-fast-math -fPIC -shared -pthread
  *        (-ffp-contract=off is REQUIRED: Rust never contracts a*b+c into an FMA.)
  *
  * Every function cites the reference file:line it restates (paths under /root/reference/).
@@ -13,6 +13,10 @@
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define GGO_X86 1
+#endif
 
 /* ------------------------------------------------------------------------------------------ */
 /* f32 <-> f16 / bf16: crate `half` 2.6.0 (Cargo.lock:243-246), not vendored in the reference. */
@@ -934,10 +938,38 @@ typedef struct {
     size_t b0, b1;        /* block range */
 } job;
 
+/* f16 <-> f32 over a whole block with the F16C instructions when the CPU has them — what the `half`
+ * crate does at run time (std feature detection).  VCVTPH2PS / VCVTPS2PH(RNE) give the same bits as
+ * the software routines above for every input, NaNs included (quieted, payload kept); checked by
+ * tests/test_oracle.py::test_f16c_mediation_equals_software. */
+#ifdef GGO_X86
+__attribute__((target("f16c,avx"))) static void widen_f16_hw(const uint8_t *src, float *dst, uint32_t n) {
+    uint32_t i = 0;
+    for (; i + 8 <= n; i += 8) _mm256_storeu_ps(dst + i, _mm256_cvtph_ps(_mm_loadu_si128((const __m128i *)(src + 2 * i))));
+    for (; i < n; i++) dst[i] = ggo_f16_to_f32(get16(src + 2 * i));
+}
+__attribute__((target("f16c,avx"))) static void narrow_f16_hw(const float *src, uint8_t *dst, uint32_t n) {
+    uint32_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        _mm_storeu_si128((__m128i *)(dst + 2 * i), _mm256_cvtps_ph(_mm256_loadu_ps(src + i), _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC));
+    for (; i < n; i++) put16(dst + 2 * i, ggo_f32_to_f16(src[i]));
+}
+static int have_f16c(void) {
+    static int v = -1;
+    if (v < 0) v = __builtin_cpu_supports("f16c") && __builtin_cpu_supports("avx");
+    return v;
+}
+#else
+static int have_f16c(void) { return 0; }
+static void widen_f16_hw(const uint8_t *s, float *d, uint32_t n) { (void)s; (void)d; (void)n; }
+static void narrow_f16_hw(const float *s, uint8_t *d, uint32_t n) { (void)s; (void)d; (void)n; }
+#endif
+
 static void run_range(const job *j) {
     const type_info *ti = j->ti;
     const uint32_t n = ti->elems;
     const int fs = fdt_size(j->fdt);
+    const int hw = have_f16c();
     float buf[256];
     for (size_t b = j->b0; b < j->b1; b++) {
         uint8_t *blk = j->blocks + b * ti->bytes;
@@ -945,6 +977,7 @@ static void run_range(const job *j) {
         if (j->quant) {
             /* lib.rs:66-69, 82-84: widen every element to f32 first */
             if (j->fdt == GGO_F32) memcpy(buf, fl, n * 4u);
+            else if (j->fdt == GGO_F16 && hw && n >= 8) widen_f16_hw(fl, buf, n);
             else if (j->fdt == GGO_F16) for (uint32_t i = 0; i < n; i++) buf[i] = ggo_f16_to_f32(get16(fl + 2 * i));
             else for (uint32_t i = 0; i < n; i++) buf[i] = ggo_bf16_to_f32(get16(fl + 2 * i));
             ti->q(buf, blk);
@@ -952,6 +985,7 @@ static void run_range(const job *j) {
             /* lib.rs:70-73, 87-89: f32 result, then RNE narrow */
             ti->dq(blk, buf);
             if (j->fdt == GGO_F32) memcpy(fl, buf, n * 4u);
+            else if (j->fdt == GGO_F16 && hw && n >= 8) narrow_f16_hw(buf, fl, n);
             else if (j->fdt == GGO_F16) for (uint32_t i = 0; i < n; i++) put16(fl + 2 * i, ggo_f32_to_f16(buf[i]));
             else for (uint32_t i = 0; i < n; i++) put16(fl + 2 * i, ggo_f32_to_bf16(buf[i]));
         }

@@ -106,3 +106,17 @@ def test_edge_blocks_do_not_crash(oracle):
         x = edge_blocks(n)
         q = oracle.quantize(ty, 0, x)
         oracle.dequantize(ty, 0, q)
+
+
+def test_f16c_mediation_equals_software(oracle):
+    """The slice drivers widen/narrow f16 with F16C when the CPU has it; results must equal the
+    software `half` restatement on every f16 pattern (NaNs included)."""
+    allh = np.arange(65536, dtype=np.uint16)
+    pad = np.zeros(32 - 65536 % 32 if 65536 % 32 else 0, np.uint16)
+    h = np.concatenate([allh, pad])
+    wide = oracle.dequantize(1, 0, h.view(np.uint8))           # software widen (1-element blocks)
+    for ty in (8, 2, 3):                                        # Q8_0, Q4_0, Q4_1 quantize from f16 vs from the widened f32
+        assert np.array_equal(oracle.quantize(ty, 1, h), oracle.quantize(ty, 0, wide)), ty
+    blocks = np.random.default_rng(3).integers(0, 256, 34 * 4096, dtype=np.uint8)
+    y32 = oracle.dequantize(8, 0, blocks)
+    assert np.array_equal(oracle.dequantize(8, 1, blocks), oracle.quantize(1, 0, y32).view(np.uint16))  # hw narrow == software narrow
