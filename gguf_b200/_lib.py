@@ -23,10 +23,25 @@ SYMBOLS = [
      [_c.c_uint32, _c.c_uint32, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     ("ggq_dequantize_slice_device", _c.c_int,
      [_c.c_uint32, _c.c_uint32, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    ("ggq_cast", _c.c_int, [_c.POINTER(_c.c_uint32), _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_size_t]),
+    ("ggq_type_nbytes", _c.c_size_t, [_c.c_uint32, _c.c_size_t]),
     ("ggq_host_alloc", _c.c_void_p, [_c.c_size_t]),
     ("ggq_host_free", None, [_c.c_void_p]),
     ("ggq_launch_count", _c.c_uint64, []),
     ("ggq_version", _c.c_char_p, []),
+]
+
+
+
+class ConvertStats(_c.Structure):
+    _fields_ = [("n_tensors", _c.c_uint64), ("n_cast_tensors", _c.c_uint64), ("cast_elems", _c.c_uint64), ("bytes_in", _c.c_uint64),
+                ("bytes_out", _c.c_uint64), ("seconds_plan", _c.c_double), ("seconds_convert", _c.c_double),
+                ("seconds_sync", _c.c_double), ("n_devices", _c.c_int)]
+
+
+SYMBOLS += [
+    ("ggq_convert_gguf", _c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_int, _c.POINTER(ConvertStats)]),
+    ("ggq_convert_last_error", _c.c_char_p, []),
 ]
 
 _lib = None

@@ -99,23 +99,57 @@ int plan_dequantize(uint32_t type, uint32_t fdt, size_t dst_elems, size_t src_bl
     return GGQ_OK;
 }
 
-cudaError_t enqueue(bool quant, const Plan &p, void *d_dst, const void *d_src, size_t nblocks, cudaStream_t st, DevInfo dev) {
-    const uint32_t ty = p.ti->type;
+// A "tensor type" is F32 or one of the block types (F16 / BF16 count as 1-element blocks).
+bool is_float_type(uint32_t t) { return t == GGQ_F32 || t == GGQ_F16 || t == GGQ_BF16; }
+bool type_geometry(uint32_t t, size_t *elems, size_t *bytes) {
+    if (t == GGQ_F32) { *elems = 1; *bytes = 4; return true; }
+    const TypeInfo *ti = find_type(t);
+    if (!ti) return false;
+    *elems = ti->elems;
+    *bytes = ti->bytes;
+    return true;
+}
+size_t type_nbytes(uint32_t t, size_t n_elems) {
+    size_t e = 1, b = 1;
+    type_geometry(t, &e, &b);
+    return n_elems / e * b;
+}
+
+// one kernel launch: `from` -> `to` over n_elems elements; never block -> block (see expand_chain)
+cudaError_t enqueue_hop(uint32_t from, uint32_t to, void *d_dst, const void *d_src, size_t n_elems, cudaStream_t st, DevInfo dev) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (ty == GGQ_F16 || ty == GGQ_BF16)  // 1-element blocks: structs/half.rs
-        return quant ? cast_elems(p.fdt, ty, d_src, d_dst, nblocks, st, dev) : cast_elems(ty, p.fdt, d_src, d_dst, nblocks, st, dev);
-    if (!quant) return dequant_blocks(ty, p.fdt, d_src, d_dst, nblocks, st, dev);
-    if (ty >= GGQ_Q2K && ty <= GGQ_Q6K) return quant_blocks_k(ty, p.fdt, d_src, d_dst, nblocks, st, dev);
-    return quant_blocks_legacy(ty, p.fdt, d_src, d_dst, nblocks, st, dev);
+    if (is_float_type(from) && is_float_type(to)) return cast_elems(from, to, d_src, d_dst, n_elems, st, dev);  // structs/half.rs
+    if (is_float_type(from)) {  // quantize::<to, from, N>
+        const size_t nb = n_elems / find_type(to)->elems;
+        if (to >= GGQ_Q2K && to <= GGQ_Q6K) return quant_blocks_k(to, from, d_src, d_dst, nb, st, dev);
+        return quant_blocks_legacy(to, from, d_src, d_dst, nb, st, dev);
+    }
+    if (is_float_type(to)) return dequant_blocks(from, to, d_src, d_dst, n_elems / find_type(from)->elems, st, dev);
+    return cudaErrorInvalidValue;
+}
+
+// cast.rs:136 `_ => cast(row, &cast(row, data, from, Ty::F32), Ty::F32, to)`: a quantized source is
+// mediated by F32.  Equal neighbours are dropped.
+int expand_chain(const uint32_t *types, int n, std::vector<uint32_t> *out) {
+    if (n < 1) return fail(GGQ_ERR_INVALID, "empty cast chain");
+    out->clear();
+    for (int i = 0; i < n; i++) {
+        size_t e, b;
+        if (!type_geometry(types[i], &e, &b)) return fail(GGQ_ERR_UNSUPPORTED, "unsupported tensor type in cast chain");
+        if (!out->empty() && out->back() == types[i]) continue;
+        if (!out->empty() && !is_float_type(out->back()) && !is_float_type(types[i])) out->push_back(GGQ_F32);
+        out->push_back(types[i]);
+    }
+    return GGQ_OK;
 }
 
 // ---- host pipeline -------------------------------------------------------------------------------
 constexpr int NSLOTS = 3;
-constexpr size_t CHUNK_ELEMS = size_t(1) << 23;          // 8 Mi elements of the float side per chunk
-constexpr size_t SLOT_BYTES = CHUNK_ELEMS * 4 + 4096;    // either side of a chunk fits (<= 4 B/elem)
+constexpr size_t CHUNK_ELEMS = size_t(1) << 23;          // 8 Mi elements per chunk (multiple of every block size)
+constexpr size_t SLOT_BYTES = CHUNK_ELEMS * 4 + 4096;    // any representation of a chunk fits (<= 4 B/elem)
 
 struct Slot {
-    void *d_in = nullptr, *d_out = nullptr, *h_in = nullptr, *h_out = nullptr;
+    void *d_a = nullptr, *d_b = nullptr, *h_in = nullptr, *h_out = nullptr;  // device ping-pong, pinned bounce
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
 };
@@ -129,8 +163,8 @@ std::vector<Pipeline *> g_pool;  // idle pipelines (any device)
 
 void destroy_pipeline(Pipeline *p) {
     for (auto &s : p->slots) {
-        if (s.d_in) cudaFree(s.d_in);
-        if (s.d_out) cudaFree(s.d_out);
+        if (s.d_a) cudaFree(s.d_a);
+        if (s.d_b) cudaFree(s.d_b);
         if (s.h_in) cudaFreeHost(s.h_in);
         if (s.h_out) cudaFreeHost(s.h_out);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -153,7 +187,7 @@ int acquire_pipeline(int device, Pipeline **out) {
     p->device = device;
     for (auto &s : p->slots) {
         cudaError_t e;
-        if ((e = cudaMalloc(&s.d_in, SLOT_BYTES)) != cudaSuccess || (e = cudaMalloc(&s.d_out, SLOT_BYTES)) != cudaSuccess ||
+        if ((e = cudaMalloc(&s.d_a, SLOT_BYTES)) != cudaSuccess || (e = cudaMalloc(&s.d_b, SLOT_BYTES)) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) {
             destroy_pipeline(p);
@@ -187,34 +221,36 @@ void parallel_memcpy(void *dst, const void *src, size_t n) {
         memcpy(dst, src, n);
         return;
     }
+    const size_t per = ((n + nt - 1) / nt + 63) & ~size_t(63);
     std::vector<std::thread> th;
-    const size_t per = (n / nt + 63) & ~size_t(63);
     for (size_t t = 1; t < nt; t++) {
         const size_t o = t * per;
         if (o >= n) break;
-        const size_t len = (o + per > n || t == nt - 1) ? n - o : per;
+        const size_t len = o + per > n ? n - o : per;
         th.emplace_back([=] { memcpy(static_cast<char *>(dst) + o, static_cast<const char *>(src) + o, len); });
     }
     memcpy(dst, src, per < n ? per : n);
     for (auto &t : th) t.join();
 }
 
-// Runs one host-pointer slice call: chunks of CHUNK_ELEMS elements flow through NSLOTS
-// (stream, device in/out, pinned bounce in/out) slots so H2D(c+1), kernel(c) and D2H(c-1) overlap.
-int run_host(bool quant, const Plan &p, void *dst, const void *src) {
-    if (p.nblocks == 0) return GGQ_OK;
+// Runs one host-pointer cast chain: chunks of CHUNK_ELEMS elements flow through NSLOTS (stream, device
+// ping-pong, pinned bounce in/out) slots so H2D(c+1), kernels(c) and D2H(c-1) overlap; intermediates
+// of a multi-hop chain never leave the device.
+int run_chain_host(const std::vector<uint32_t> &chain, void *dst, const void *src, size_t n_elems) {
+    if (n_elems == 0) return GGQ_OK;
     if (!dst || !src) return fail(GGQ_ERR_INVALID, "null pointer with non-zero length");
+    const uint32_t t_in = chain.front(), t_out = chain.back();
+    if (chain.size() == 1) {  // same type: plain copy (cast.rs never calls this; kept total)
+        memmove(dst, src, type_nbytes(t_in, n_elems));
+        return GGQ_OK;
+    }
     DevInfo dev;
     int rc = resolve_device(&dev);
     if (rc != GGQ_OK) return rc;
     Pipeline *pl = nullptr;
     if ((rc = acquire_pipeline(dev.device, &pl)) != GGQ_OK) return rc;
 
-    const size_t fsz = fdt_size(p.fdt);
-    const size_t blocks_per_chunk = CHUNK_ELEMS / p.ti->elems;
-    const size_t nchunks = (p.nblocks + blocks_per_chunk - 1) / blocks_per_chunk;
-    const size_t in_per_block = quant ? p.ti->elems * fsz : p.ti->bytes;
-    const size_t out_per_block = quant ? p.ti->bytes : p.ti->elems * fsz;
+    const size_t nchunks = (n_elems + CHUNK_ELEMS - 1) / CHUNK_ELEMS;
     const bool pin_in = is_pinned(src), pin_out = is_pinned(dst);
 
     // lazily allocate bounce buffers only when the caller's memory is pageable
@@ -228,7 +264,8 @@ int run_host(bool quant, const Plan &p, void *dst, const void *src) {
         return fail_cuda(e, "cudaHostAlloc");
     }
 
-    auto chunk_blocks = [&](size_t c) { return (c + 1 == nchunks) ? p.nblocks - c * blocks_per_chunk : blocks_per_chunk; };
+    auto chunk_elems = [&](size_t c) { return (c + 1 == nchunks) ? n_elems - c * CHUNK_ELEMS : CHUNK_ELEMS; };
+    const size_t in_chunk = type_nbytes(t_in, CHUNK_ELEMS), out_chunk = type_nbytes(t_out, CHUNK_ELEMS);
     const char *srcb = static_cast<const char *>(src);
     char *dstb = static_cast<char *>(dst);
 
@@ -237,19 +274,24 @@ int run_host(bool quant, const Plan &p, void *dst, const void *src) {
         if (c >= NSLOTS) {  // retire chunk c - NSLOTS
             const size_t r = c - NSLOTS;
             if ((e = cudaEventSynchronize(s.done)) != cudaSuccess) break;
-            if (!pin_out) parallel_memcpy(dstb + r * blocks_per_chunk * out_per_block, s.h_out, chunk_blocks(r) * out_per_block);
+            if (!pin_out) parallel_memcpy(dstb + r * out_chunk, s.h_out, type_nbytes(t_out, chunk_elems(r)));
         }
         if (c < nchunks) {
-            const size_t nb = chunk_blocks(c);
-            const char *hsrc = srcb + c * blocks_per_chunk * in_per_block;
+            const size_t ne = chunk_elems(c);
+            const char *hsrc = srcb + c * in_chunk;
             if (!pin_in) {
-                parallel_memcpy(s.h_in, hsrc, nb * in_per_block);
+                parallel_memcpy(s.h_in, hsrc, type_nbytes(t_in, ne));
                 hsrc = static_cast<const char *>(s.h_in);
             }
-            if ((e = cudaMemcpyAsync(s.d_in, hsrc, nb * in_per_block, cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) break;
-            if ((e = enqueue(quant, p, s.d_out, s.d_in, nb, s.stream, dev)) != cudaSuccess) break;
-            void *hdst = pin_out ? static_cast<void *>(dstb + c * blocks_per_chunk * out_per_block) : s.h_out;
-            if ((e = cudaMemcpyAsync(hdst, s.d_out, nb * out_per_block, cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) break;
+            if ((e = cudaMemcpyAsync(s.d_a, hsrc, type_nbytes(t_in, ne), cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) break;
+            void *cur = s.d_a, *nxt = s.d_b;
+            for (size_t h = 0; h + 1 < chain.size(); h++) {
+                if ((e = enqueue_hop(chain[h], chain[h + 1], nxt, cur, ne, s.stream, dev)) != cudaSuccess) break;
+                std::swap(cur, nxt);
+            }
+            if (e != cudaSuccess) break;
+            void *hdst = pin_out ? static_cast<void *>(dstb + c * out_chunk) : s.h_out;
+            if ((e = cudaMemcpyAsync(hdst, cur, type_nbytes(t_out, ne), cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) break;
             if ((e = cudaEventRecord(s.done, s.stream)) != cudaSuccess) break;
         }
     }
@@ -257,10 +299,16 @@ int run_host(bool quant, const Plan &p, void *dst, const void *src) {
         for (auto &s : pl->slots) cudaStreamSynchronize(s.stream);
         cudaGetLastError();
         release_pipeline(pl);
-        return fail_cuda(e, quant ? "quantize_slice" : "dequantize_slice");
+        return fail_cuda(e, "host cast pipeline");
     }
     release_pipeline(pl);
     return GGQ_OK;
+}
+
+int run_host(bool quant, const Plan &p, void *dst, const void *src) {
+    std::vector<uint32_t> chain = quant ? std::vector<uint32_t>{p.fdt, p.ti->type} : std::vector<uint32_t>{p.ti->type, p.fdt};
+    if (chain[0] == chain[1]) chain.insert(chain.begin() + 1, GGQ_F32);  // e.g. quantize::<f16, f16, 1>: still mediated by f32 (lib.rs:66-73)
+    return run_chain_host(chain, dst, src, p.nblocks * p.ti->elems);
 }
 
 int run_device(bool quant, const Plan &p, void *dst, const void *src, void *stream) {
@@ -269,9 +317,21 @@ int run_device(bool quant, const Plan &p, void *dst, const void *src, void *stre
     DevInfo dev;
     int rc = resolve_device(&dev);
     if (rc != GGQ_OK) return rc;
-    cudaError_t e = enqueue(quant, p, dst, src, p.nblocks, static_cast<cudaStream_t>(stream), dev);
-    if (e == cudaErrorNotSupported) return fail(GGQ_ERR_UNSUPPORTED, "codec not implemented for this type");
+    const uint32_t from = quant ? p.fdt : p.ti->type, to = quant ? p.ti->type : p.fdt;
+    cudaError_t e = enqueue_hop(from, to, dst, src, p.nblocks * p.ti->elems, static_cast<cudaStream_t>(stream), dev);
     if (e != cudaSuccess) return fail_cuda(e, quant ? "quantize_slice_device" : "dequantize_slice_device");
+    return GGQ_OK;
+}
+
+// cast.rs:93-138 `cast(row, data, from, to)` for every pair of supported tensor types
+int plan_cast(const uint32_t *types, int n_types, size_t n_elems, std::vector<uint32_t> *chain) {
+    int rc = expand_chain(types, n_types, chain);
+    if (rc != GGQ_OK) return rc;
+    for (uint32_t t : *chain) {
+        size_t e, b;
+        type_geometry(t, &e, &b);
+        if (n_elems % e != 0) return fail(GGQ_ERR_INDIVISIBLE, "element count is not a multiple of a block size in the chain");
+    }
     return GGQ_OK;
 }
 
@@ -323,6 +383,18 @@ int ggq_dequantize_slice_device(uint32_t type, uint32_t fdt, void *dst, size_t d
     Plan p;
     int rc = plan_dequantize(type, fdt, dst_elems, src_blocks, &p);
     return rc != GGQ_OK ? rc : run_device(false, p, dst, src, stream);
+}
+
+int ggq_cast(const uint32_t *types, int n_types, void *dst, const void *src, size_t n_elems) {
+    std::vector<uint32_t> chain;
+    int rc = plan_cast(types, n_types, n_elems, &chain);
+    return rc != GGQ_OK ? rc : run_chain_host(chain, dst, src, n_elems);
+}
+
+size_t ggq_type_nbytes(uint32_t type, size_t n_elems) {
+    size_t e, b;
+    if (!type_geometry(type, &e, &b) || n_elems % e) return 0;
+    return n_elems / e * b;
 }
 
 void *ggq_host_alloc(size_t bytes) {

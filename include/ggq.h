@@ -92,6 +92,41 @@ int ggq_quantize_slice_device(uint32_t type, uint32_t fdt, void *dst, size_t dst
 int ggq_dequantize_slice_device(uint32_t type, uint32_t fdt, void *dst, size_t dst_elems,
                                 const void *src, size_t src_blocks, void *stream);
 
+/* ---- tensor casts (the caller of the slice API) ---------------------------------------------- */
+
+/* `cast(row, data, from, to)` — xtask/src/utils/operator/cast.rs:93-138, for every pair of supported
+ * tensor types (F32, F16, BF16 and the block types), including the pairs the reference leaves as
+ * `todo!()` (cast.rs:132-135) or sends into unbounded recursion (cast.rs:136; a quantized source is
+ * mediated by F32 exactly as that arm intends).  `types[0]` is the type of `src`, `types[n-1]` the
+ * type of `dst`; intermediate entries apply chained casts (`convert --steps "a -> b -> c"`,
+ * xtask/src/convert.rs:38-51) whose intermediates stay on the device.  Host pointers, synchronous.
+ * Returns GGQ_ERR_INDIVISIBLE when `n_elems` is not a multiple of every block size in the chain. */
+int ggq_cast(const uint32_t *types, int n_types, void *dst, const void *src, size_t n_elems);
+
+/* `GGmlType::size().elements_to_bytes(shape)` (ggus/src/tensor.rs:83-96) for a flat element count;
+ * 0 when the type is unknown or `n_elems` is not a whole number of blocks. */
+size_t ggq_type_nbytes(uint32_t type, size_t n_elems);
+
+/* ---- whole-file conversion --------------------------------------------------------------------- */
+
+struct ggq_convert_stats {
+    uint64_t n_tensors, n_cast_tensors, cast_elems, bytes_in, bytes_out;
+    double seconds_plan, seconds_convert, seconds_sync;
+    int n_devices;
+};
+
+/* `xtask convert FILE --steps "cast:linear:q8_0 embd:q8_0 -> cast:linear:f32 ..."` —
+ * xtask/src/convert.rs:24-58 → utils/mod.rs:36-59 → operator/cast.rs:28-90 → utils/write.rs:6-100,
+ * for `cast:` steps (the only operator that computes on tensor values) and a single output shard.
+ * Tensor-name → target-type rules are cast.rs:28-71 (architectures llama | gpt2 | qwen2 | clip); all
+ * steps of a tensor run as one device-resident chain; tensors are spread over `n_devices` GPUs
+ * (<= 0: all visible) with no inter-GPU traffic.  The output file is byte-identical to what the
+ * reference writer emits: header, `general.alignment`, the other KVs in input order (minus
+ * `split.*`), tensor infos, alignment-padded data.  `stats` may be NULL. */
+int ggq_convert_gguf(const char *in_path, const char *out_path, const char *steps, int n_devices,
+                     struct ggq_convert_stats *stats);
+const char *ggq_convert_last_error(void);
+
 /* ---- memory helpers ------------------------------------------------------------------------ */
 
 /* Page-locked host memory (stands in for cast.rs:158-161 `MmapMut::map_anon` when the caller

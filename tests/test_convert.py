@@ -1,0 +1,194 @@
+"""Whole-file conversion (`ggq_convert_gguf`, the xtask `convert --steps cast:...` path)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from data import F16, F32, gaussian, to_fdt
+from gguf_util import ARRAY, STRING, U32, read_gguf, write_gguf
+
+Q4_0, Q8_0, Q4K, Q6K = 2, 8, 12, 14
+
+
+def llama_like(rng_seed=0, hidden=256, ffn=512, vocab=320, layers=2, dtype=F16, big=None):
+    """(name, shape, type, bytes) for a tiny llama-architecture model; shapes are ggml order (ne0 first)."""
+    ts = []
+
+    def add(name, shape, ty=dtype, seed=[rng_seed]):
+        seed[0] += 1
+        n = int(np.prod(shape))
+        x = gaussian(n, seed[0])
+        ts.append((name, tuple(shape), ty, to_fdt(x, ty).tobytes()))
+    add("token_embd.weight", (hidden, vocab))
+    for l in range(layers):
+        add(f"blk.{l}.attn_norm.weight", (hidden,), F32)
+        add(f"blk.{l}.attn_q.weight", (hidden, hidden))
+        add(f"blk.{l}.attn_q.bias", (hidden,), F32)
+        add(f"blk.{l}.ffn_down.weight", (ffn, hidden))
+        add(f"blk.{l}.ffn_up.weight", (hidden, ffn))
+    add("output_norm.weight", (hidden,), F32)
+    add("output.weight", (hidden, vocab))
+    add("rope_freqs.weight", (64,), F32)  # 1-D, not norm/bias -> "else"
+    if big:
+        add("blk.9.ffn_gate.weight", big)
+    return ts
+
+
+KVS = [("general.architecture", STRING, "llama"), ("general.name", STRING, "tiny"), ("general.alignment", U32, 64),
+       ("llama.block_count", U32, 2), ("tokenizer.ggml.tokens", ARRAY, (STRING, ["a", "bc", "def"])),
+       ("split.count", U32, 1)]
+
+
+def test_copy_only_layout_matches_reference_writer(ggq, tmp_path):
+    """No cast step => no GPU needed.  Layout: header, general.alignment first, KVs in order minus split.*,
+    infos, alignment-padded data (xtask/src/utils/write.rs:70-90, read.rs:37-39)."""
+    from gguf_b200.convert import convert
+    src, dst = tmp_path / "in.gguf", tmp_path / "out.gguf"
+    ts = llama_like()
+    write_gguf(src, KVS, ts, alignment=64)
+    st = convert(src, dst, "")
+    kvs, tensors, alignment, size = read_gguf(dst)
+    assert alignment == 64 and st["bytes_out"] == size and st["n_cast_tensors"] == 0
+    assert [k for k, _, _ in kvs] == ["general.alignment", "general.architecture", "general.name", "llama.block_count", "tokenizer.ggml.tokens"]
+    assert list(tensors) == [t[0] for t in ts]
+    for name, shape, ty, data in ts:
+        assert tensors[name] == (shape, ty, data)
+    # idempotent: converting the output again reproduces it byte for byte
+    dst2 = tmp_path / "out2.gguf"
+    convert(dst, dst2, "")
+    assert open(dst, "rb").read() == open(dst2, "rb").read()
+
+
+@pytest.mark.parametrize("mutate,msg", [
+    (dict(magic=b"GGUX"), "MagicMismatch"), (dict(version=2), "VersionNotSupport"),
+])
+def test_parse_errors(ggq, tmp_path, mutate, msg):
+    """ggus/src/file.rs:148-444 error cases."""
+    from gguf_b200.convert import convert
+    src = tmp_path / "bad.gguf"
+    write_gguf(src, KVS, llama_like(), alignment=64, **mutate)
+    with pytest.raises(ggq.GgqError) as e:
+        convert(src, tmp_path / "o.gguf", "")
+    assert msg in str(e.value)
+
+
+def test_parse_errors_duplicates_and_truncation(ggq, tmp_path):
+    from gguf_b200.convert import convert
+    src = tmp_path / "dup.gguf"
+    write_gguf(src, KVS + [("general.name", STRING, "again")], llama_like(), alignment=64)
+    with pytest.raises(ggq.GgqError) as e:
+        convert(src, tmp_path / "o.gguf", "")
+    assert "DuplicateMetaKey" in str(e.value)
+    ts = llama_like()
+    write_gguf(src, KVS, ts + [ts[0]], alignment=64)
+    with pytest.raises(ggq.GgqError) as e:
+        convert(src, tmp_path / "o.gguf", "")
+    assert "DuplicateTensorName" in str(e.value)
+    write_gguf(src, KVS, ts, alignment=64)
+    blob = open(src, "rb").read()
+    open(src, "wb").write(blob[:-100])
+    with pytest.raises(ggq.GgqError) as e:
+        convert(src, tmp_path / "o.gguf", "")
+    assert "Eos" in str(e.value)
+    write_gguf(src, [("general.architecture", STRING, "mamba")], ts)
+    with pytest.raises(ggq.GgqError) as e:
+        convert(src, tmp_path / "o.gguf", "cast:linear:q8_0")
+    assert "Unsupported architecture" in str(e.value)
+    with pytest.raises(ggq.GgqError):
+        convert(src, tmp_path / "o.gguf", "sort:")
+
+
+def _expect(oracle, ts, rules_per_step):
+    """Apply cast.rs:28-90 with the oracle: dict name -> (type, bytes)."""
+    out = {}
+    for name, shape, ty, data in ts:
+        if name in ("token_embd.weight", "output.weight"):
+            cls = "embd"
+        elif name.endswith("_norm.weight") or name.endswith("_norm.bias"):
+            cls = "norm"
+        elif len(shape) > 1 or name.endswith(".bias"):
+            cls = "linear"
+        else:
+            cls = "else"
+        cur_ty, cur = ty, np.frombuffer(data, np.uint8)
+        for rules in rules_per_step:
+            to = rules.get(cls)
+            if to is None or to == cur_ty:
+                continue
+            # cast.rs:93-138: float -> anything = quantize; block -> float = dequantize; block -> block via F32
+            def as_float(t, b):
+                return b.view(np.float32) if t == 0 else b.view(np.uint16)
+            if cur_ty in (0, 1, 30) and to in (0,):
+                cur = oracle.dequantize(cur_ty, 0, cur).view(np.uint8)
+            elif cur_ty in (0, 1, 30):
+                cur = oracle.quantize(to, cur_ty, as_float(cur_ty, cur)).view(np.uint8)
+            elif to in (0, 1, 30):
+                cur = oracle.dequantize(cur_ty, to, cur).view(np.uint8)
+            else:
+                cur = oracle.quantize(to, 0, oracle.dequantize(cur_ty, 0, cur)).view(np.uint8)
+            cur_ty = to
+        out[name] = (cur_ty, cur.tobytes())
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("steps,rules", [
+    ("cast:linear:q8_0 embd:q4_0", [dict(linear=8, embd=2)]),
+    ("cast:linear:q8_0 embd:q8_0 -> cast:linear:f32 embd:f32 -> cast:linear:f16 embd:f16", [dict(linear=8, embd=8), dict(linear=0, embd=0), dict(linear=1, embd=1)]),
+    ("cast:linear:Q4K embd:q6k norm:f16 else:bf16", [dict(linear=12, embd=14, norm=1, **{"else": 30})]),
+    ("cast:linear:q5_1 -> cast:linear:q4_0", [dict(linear=7), dict(linear=2)]),
+])
+def test_convert_matches_oracle(ggq, oracle, tmp_path, steps, rules):
+    from gguf_b200.convert import convert
+    src, dst = tmp_path / "in.gguf", tmp_path / "out.gguf"
+    ts = llama_like(rng_seed=5)
+    write_gguf(src, KVS, ts, alignment=64)
+    st = convert(src, dst, steps)
+    _, tensors, _, size = read_gguf(dst)
+    want = _expect(oracle, ts, rules)
+    for name, shape, ty, data in ts:
+        got_shape, got_ty, got = tensors[name]
+        assert got_shape == shape and got_ty == want[name][0], name
+        assert got == want[name][1], name
+    assert st["bytes_out"] == size and st["n_cast_tensors"] > 0
+
+
+@pytest.mark.gpu
+def test_convert_multichunk_tensor_and_gguf_py_reader(ggq, oracle, tmp_path):
+    """A tensor larger than one 8 Mi-element pipeline chunk; the output is also readable by gguf-py."""
+    from gguf_b200.convert import convert
+    src, dst = tmp_path / "in.gguf", tmp_path / "out.gguf"
+    ts = llama_like(rng_seed=9, big=(4096, 2304))  # 9.4 M elements
+    write_gguf(src, [kv for kv in KVS if kv[0] != "general.alignment"], ts)
+    convert(src, dst, "cast:linear:q8_0 embd:q8_0")
+    _, tensors, alignment, _ = read_gguf(dst)
+    assert alignment == 32
+    want = _expect(oracle, ts, [dict(linear=8, embd=8)])
+    for name, *_ in ts:
+        assert tensors[name][2] == want[name][1], name
+    gr = pytest.importorskip("gguf.gguf_reader")
+    r = gr.GGUFReader(str(dst))
+    by_name = {t.name: t for t in r.tensors}
+    assert set(by_name) == {t[0] for t in ts}
+    t = by_name["blk.9.ffn_gate.weight"]
+    assert int(t.tensor_type) == 8 and bytes(t.data.tobytes()) == want["blk.9.ffn_gate.weight"][1]
+
+
+@pytest.mark.gpu
+def test_cast_api_pairs_the_reference_leaves_unimplemented(ggq, oracle):
+    """cast.rs:132-136: Q8_0 -> F16 is todo!(), Q4_0 -> anything recurses forever; ggq_cast implements them."""
+    import ctypes
+    from gguf_b200._lib import lib
+    x = gaussian(32 * 1000, 3)
+    q8 = oracle.quantize(8, 0, x)
+    out = np.empty(x.size, np.uint16)
+    chain = (ctypes.c_uint32 * 2)(8, 1)
+    assert lib().ggq_cast(chain, 2, out.ctypes.data, q8.ctypes.data, x.size) == 0
+    assert np.array_equal(out, oracle.dequantize(8, 1, q8))
+    q4 = oracle.quantize(2, 0, x)
+    out2 = np.empty(x.size // 32 * 34, np.uint8)
+    chain = (ctypes.c_uint32 * 2)(2, 8)
+    assert lib().ggq_cast(chain, 2, out2.ctypes.data, q4.ctypes.data, x.size) == 0
+    assert np.array_equal(out2, oracle.quantize(8, 0, oracle.dequantize(2, 0, q4)))
+    assert lib().ggq_cast(chain, 2, out2.ctypes.data, q4.ctypes.data, 31) == 1  # Indivisible
