@@ -13,6 +13,7 @@
 #include <thread>
 #include <vector>
 
+#include "ggq_internal.h"
 #include "ggq_kernels.h"
 
 namespace {
@@ -233,17 +234,15 @@ void parallel_memcpy(void *dst, const void *src, size_t n) {
     for (auto &t : th) t.join();
 }
 
-// Runs one host-pointer cast chain: chunks of CHUNK_ELEMS elements flow through NSLOTS (stream, device
-// ping-pong, pinned bounce in/out) slots so H2D(c+1), kernels(c) and D2H(c-1) overlap; intermediates
-// of a multi-hop chain never leave the device.
-int run_chain_host(const std::vector<uint32_t> &chain, void *dst, const void *src, size_t n_elems) {
+// Runs one cast chain over `n_elems` elements: chunks of CHUNK_ELEMS elements flow through NSLOTS
+// (stream, device ping-pong, pinned in/out) slots so H2D(c+1), kernels(c) and D2H(c-1) overlap;
+// intermediates of a multi-hop chain never leave the device.  `io` supplies and consumes the bytes:
+//   direct_src / direct_dst  non-null => pinned caller memory, DMA straight from / to it;
+//   otherwise read(pinned, byte_off, nbytes) fills a pinned bounce buffer and
+//   write(pinned, byte_off, nbytes) drains one (memcpy for pageable memory, pread/pwrite for files).
+int run_chain_io(const std::vector<uint32_t> &chain, size_t n_elems, const ggq::ChainIO &io) {
     if (n_elems == 0) return GGQ_OK;
-    if (!dst || !src) return fail(GGQ_ERR_INVALID, "null pointer with non-zero length");
     const uint32_t t_in = chain.front(), t_out = chain.back();
-    if (chain.size() == 1) {  // same type: plain copy (cast.rs never calls this; kept total)
-        memmove(dst, src, type_nbytes(t_in, n_elems));
-        return GGQ_OK;
-    }
     DevInfo dev;
     int rc = resolve_device(&dev);
     if (rc != GGQ_OK) return rc;
@@ -251,9 +250,9 @@ int run_chain_host(const std::vector<uint32_t> &chain, void *dst, const void *sr
     if ((rc = acquire_pipeline(dev.device, &pl)) != GGQ_OK) return rc;
 
     const size_t nchunks = (n_elems + CHUNK_ELEMS - 1) / CHUNK_ELEMS;
-    const bool pin_in = is_pinned(src), pin_out = is_pinned(dst);
+    const bool pin_in = io.direct_src != nullptr, pin_out = io.direct_dst != nullptr;
 
-    // lazily allocate bounce buffers only when the caller's memory is pageable
+    // lazily allocate bounce buffers only when they are needed
     cudaError_t e = cudaSuccess;
     for (auto &s : pl->slots) {
         if (!pin_in && !s.h_in && (e = cudaHostAlloc(&s.h_in, SLOT_BYTES, cudaHostAllocDefault)) != cudaSuccess) break;
@@ -266,21 +265,22 @@ int run_chain_host(const std::vector<uint32_t> &chain, void *dst, const void *sr
 
     auto chunk_elems = [&](size_t c) { return (c + 1 == nchunks) ? n_elems - c * CHUNK_ELEMS : CHUNK_ELEMS; };
     const size_t in_chunk = type_nbytes(t_in, CHUNK_ELEMS), out_chunk = type_nbytes(t_out, CHUNK_ELEMS);
-    const char *srcb = static_cast<const char *>(src);
-    char *dstb = static_cast<char *>(dst);
+    bool io_ok = true;
 
-    for (size_t c = 0; c < nchunks + NSLOTS && e == cudaSuccess; c++) {
+    for (size_t c = 0; c < nchunks + NSLOTS && e == cudaSuccess && io_ok; c++) {
         Slot &s = pl->slots[c % NSLOTS];
         if (c >= NSLOTS) {  // retire chunk c - NSLOTS
             const size_t r = c - NSLOTS;
             if ((e = cudaEventSynchronize(s.done)) != cudaSuccess) break;
-            if (!pin_out) parallel_memcpy(dstb + r * out_chunk, s.h_out, type_nbytes(t_out, chunk_elems(r)));
+            if (!pin_out) io_ok = io.write(s.h_out, r * out_chunk, type_nbytes(t_out, chunk_elems(r)));
         }
-        if (c < nchunks) {
+        if (c < nchunks && io_ok) {
             const size_t ne = chunk_elems(c);
-            const char *hsrc = srcb + c * in_chunk;
-            if (!pin_in) {
-                parallel_memcpy(s.h_in, hsrc, type_nbytes(t_in, ne));
+            const char *hsrc;
+            if (pin_in) {
+                hsrc = static_cast<const char *>(io.direct_src) + c * in_chunk;
+            } else {
+                if (!(io_ok = io.read(s.h_in, c * in_chunk, type_nbytes(t_in, ne)))) break;
                 hsrc = static_cast<const char *>(s.h_in);
             }
             if ((e = cudaMemcpyAsync(s.d_a, hsrc, type_nbytes(t_in, ne), cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) break;
@@ -290,19 +290,34 @@ int run_chain_host(const std::vector<uint32_t> &chain, void *dst, const void *sr
                 std::swap(cur, nxt);
             }
             if (e != cudaSuccess) break;
-            void *hdst = pin_out ? static_cast<void *>(dstb + c * out_chunk) : s.h_out;
+            void *hdst = pin_out ? static_cast<void *>(static_cast<char *>(io.direct_dst) + c * out_chunk) : s.h_out;
             if ((e = cudaMemcpyAsync(hdst, cur, type_nbytes(t_out, ne), cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) break;
             if ((e = cudaEventRecord(s.done, s.stream)) != cudaSuccess) break;
         }
     }
-    if (e != cudaSuccess) {
+    if (e != cudaSuccess || !io_ok) {
         for (auto &s : pl->slots) cudaStreamSynchronize(s.stream);
         cudaGetLastError();
         release_pipeline(pl);
-        return fail_cuda(e, "host cast pipeline");
+        return e != cudaSuccess ? fail_cuda(e, "host cast pipeline") : fail(GGQ_ERR_INVALID, "I/O callback failed in the cast pipeline");
     }
     release_pipeline(pl);
     return GGQ_OK;
+}
+
+int run_chain_host(const std::vector<uint32_t> &chain, void *dst, const void *src, size_t n_elems) {
+    if (n_elems == 0) return GGQ_OK;
+    if (!dst || !src) return fail(GGQ_ERR_INVALID, "null pointer with non-zero length");
+    if (chain.size() == 1) {  // same type: plain copy (cast.rs never calls this; kept total)
+        memmove(dst, src, type_nbytes(chain.front(), n_elems));
+        return GGQ_OK;
+    }
+    ggq::ChainIO io;
+    io.direct_src = is_pinned(src) ? src : nullptr;
+    io.direct_dst = is_pinned(dst) ? dst : nullptr;
+    io.read = [src](void *pinned, size_t off, size_t n) { parallel_memcpy(pinned, static_cast<const char *>(src) + off, n); return true; };
+    io.write = [dst](const void *pinned, size_t off, size_t n) { parallel_memcpy(static_cast<char *>(dst) + off, pinned, n); return true; };
+    return run_chain_io(chain, n_elems, io);
 }
 
 int run_host(bool quant, const Plan &p, void *dst, const void *src) {
@@ -336,6 +351,17 @@ int plan_cast(const uint32_t *types, int n_types, size_t n_elems, std::vector<ui
 }
 
 }  // namespace
+
+namespace ggq {
+// internal (not part of the C ABI): used by convert.cpp to stream files through the pipeline
+int cast_chain_io(const uint32_t *types, int n_types, size_t n_elems, const ChainIO &io) {
+    std::vector<uint32_t> chain;
+    int rc = plan_cast(types, n_types, n_elems, &chain);
+    if (rc != GGQ_OK) return rc;
+    if (chain.size() < 2) return fail(GGQ_ERR_INVALID, "cast_chain_io needs at least one hop");
+    return run_chain_io(chain, n_elems, io);
+}
+}  // namespace ggq
 
 extern "C" {
 

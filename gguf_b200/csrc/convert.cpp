@@ -28,6 +28,7 @@
 
 #include "../../include/ggq.h"
 #include "../host/gguf.hpp"
+#include "ggq_internal.h"
 
 namespace {
 
@@ -177,22 +178,48 @@ int ggq_convert_gguf(const char *in_path, const char *out_path, const char *step
         }
         gguf::Sink sim;
         const uint64_t out_len = gguf::write_front(sim, f.alignment, kvs, outs);
+        const uint64_t front_len = sim.pos();
 
-        int ofd = open(out_path, O_RDWR | O_CREAT | O_TRUNC, 0644);
+        // ---- output file: front matter with one write, tensor bytes with pwrite at their final
+        // offsets; the gaps between tensors are the zero padding of writer.rs:95-100 (ftruncate) ----
+        unlink(out_path);
+        int ofd = open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
         if (ofd < 0) return failc(GGQ_ERR_INVALID, std::string("cannot create ") + out_path);
-        if (ftruncate(ofd, (off_t)out_len) != 0) { close(ofd); return failc(GGQ_ERR_INVALID, "ftruncate failed"); }
-        Mapping out;
-        out.len = (size_t)out_len;
-        out.p = (uint8_t *)mmap(nullptr, out.len, PROT_READ | PROT_WRITE, MAP_SHARED, ofd, 0);
-        close(ofd);
-        if (out.p == MAP_FAILED) { out.p = nullptr; return failc(GGQ_ERR_INVALID, "mmap of the output failed"); }
-        gguf::Sink sink(out.p);
-        gguf::write_front(sink, f.alignment, kvs, outs);
-        {   // zero the alignment gaps (write_padding, writer.rs:95-100); ftruncate already zero-fills
+        struct FdGuard { int fd; ~FdGuard() { if (fd >= 0) close(fd); } } og{ofd};
+        if (ftruncate(ofd, (off_t)out_len) != 0) return failc(GGQ_ERR_INVALID, "ftruncate failed");
+        {
+            std::vector<uint8_t> front(front_len);
+            gguf::Sink sink(front.data());
+            gguf::write_front(sink, f.alignment, kvs, outs);
+            if (pwrite(ofd, front.data(), front.size(), 0) != (ssize_t)front.size()) return failc(GGQ_ERR_INVALID, "write of the header failed");
         }
+        int ifd = open(in_path, O_RDONLY);
+        if (ifd < 0) return failc(GGQ_ERR_INVALID, std::string("cannot reopen ") + in_path);
+        FdGuard ig{ifd};
+        const uint64_t in_data_off = (uint64_t)(f.data - in.p);
+        auto pread_all = [](int fd, void *buf, size_t n, uint64_t off) {
+            char *p = static_cast<char *>(buf);
+            while (n) {
+                ssize_t r = pread(fd, p, n, (off_t)off);
+                if (r <= 0) return false;
+                p += r; off += (uint64_t)r; n -= (size_t)r;
+            }
+            return true;
+        };
+        auto pwrite_all = [](int fd, const void *buf, size_t n, uint64_t off) {
+            const char *p = static_cast<const char *>(buf);
+            while (n) {
+                ssize_t r = pwrite(fd, p, n, (off_t)off);
+                if (r <= 0) return false;
+                p += r; off += (uint64_t)r; n -= (size_t)r;
+            }
+            return true;
+        };
         const double t1 = now();
 
-        // ---- convert: largest tensors first, one worker thread per device ----
+        // ---- convert: largest tensors first; WORKERS_PER_DEVICE threads per GPU, each with its own
+        // stream pipeline, so one tensor's pread overlaps another's kernels / D2H / pwrite ----
+        constexpr int WORKERS_PER_DEVICE = 3;
         std::vector<size_t> order(nt);
         for (size_t i = 0; i < nt; i++) order[i] = i;
         std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return f.tensors[a].nbytes > f.tensors[b].nbytes; });
@@ -207,37 +234,49 @@ int ggq_convert_gguf(const char *in_path, const char *out_path, const char *step
         for (size_t i = 0; i < nt; i++) need_gpu |= chains[i].size() > 1;
         if (need_gpu && ndev < 1) return failc(GGQ_ERR_CUDA, "no CUDA device (libggq has no CPU fallback)");
         if (ndev < 1) ndev = 1;
+        auto set_err = [&](int rc, const std::string &m) {
+            std::lock_guard<std::mutex> lk(err_mu);
+            int ok = GGQ_OK;
+            if (rc_all.compare_exchange_strong(ok, rc)) first_err = m;
+        };
         auto worker = [&](int dev) {
-            if (need_gpu && ggq_set_device(dev) != GGQ_OK) { rc_all = GGQ_ERR_CUDA; return; }
+            if (need_gpu && ggq_set_device(dev) != GGQ_OK) { set_err(GGQ_ERR_CUDA, ggq_last_error()); return; }
+            std::vector<uint8_t> copy_buf;
             for (;;) {
                 const size_t k = next.fetch_add(1);
                 if (k >= nt || rc_all.load() != GGQ_OK) return;
                 const size_t i = order[k];
                 const auto &t = f.tensors[i];
-                const uint8_t *src = f.data + t.offset;
-                uint8_t *dst = out.p + outs[i].file_offset;
-                if (chains[i].size() == 1) {
-                    std::memcpy(dst, src, t.nbytes);
-                } else {
-                    const int rc = ggq_cast(chains[i].data(), (int)chains[i].size(), dst, src, t.n_elems());
-                    if (rc != GGQ_OK) {
-                        std::lock_guard<std::mutex> lk(err_mu);
-                        if (rc_all.exchange(rc) == GGQ_OK) first_err = std::string(t.name) + ": " + ggq_last_error();
-                        return;
+                const uint64_t src_off = in_data_off + t.offset, dst_off = outs[i].file_offset;
+                if (chains[i].size() == 1) {  // untouched tensor: byte copy
+                    constexpr size_t CH = size_t(8) << 20;
+                    copy_buf.resize(std::min<uint64_t>(CH, t.nbytes));
+                    for (uint64_t o = 0; o < t.nbytes; o += CH) {
+                        const size_t n = (size_t)std::min<uint64_t>(CH, t.nbytes - o);
+                        if (!pread_all(ifd, copy_buf.data(), n, src_off + o) || !pwrite_all(ofd, copy_buf.data(), n, dst_off + o)) {
+                            set_err(GGQ_ERR_INVALID, "I/O error copying " + std::string(t.name));
+                            return;
+                        }
                     }
-                    cast_elems += t.n_elems();
-                    cast_tensors += 1;
+                    continue;
                 }
+                ggq::ChainIO io;
+                io.read = [&](void *pinned, size_t off, size_t n) { return pread_all(ifd, pinned, n, src_off + off); };
+                io.write = [&](const void *pinned, size_t off, size_t n) { return pwrite_all(ofd, pinned, n, dst_off + off); };
+                const int rc = ggq::cast_chain_io(chains[i].data(), (int)chains[i].size(), t.n_elems(), io);
+                if (rc != GGQ_OK) { set_err(rc, std::string(t.name) + ": " + ggq_last_error()); return; }
+                cast_elems += t.n_elems();
+                cast_tensors += 1;
             }
         };
         std::vector<std::thread> th;
-        for (int d = 1; d < ndev; d++) th.emplace_back(worker, d);
+        const int nworkers = ndev * (need_gpu ? WORKERS_PER_DEVICE : 1);
+        for (int w = 1; w < nworkers; w++) th.emplace_back(worker, w % ndev);
         worker(0);
         for (auto &x : th) x.join();
         if (rc_all.load() != GGQ_OK) return failc(rc_all.load(), first_err);
         const double t2 = now();
-        msync(out.p, out.len, MS_SYNC);
-        const double t3 = now();
+        const double t3 = t2;  // like the reference writer, no fsync: the page cache owns the rest
         if (stats) {
             stats->n_tensors = nt;
             stats->n_cast_tensors = cast_tensors.load();
