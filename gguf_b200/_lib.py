@@ -17,6 +17,7 @@ SYMBOLS = [
     ("ggq_last_error", _c.c_char_p, []),
     ("ggq_device_count", _c.c_int, []),
     ("ggq_set_device", _c.c_int, [_c.c_int]),
+    ("ggq_set_shard_devices", _c.c_int, [_c.c_int]),
     ("ggq_quantize_slice", _c.c_int, [_c.c_uint32, _c.c_uint32, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_size_t]),
     ("ggq_dequantize_slice", _c.c_int, [_c.c_uint32, _c.c_uint32, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_size_t]),
     ("ggq_quantize_slice_device", _c.c_int,

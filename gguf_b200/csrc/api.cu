@@ -23,6 +23,7 @@ using namespace ggq;
 thread_local std::string t_err;
 thread_local int t_device = -1;  // ggq_set_device override for the calling thread
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_shard_devices{1};  // ggq_set_shard_devices: GPUs one host-pointer call is split over
 
 int fail(int code, const std::string &msg) {
     t_err = msg;
@@ -312,12 +313,42 @@ int run_chain_host(const std::vector<uint32_t> &chain, void *dst, const void *sr
         memmove(dst, src, type_nbytes(chain.front(), n_elems));
         return GGQ_OK;
     }
-    ggq::ChainIO io;
-    io.direct_src = is_pinned(src) ? src : nullptr;
-    io.direct_dst = is_pinned(dst) ? dst : nullptr;
-    io.read = [src](void *pinned, size_t off, size_t n) { parallel_memcpy(pinned, static_cast<const char *>(src) + off, n); return true; };
-    io.write = [dst](const void *pinned, size_t off, size_t n) { parallel_memcpy(static_cast<char *>(dst) + off, pinned, n); return true; };
-    return run_chain_io(chain, n_elems, io);
+    const bool pin_src = is_pinned(src), pin_dst = is_pinned(dst);
+    auto make_io = [&](size_t elem0) {  // the sub-tensor starting at element `elem0`
+        const char *s0 = static_cast<const char *>(src) + type_nbytes(chain.front(), elem0);
+        char *d0 = static_cast<char *>(dst) + type_nbytes(chain.back(), elem0);
+        ggq::ChainIO io;
+        io.direct_src = pin_src ? s0 : nullptr;
+        io.direct_dst = pin_dst ? d0 : nullptr;
+        io.read = [s0](void *pinned, size_t off, size_t n) { parallel_memcpy(pinned, s0 + off, n); return true; };
+        io.write = [d0](const void *pinned, size_t off, size_t n) { parallel_memcpy(d0 + off, pinned, n); return true; };
+        return io;
+    };
+    // Blocks are independent (lib.rs:129-131): split the element range over the configured GPUs in
+    // contiguous, chunk-aligned parts; each part runs its own pipeline on its own device, there is
+    // no inter-GPU traffic.  Small calls and an explicit ggq_set_device() stay on one GPU.
+    const int ndev = (t_device >= 0) ? 1 : g_shard_devices.load();
+    const size_t nchunks = (n_elems + CHUNK_ELEMS - 1) / CHUNK_ELEMS;
+    if (ndev <= 1 || nchunks < 2) return run_chain_io(chain, n_elems, make_io(0));
+    const size_t parts = std::min<size_t>((size_t)ndev, nchunks);
+    std::vector<int> rcs(parts, GGQ_OK);
+    std::vector<std::string> errs(parts);
+    std::vector<std::thread> th;
+    auto part_fn = [&](size_t k) {
+        const size_t c0 = nchunks * k / parts, c1 = nchunks * (k + 1) / parts;
+        const size_t e0 = c0 * CHUNK_ELEMS, e1 = std::min(n_elems, c1 * CHUNK_ELEMS);
+        t_device = (int)k;  // worker thread: pin to device k
+        rcs[k] = run_chain_io(chain, e1 - e0, make_io(e0));
+        if (rcs[k] != GGQ_OK) errs[k] = t_err;
+    };
+    const int saved = t_device;
+    for (size_t k = 1; k < parts; k++) th.emplace_back(part_fn, k);
+    part_fn(0);
+    t_device = saved;
+    for (auto &t : th) t.join();
+    for (size_t k = 0; k < parts; k++)
+        if (rcs[k] != GGQ_OK) return fail(rcs[k], errs[k]);
+    return GGQ_OK;
 }
 
 int run_host(bool quant, const Plan &p, void *dst, const void *src) {
@@ -388,6 +419,15 @@ int ggq_set_device(int device) {
     if (device < 0 || device >= ggq_device_count()) return fail(GGQ_ERR_INVALID, "no such CUDA device");
     t_device = device;
     return GGQ_OK;
+}
+
+int ggq_set_shard_devices(int n_devices) {
+    const int avail = ggq_device_count();
+    if (n_devices <= 0) n_devices = avail;
+    if (n_devices > avail) return fail(GGQ_ERR_INVALID, "more shard devices than CUDA devices");
+    if (n_devices < 1) n_devices = 1;
+    g_shard_devices.store(n_devices);
+    return n_devices;
 }
 
 int ggq_quantize_slice(uint32_t type, uint32_t fdt, void *dst, size_t dst_blocks, const void *src, size_t src_elems) {

@@ -68,6 +68,13 @@ const char *ggq_last_error(void);
 int ggq_device_count(void);
 int ggq_set_device(int device);
 
+/* Spread every large host-pointer call (slice API and ggq_cast) over the first `n_devices` GPUs by
+ * contiguous block range — blocks are independent (lib.rs:129-131), so there is no inter-GPU
+ * traffic: each GPU pulls and pushes its own range over its own PCIe link.  <= 0 selects all visible
+ * devices.  Returns the device count now in effect (>= 1) or a negative status.  Default 1.  A
+ * thread that called ggq_set_device() is not sharded. */
+int ggq_set_shard_devices(int n_devices);
+
 /* ---- host-pointer slice API (the drop-in) ------------------------------------------------- */
 
 /* `QuantExt::<T, N>::quantize_slice(dst: &mut [Blk], src: &[T])` — lib.rs:121-133; called from

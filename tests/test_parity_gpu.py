@@ -211,3 +211,19 @@ def test_kquant_full_tensor_sample_vs_oracle(ggq, oracle, ty):
     idx = np.arange(0, n // 256, 97)
     xs = np.ascontiguousarray(x.reshape(-1, 256)[idx]).reshape(-1)
     assert same_blocks(q.reshape(-1, b)[idx].reshape(-1), oracle.quantize(ty, F16, xs, threads=8), ty, b)
+
+
+def test_block_range_sharding_over_all_gpus_same_bytes(ggq, oracle):
+    """ggq_set_shard_devices: a multi-chunk host call split over every visible GPU gives the same bytes
+    (with one GPU this degenerates to the single-device path)."""
+    from gguf_b200._lib import lib
+    n = (1 << 23) * 3 + 32 * 777
+    x = to_fdt(gaussian(n, 31), F16)
+    want = oracle.quantize(2, F16, x, threads=8)
+    ndev = lib().ggq_set_shard_devices(0)
+    try:
+        assert ndev >= 1
+        assert np.array_equal(ggq.quantize(2, x, F16), want)
+        assert np.array_equal(ggq.dequantize(2, want, F16), oracle.dequantize(2, F16, want, threads=8))
+    finally:
+        assert lib().ggq_set_shard_devices(1) == 1
