@@ -35,6 +35,24 @@ __device__ __forceinline__ float i2f_small(int l) { return u2f_biased((uint32_t)
 template <int NW> __device__ __forceinline__ void set_code(uint32_t (&w)[NW], int i, int l) { w[i >> 2] |= (uint32_t)(l & 0xFF) << (8 * (i & 3)); }
 template <int NW> __device__ __forceinline__ int get_code(const uint32_t (&w)[NW], int i) { return (int)((w[i >> 2] >> (8 * (i & 3))) & 0xFF); }
 
+// Rounding without leaving the FP pipes.  On upstream's domain (|v| <= 4194303, its assert)
+//   clamp(nearest_int(v), lo, hi) == rint(clamp(v, lo, hi))            (rint is monotone, lo/hi integers)
+// and rint(c) for |c| < 2^22 is (c + 1.5*2^23) - 1.5*2^23 in round-to-nearest-even, which is the very
+// addition upstream's bit trick performs.  `rb` keeps the sum: its low mantissa byte is the code.
+constexpr float RMAGIC = 12582912.f;
+__device__ __forceinline__ float round_clamped(float v, float lo, float hi, float &rb) {
+    rb = fminf(fmaxf(v, lo), hi) + RMAGIC;
+    return rb - RMAGIC;
+}
+// byte k of `word` <- low byte of `bits`
+__device__ __forceinline__ uint32_t put_byte(uint32_t word, uint32_t bits, int k) {
+    return __byte_perm(word, bits, k == 0 ? 0x3214u : k == 1 ? 0x3240u : k == 2 ? 0x3410u : 0x4210u);
+}
+// exact float(byte k of word) for small unsigned codes
+__device__ __forceinline__ float byte_as_float(uint32_t word, int k) {
+    return __uint_as_float(__byte_perm(word, 0x4B400000u, 0x7650u + k)) - RMAGIC;
+}
+
 // ---- upstream make_qkx2_quants ------------------------------------------------------------------
 template <int N, bool USE_MAD>
 __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const float (&w)[N], const int nmax, uint32_t (&L)[N / 4],
@@ -56,32 +74,31 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
         the_min = -mn;
         return 0.f;
     }
-    float iscale = (float)nmax / (mx - mn);
+    const float fmax_l = (float)nmax;
+    float iscale = fmax_l / (mx - mn);
     float scale = 1 / iscale;
     float best_mad = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        int l = nearest_int(iscale * (x[i] - mn));
-        l = max(0, min(nmax, l));
-        set_code(L, i, l);
-        float diff = scale * i2f_small(l) + mn - x[i];
+        float rb;
+        const float l = round_clamped(iscale * (x[i] - mn), 0.f, fmax_l, rb);
+        L[i >> 2] = put_byte(L[i >> 2], __float_as_uint(rb), i & 3);
+        float diff = scale * l + mn - x[i];
         diff = USE_MAD ? fabsf(diff) : diff * diff;
         best_mad += w[i] * diff;
     }
     for (int is = 0; is <= nstep; ++is) {
-        iscale = (rmin + rdelta * (float)is + (float)nmax) / (mx - mn);
+        iscale = (rmin + rdelta * (float)is + fmax_l) / (mx - mn);
         float sum_l = 0, sum_l2 = 0, sum_xl = 0;
         uint32_t Laux[N / 4];
 #pragma unroll
-        for (int k = 0; k < N / 4; k++) Laux[k] = 0;
-#pragma unroll
         for (int i = 0; i < N; ++i) {
-            int l = nearest_int(iscale * (x[i] - mn));
-            l = max(0, min(nmax, l));
-            set_code(Laux, i, l);
-            const float wl = w[i] * i2f_small(l);
+            float rb;
+            const float l = round_clamped(iscale * (x[i] - mn), 0.f, fmax_l, rb);
+            Laux[i >> 2] = (i & 3) == 0 ? __float_as_uint(rb) & 0xFFu : put_byte(Laux[i >> 2], __float_as_uint(rb), i & 3);
+            const float wl = w[i] * l;
             sum_l += wl;
-            sum_l2 += wl * i2f_small(l);
+            sum_l2 += wl * l;
             sum_xl += wl * x[i];
         }
         const float D = sum_w * sum_l2 - sum_l * sum_l;
@@ -95,7 +112,7 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
             float mad = 0;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                float diff = this_scale * i2f_small(get_code(Laux, i)) + this_min - x[i];
+                float diff = this_scale * byte_as_float(Laux[i >> 2], i & 3) + this_min - x[i];
                 diff = USE_MAD ? fabsf(diff) : diff * diff;
                 mad += w[i] * diff;
             }
@@ -123,36 +140,44 @@ __device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const in
 #pragma unroll
     for (int k = 0; k < 4; k++) L[k] = 0;
     if (amax < GROUP_MAX_EPS) return 0.f;
-    float iscale = (float)(-nmax) / mx;
+    const float lo = (float)(-nmax), hi = (float)(nmax - 1), fn = (float)nmax;
+    float w[16], wx[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { w[i] = x[i] * x[i]; wx[i] = w[i] * x[i]; }  // w*x*l is evaluated (w*x)*l
+    // codes for `iscale` (upstream recomputes them on acceptance with the same expression)
+    auto codes = [&](float isc) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float rb;
+            round_clamped(isc * x[i], lo, hi, rb);
+            L[i >> 2] = put_byte(L[i >> 2], __float_as_uint(rb + fn), i & 3);  // low byte of (l + nmax)
+        }
+    };
+    float iscale = lo / mx;
     float sumlx = 0, suml2 = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        int l = nearest_int(iscale * x[i]);
-        l = max(-nmax, min(nmax - 1, l));
-        set_code(L, i, l + nmax);
-        const float w = x[i] * x[i];
-        sumlx += w * x[i] * i2f_small(l);
-        suml2 += w * i2f_small(l) * i2f_small(l);
+        float rb;
+        const float l = round_clamped(iscale * x[i], lo, hi, rb);
+        sumlx += wx[i] * l;
+        suml2 += w[i] * l * l;
     }
+    codes(iscale);
     float scale = suml2 ? sumlx / suml2 : 0.0f;
     float best = scale * sumlx;
     for (int is = -9; is <= 9; ++is) {
         if (is == 0) continue;
-        iscale = -((float)nmax + 0.1f * (float)is) / mx;
+        iscale = -(fn + 0.1f * (float)is) / mx;
         sumlx = suml2 = 0;
-        uint32_t Laux[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            int l = nearest_int(iscale * x[i]);
-            l = max(-nmax, min(nmax - 1, l));
-            set_code(Laux, i, l + nmax);
-            const float w = x[i] * x[i];
-            sumlx += w * x[i] * i2f_small(l);
-            suml2 += w * i2f_small(l) * i2f_small(l);
+            float rb;
+            const float l = round_clamped(iscale * x[i], lo, hi, rb);
+            sumlx += wx[i] * l;
+            suml2 += w[i] * l * l;
         }
         if (suml2 > 0 && sumlx * sumlx > best * suml2) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) L[k] = Laux[k];
+            codes(iscale);
             scale = sumlx / suml2;
             best = scale * sumlx;
         }
