@@ -148,6 +148,7 @@ int expand_chain(const uint32_t *types, int n, std::vector<uint32_t> *out) {
 // ---- host pipeline -------------------------------------------------------------------------------
 constexpr int NSLOTS = 3;
 constexpr size_t CHUNK_ELEMS = size_t(1) << 23;          // 8 Mi elements per chunk (multiple of every block size)
+constexpr size_t FIRST_CHUNK_ELEMS = size_t(1) << 20;    // ramp: 1, 2, 4, 8, 8, ... Mi elements
 constexpr size_t SLOT_BYTES = CHUNK_ELEMS * 4 + 4096;    // any representation of a chunk fits (<= 4 B/elem)
 
 struct Slot {
@@ -250,7 +251,11 @@ int run_chain_io(const std::vector<uint32_t> &chain, size_t n_elems, const ggq::
     Pipeline *pl = nullptr;
     if ((rc = acquire_pipeline(dev.device, &pl)) != GGQ_OK) return rc;
 
-    const size_t nchunks = (n_elems + CHUNK_ELEMS - 1) / CHUNK_ELEMS;
+    // Chunk boundaries (elements).  The first chunks are small (1, 2, 4 Mi elements) so the first D2H
+    // starts ~0.1 ms earlier on every call; steady state uses CHUNK_ELEMS.
+    std::vector<size_t> bound{0};
+    for (size_t sz = FIRST_CHUNK_ELEMS; bound.back() < n_elems; sz = std::min(sz * 2, CHUNK_ELEMS)) bound.push_back(std::min(n_elems, bound.back() + sz));
+    const size_t nchunks = bound.size() - 1;
     const bool pin_in = io.direct_src != nullptr, pin_out = io.direct_dst != nullptr;
 
     // lazily allocate bounce buffers only when they are needed
@@ -264,24 +269,22 @@ int run_chain_io(const std::vector<uint32_t> &chain, size_t n_elems, const ggq::
         return fail_cuda(e, "cudaHostAlloc");
     }
 
-    auto chunk_elems = [&](size_t c) { return (c + 1 == nchunks) ? n_elems - c * CHUNK_ELEMS : CHUNK_ELEMS; };
-    const size_t in_chunk = type_nbytes(t_in, CHUNK_ELEMS), out_chunk = type_nbytes(t_out, CHUNK_ELEMS);
     bool io_ok = true;
-
     for (size_t c = 0; c < nchunks + NSLOTS && e == cudaSuccess && io_ok; c++) {
         Slot &s = pl->slots[c % NSLOTS];
         if (c >= NSLOTS) {  // retire chunk c - NSLOTS
             const size_t r = c - NSLOTS;
             if ((e = cudaEventSynchronize(s.done)) != cudaSuccess) break;
-            if (!pin_out) io_ok = io.write(s.h_out, r * out_chunk, type_nbytes(t_out, chunk_elems(r)));
+            if (!pin_out) io_ok = io.write(s.h_out, type_nbytes(t_out, bound[r]), type_nbytes(t_out, bound[r + 1] - bound[r]));
         }
         if (c < nchunks && io_ok) {
-            const size_t ne = chunk_elems(c);
+            const size_t ne = bound[c + 1] - bound[c];
+            const size_t in_off = type_nbytes(t_in, bound[c]), out_off = type_nbytes(t_out, bound[c]);
             const char *hsrc;
             if (pin_in) {
-                hsrc = static_cast<const char *>(io.direct_src) + c * in_chunk;
+                hsrc = static_cast<const char *>(io.direct_src) + in_off;
             } else {
-                if (!(io_ok = io.read(s.h_in, c * in_chunk, type_nbytes(t_in, ne)))) break;
+                if (!(io_ok = io.read(s.h_in, in_off, type_nbytes(t_in, ne)))) break;
                 hsrc = static_cast<const char *>(s.h_in);
             }
             if ((e = cudaMemcpyAsync(s.d_a, hsrc, type_nbytes(t_in, ne), cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) break;
@@ -291,7 +294,7 @@ int run_chain_io(const std::vector<uint32_t> &chain, size_t n_elems, const ggq::
                 std::swap(cur, nxt);
             }
             if (e != cudaSuccess) break;
-            void *hdst = pin_out ? static_cast<void *>(static_cast<char *>(io.direct_dst) + c * out_chunk) : s.h_out;
+            void *hdst = pin_out ? static_cast<void *>(static_cast<char *>(io.direct_dst) + out_off) : s.h_out;
             if ((e = cudaMemcpyAsync(hdst, cur, type_nbytes(t_out, ne), cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) break;
             if ((e = cudaEventRecord(s.done, s.stream)) != cudaSuccess) break;
         }

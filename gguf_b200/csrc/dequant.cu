@@ -41,9 +41,8 @@ static cudaError_t launch_dequant(const void *src, void *dst, size_t nblocks, cu
     const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
     size_t grid = DQ_MODE == 0 ? (size_t)dev.sm_count * ctas_per_sm : ntiles;
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, DQ_THREADS, SMEM, stream>>>(static_cast<const uint8_t *>(src),
-                                                       static_cast<typename FT::raw *>(dst), nblocks);
-    return cudaGetLastError();
+    return launch_pdl(kern, (unsigned)grid, DQ_THREADS, SMEM, stream, static_cast<const uint8_t *>(src),
+                      static_cast<typename FT::raw *>(dst), nblocks);
 }
 template <uint32_t T>
 static cudaError_t launch_dequant_fdt(uint32_t fdt, const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {

@@ -346,7 +346,9 @@ dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ d
         for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
         fence_barrier_init();
     }
+    pdl_launch_dependents();  // the next kernel may begin scheduling as our CTAs retire
     __syncthreads();
+    pdl_wait();               // the previous kernel in the stream is complete before any global access
 
     auto issue = [&](size_t i) {  // thread 0 only
         const size_t t = blockIdx.x + i * (size_t)gridDim.x;

@@ -223,6 +223,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Programmatic dependent launch (PDL): `pdl_launch_dependents` lets the next kernel in the stream start
+// scheduling its CTAs as ours retire; `pdl_wait` blocks until the previous kernel in the stream has
+// completed and flushed.  Every kernel calls pdl_wait before its first global access, so stream-order
+// semantics are unchanged; only launch latency and the prologue overlap the predecessor's tail.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Byte-exact cooperative copy global -> shared for tiles the bulk path cannot take (tail tile,
 // source not 16-byte aligned).  Never reads outside [g, g+n).
 __device__ __forceinline__ void cta_copy_g2s(uint8_t *s, const uint8_t *g, uint32_t n, int tid, int nthreads) {

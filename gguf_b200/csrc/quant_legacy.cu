@@ -469,6 +469,8 @@ quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, si
         g_issue += g_step;
         s_issue = (s_issue + 1 == QS) ? 0 : s_issue + 1;
     };
+    pdl_launch_dependents();
+    pdl_wait();  // previous kernel in the stream complete before the first global access
 #pragma unroll
     for (int i = 0; i < QS; i++) issue();
     cp_async_wait<QS - 1>();
@@ -524,8 +526,7 @@ static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cuda
     const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
     size_t grid = (size_t)dev.sm_count * ctas_per_sm;
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, QL_THREADS, SMEM, stream>>>(static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
-    return cudaGetLastError();
+    return launch_pdl(kern, (unsigned)grid, QL_THREADS, SMEM, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
 }
 
 template <uint32_t T>
@@ -565,47 +566,60 @@ template <> __device__ __forceinline__ float narrow_exact<F32>(float f) { return
 template <> __device__ __forceinline__ uint16_t narrow_exact<F16>(float f) { return f2h_exact(f); }
 template <> __device__ __forceinline__ uint16_t narrow_exact<BF16>(float f) { return f2bf_exact(f); }
 
+// Persistent CTAs over contiguous tiles of 8192 elements (each CTA reads/writes one contiguous 16-32 KB
+// range at a time: better DRAM row locality than a grid-wide stride).  A chunk is V elements with the
+// WIDER side exactly 16 bytes, so every warp access on either side is a contiguous run (no half-filled
+// sectors); U independent loads per thread are in flight before the first store.
+constexpr int CAST_THREADS = 256, CAST_TILE = 8192;
+template <int BYTES> struct VecOf;
+template <> struct VecOf<16> { using type = uint4; };
+template <> struct VecOf<8> { using type = uint2; };
 template <class ST, class DT>
-__global__ void __launch_bounds__(256) cast_kernel(const typename ST::raw *__restrict__ src, typename DT::raw *__restrict__ dst, size_t n) {
+__global__ void __launch_bounds__(CAST_THREADS) cast_kernel(const typename ST::raw *__restrict__ src, typename DT::raw *__restrict__ dst, size_t n) {
     using SR = typename ST::raw;
     using DR = typename DT::raw;
+    constexpr int WIDE = sizeof(SR) > sizeof(DR) ? sizeof(SR) : sizeof(DR);
+    constexpr int V = 16 / WIDE;                       // elements per chunk: 8 (16-bit <-> 16-bit) or 4
+    constexpr int U = CAST_TILE / (CAST_THREADS * V);  // chunks per thread per tile: 4 or 8
+    using SV = typename VecOf<V * sizeof(SR)>::type;
+    using DV = typename VecOf<V * sizeof(DR)>::type;
     const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
-    const size_t nchunks = n / 8;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t full_tiles = n / CAST_TILE;
     if (vec) {
-        for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
-            alignas(16) SR in[8];
-            if constexpr (sizeof(SR) == 4) {
-                *reinterpret_cast<uint4 *>(in) = __ldg(reinterpret_cast<const uint4 *>(src + c * 8));
-                *reinterpret_cast<uint4 *>(in + 4) = __ldg(reinterpret_cast<const uint4 *>(src + c * 8) + 1);
-            } else {
-                *reinterpret_cast<uint4 *>(in) = __ldg(reinterpret_cast<const uint4 *>(src + c * 8));
-            }
-            alignas(16) DR out[8];
+        for (size_t t = blockIdx.x; t < full_tiles; t += gridDim.x) {
+            const SR *sp = src + t * CAST_TILE + threadIdx.x * V;
+            DR *dp = dst + t * CAST_TILE + threadIdx.x * V;
+            alignas(16) SR in[U][V];
 #pragma unroll
-            for (int k = 0; k < 8; k++) out[k] = narrow_exact<DT>(widen_exact<ST>(in[k]));
-            if constexpr (sizeof(DR) == 4) {
-                *reinterpret_cast<uint4 *>(dst + c * 8) = *reinterpret_cast<uint4 *>(out);
-                *reinterpret_cast<uint4 *>(dst + c * 8 + 4) = *reinterpret_cast<uint4 *>(out + 4);
-            } else {
-                *reinterpret_cast<uint4 *>(dst + c * 8) = *reinterpret_cast<uint4 *>(out);
+            for (int u = 0; u < U; u++) *reinterpret_cast<SV *>(in[u]) = __ldg(reinterpret_cast<const SV *>(sp + u * CAST_THREADS * V));
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                alignas(16) DR out[V];
+#pragma unroll
+                for (int k = 0; k < V; k++) out[k] = narrow_exact<DT>(widen_exact<ST>(in[u][k]));
+                *reinterpret_cast<DV *>(dp + u * CAST_THREADS * V) = *reinterpret_cast<DV *>(out);
             }
         }
-        for (size_t i = nchunks * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-            dst[i] = narrow_exact<DT>(widen_exact<ST>(src[i]));
-    } else {
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-            dst[i] = narrow_exact<DT>(widen_exact<ST>(src[i]));
     }
+    // tail (and the whole range when a pointer is not 16-byte aligned): element-wise grid stride
+    const size_t start = vec ? full_tiles * CAST_TILE : 0;
+    for (size_t i = start + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = narrow_exact<DT>(widen_exact<ST>(src[i]));
 }
 
 template <class ST, class DT>
 static cudaError_t launch_cast(const void *src, void *dst, size_t n, cudaStream_t stream, DevInfo dev) {
-    size_t want = (n / 8 + 255) / 256;
-    size_t grid = (size_t)dev.sm_count * 8;
+    auto kern = cast_kernel<ST, DT>;
+    static int occ_cache[MAX_DEVICES];
+    int ctas_per_sm = 0;
+    cudaError_t e = cached_occupancy(kern, CAST_THREADS, 0, dev.device, occ_cache, &ctas_per_sm);
+    if (e != cudaSuccess) return e;
+    size_t want = (n + CAST_TILE - 1) / CAST_TILE;
+    size_t grid = (size_t)dev.sm_count * ctas_per_sm;
     if (grid > want) grid = want ? want : 1;
-    cast_kernel<ST, DT><<<(unsigned)grid, 256, 0, stream>>>(static_cast<const typename ST::raw *>(src), static_cast<typename DT::raw *>(dst), n);
-    return cudaGetLastError();
+    return launch_pdl(kern, (unsigned)grid, CAST_THREADS, 0, stream, static_cast<const typename ST::raw *>(src), static_cast<typename DT::raw *>(dst), n);
 }
 template <class ST>
 static cudaError_t launch_cast_dst(uint32_t dst_dt, const void *src, void *dst, size_t n, cudaStream_t stream, DevInfo dev) {
