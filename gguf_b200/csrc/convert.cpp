@@ -20,6 +20,7 @@
 #include <cctype>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -219,7 +220,8 @@ int ggq_convert_gguf(const char *in_path, const char *out_path, const char *step
 
         // ---- convert: largest tensors first; WORKERS_PER_DEVICE threads per GPU, each with its own
         // stream pipeline, so one tensor's pread overlaps another's kernels / D2H / pwrite ----
-        constexpr int WORKERS_PER_DEVICE = 3;
+        int WORKERS_PER_DEVICE = 4;  // GGQ_CONVERT_WORKERS overrides (file I/O is the bound, not the GPU)
+        if (const char *wenv = getenv("GGQ_CONVERT_WORKERS")) { const int v = atoi(wenv); if (v >= 1 && v <= 32) WORKERS_PER_DEVICE = v; }
         std::vector<size_t> order(nt);
         for (size_t i = 0; i < nt; i++) order[i] = i;
         std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return f.tensors[a].nbytes > f.tensors[b].nbytes; });

@@ -227,3 +227,29 @@ def test_block_range_sharding_over_all_gpus_same_bytes(ggq, oracle):
         assert np.array_equal(ggq.dequantize(2, want, F16), oracle.dequantize(2, F16, want, threads=8))
     finally:
         assert lib().ggq_set_shard_devices(1) == 1
+
+
+def test_more_than_2_31_elements_device_path(ggq, oracle):
+    """Index arithmetic past 2^31 elements / 4 GiB of output (device API, Q4_0 <-> f16): slices at the
+    start, across the 2^31 boundary and at the ragged end are compared with the oracle."""
+    import torch
+    n = (1 << 31) + 32 * 8 * 5 + 32 * 3          # not a multiple of a tile
+    nb = n // 32
+    st = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator(device="cuda"); gen.manual_seed(5)
+    x = torch.empty(n, dtype=torch.float16, device="cuda")
+    step = 1 << 28
+    for o in range(0, n, step):
+        m = min(step, n - o)
+        x[o:o + m] = (torch.randn(m, device="cuda", generator=gen) * 0.02).to(torch.float16)
+    q = torch.empty(nb * 18, dtype=torch.uint8, device="cuda")
+    ggq.quantize_slice_device(2, F16, q, nb, x, n, st)
+    y = torch.empty(n, dtype=torch.float16, device="cuda")
+    ggq.dequantize_slice_device(2, F16, y, n, q, nb, st)
+    torch.cuda.synchronize()
+    for b0 in (0, (1 << 31) // 32 - 700, nb - 1500):
+        b1 = min(nb, b0 + 1500)
+        xs = x[b0 * 32:b1 * 32].cpu().numpy().view(np.uint16)
+        want_q = oracle.quantize(2, F16, xs)
+        assert np.array_equal(q[b0 * 18:b1 * 18].cpu().numpy(), want_q), b0
+        assert np.array_equal(y[b0 * 32:b1 * 32].cpu().numpy().view(np.uint16), oracle.dequantize(2, F16, want_q)), b0
