@@ -363,6 +363,11 @@ int run_host(bool quant, const Plan &p, void *dst, const void *src) {
 int run_device(bool quant, const Plan &p, void *dst, const void *src, void *stream) {
     if (p.nblocks == 0) return GGQ_OK;
     if (!dst || !src) return fail(GGQ_ERR_INVALID, "null pointer with non-zero length");
+    // cast.rs:163-177 `reslice` panics on a misaligned slice; here: the float side needs its element
+    // alignment, the packed side 2 bytes (every block starts with or contains f16 fields)
+    const void *fl = quant ? src : dst, *pk = quant ? dst : src;
+    if ((reinterpret_cast<uintptr_t>(fl) & (fdt_size(p.fdt) - 1)) || (reinterpret_cast<uintptr_t>(pk) & 1))
+        return fail(GGQ_ERR_INVALID, "data is not aligned");
     DevInfo dev;
     int rc = resolve_device(&dev);
     if (rc != GGQ_OK) return rc;

@@ -253,3 +253,48 @@ def test_more_than_2_31_elements_device_path(ggq, oracle):
         want_q = oracle.quantize(2, F16, xs)
         assert np.array_equal(q[b0 * 18:b1 * 18].cpu().numpy(), want_q), b0
         assert np.array_equal(y[b0 * 32:b1 * 32].cpu().numpy().view(np.uint16), oracle.dequantize(2, F16, want_q)), b0
+
+
+def test_device_api_rejects_misaligned_pointers(ggq):
+    """cast.rs:163-177: a slice that is not aligned for its element type is refused, not faulted on."""
+    import torch
+    buf = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    with pytest.raises(ggq.GgqError) as e:
+        ggq.quantize_slice_device(8, F32, out, 2, buf.data_ptr() + 2, 64, 0)     # f32 at a 2-byte offset
+    assert e.value.code == -3
+    with pytest.raises(ggq.GgqError):
+        ggq.dequantize_slice_device(8, F16, out.data_ptr() + 1, 64, buf, 2, 0)   # f16 at an odd address
+    with pytest.raises(ggq.GgqError):
+        ggq.dequantize_slice_device(8, F16, out, 64, buf.data_ptr() + 1, 2, 0)   # packed blocks at an odd address
+    ggq.quantize_slice_device(8, F32, out, 2, buf.data_ptr() + 4, 64, 0)         # 4-byte aligned f32 is fine
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("fdt", FDTS)
+@pytest.mark.parametrize("ty", ALLQ)
+def test_every_kernel_ragged_with_guard_zones(ggq, oracle, ty, fdt):
+    """compute-sanitizer is closed on this pool, so bounds are checked the hard way: every kernel runs
+    on a ragged block count, at 16-byte-aligned and at merely element-aligned device pointers, inside
+    buffers whose guard zones (64 bytes either side) must stay untouched."""
+    import torch
+    n, b = oracle.block_info(ty)
+    nb = (300 if n == 32 else 70) + 3
+    x = to_fdt(gaussian(n * nb, ty * 7 + fdt), fdt)
+    want_q = oracle.quantize(ty, fdt, x)
+    want_d = oracle.dequantize(ty, fdt, want_q)
+    st = torch.cuda.current_stream().cuda_stream
+    G = 64
+    for off in (0, 4 if fdt == F32 else 2):
+        src = torch.zeros(x.nbytes + 2 * G, dtype=torch.uint8, device="cuda")
+        src[G + off:G + off + x.nbytes] = torch.from_numpy(x.view(np.uint8)).cuda()
+        q = torch.full((nb * b + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        ggq.quantize_slice_device(ty, fdt, q.data_ptr() + G + off, nb, src.data_ptr() + G + off, n * nb, st)
+        d = torch.full((x.nbytes + 2 * G,), 0x5A, dtype=torch.uint8, device="cuda")
+        ggq.dequantize_slice_device(ty, fdt, d.data_ptr() + G + off, n * nb, q.data_ptr() + G + off, nb, st)
+        torch.cuda.synchronize()
+        gq, gd = q.cpu().numpy(), d.cpu().numpy()
+        assert same_blocks(gq[G + off:G + off + nb * b], want_q, ty, b)
+        assert same_floats(gd[G + off:G + off + x.nbytes].view(want_d.dtype), want_d)
+        assert (gq[:G + off] == 0xA5).all() and (gq[G + off + nb * b:] == 0xA5).all(), "quantize wrote outside dst"
+        assert (gd[:G + off] == 0x5A).all() and (gd[G + off + x.nbytes:] == 0x5A).all(), "dequantize wrote outside dst"
