@@ -7,7 +7,10 @@
 
 #include <atomic>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -205,35 +208,85 @@ void release_pipeline(Pipeline *p) {
     g_pool.push_back(p);
 }
 
-bool is_pinned(const void *p) {
+// cudaMemoryTypeHost = page-locked (DMA-able); Unregistered = ordinary pageable memory
+cudaMemoryType pointer_kind(const void *p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
         cudaGetLastError();
-        return false;
+        return cudaMemoryTypeUnregistered;
     }
-    return a.type == cudaMemoryTypeHost;
+    return a.type;
 }
+bool is_pinned(const void *p) { return pointer_kind(p) == cudaMemoryTypeHost; }
+
+// ---- persistent copy pool: bounce copies between pageable caller memory and the pinned staging
+// buffers are split over a few long-lived worker threads (spawning threads per 16-32 MB chunk cost as
+// much as the copy itself).  The pool is created on first use and intentionally never destroyed.
+class CopyPool {
+   public:
+    static CopyPool &get() {
+        static CopyPool *p = new CopyPool();
+        return *p;
+    }
+    int size() const { return (int)workers_.size(); }
+    // run fn(0..parts-1), part 0 on the calling thread, and return when all parts are done
+    void run(int parts, const std::function<void(int)> &fn) {
+        if (parts <= 1) { if (parts == 1) fn(0); return; }
+        struct Job { std::mutex mu; std::condition_variable cv; int pending; } job;
+        job.pending = parts - 1;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (int i = 1; i < parts; i++)
+                q_.push_back([&job, &fn, i] {
+                    fn(i);
+                    std::lock_guard<std::mutex> lk(job.mu);
+                    if (--job.pending == 0) job.cv.notify_one();
+                });
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lk(job.mu);
+        job.cv.wait(lk, [&] { return job.pending == 0; });
+    }
+
+   private:
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int n = hw ? (int)std::min(8u, std::max(2u, hw / 2)) : 4;
+        for (int i = 0; i < n; i++)
+            workers_.emplace_back([this] {
+                for (;;) {
+                    std::function<void()> f;
+                    {
+                        std::unique_lock<std::mutex> lk(mu_);
+                        cv_.wait(lk, [&] { return !q_.empty(); });
+                        f = std::move(q_.front());
+                        q_.pop_front();
+                    }
+                    f();
+                }
+            });
+        for (auto &t : workers_) t.detach();
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    std::vector<std::thread> workers_;
+};
 
 void parallel_memcpy(void *dst, const void *src, size_t n) {
-    constexpr size_t MIN_PER_THREAD = size_t(2) << 20;
-    unsigned hw = std::thread::hardware_concurrency();
-    size_t nt = n / MIN_PER_THREAD;
-    if (nt > 8) nt = 8;
-    if (hw && nt > hw) nt = hw;
-    if (nt <= 1) {
+    constexpr size_t MIN_PER_PART = size_t(1) << 20;
+    CopyPool &pool = CopyPool::get();
+    const int parts = (int)std::min<size_t>((size_t)pool.size() + 1, std::max<size_t>(1, n / MIN_PER_PART));
+    if (parts <= 1) {
         memcpy(dst, src, n);
         return;
     }
-    const size_t per = ((n + nt - 1) / nt + 63) & ~size_t(63);
-    std::vector<std::thread> th;
-    for (size_t t = 1; t < nt; t++) {
-        const size_t o = t * per;
-        if (o >= n) break;
-        const size_t len = o + per > n ? n - o : per;
-        th.emplace_back([=] { memcpy(static_cast<char *>(dst) + o, static_cast<const char *>(src) + o, len); });
-    }
-    memcpy(dst, src, per < n ? per : n);
-    for (auto &t : th) t.join();
+    const size_t per = ((n + parts - 1) / parts + 4095) & ~size_t(4095);
+    pool.run(parts, [=](int k) {
+        const size_t o = (size_t)k * per;
+        if (o < n) memcpy(static_cast<char *>(dst) + o, static_cast<const char *>(src) + o, std::min(per, n - o));
+    });
 }
 
 // Runs one cast chain over `n_elems` elements: chunks of CHUNK_ELEMS elements flow through NSLOTS
@@ -316,7 +369,10 @@ int run_chain_host(const std::vector<uint32_t> &chain, void *dst, const void *sr
         memmove(dst, src, type_nbytes(chain.front(), n_elems));
         return GGQ_OK;
     }
-    const bool pin_src = is_pinned(src), pin_dst = is_pinned(dst);
+    const cudaMemoryType ks = pointer_kind(src), kd = pointer_kind(dst);
+    if (ks == cudaMemoryTypeDevice || kd == cudaMemoryTypeDevice)
+        return fail(GGQ_ERR_INVALID, "device pointer passed to a host-pointer entry point (use the *_device variants)");
+    const bool pin_src = ks == cudaMemoryTypeHost, pin_dst = kd == cudaMemoryTypeHost;
     auto make_io = [&](size_t elem0) {  // the sub-tensor starting at element `elem0`
         const char *s0 = static_cast<const char *>(src) + type_nbytes(chain.front(), elem0);
         char *d0 = static_cast<char *>(dst) + type_nbytes(chain.back(), elem0);

@@ -298,3 +298,12 @@ def test_every_kernel_ragged_with_guard_zones(ggq, oracle, ty, fdt):
         assert same_floats(gd[G + off:G + off + x.nbytes].view(want_d.dtype), want_d)
         assert (gq[:G + off] == 0xA5).all() and (gq[G + off + nb * b:] == 0xA5).all(), "quantize wrote outside dst"
         assert (gd[:G + off] == 0x5A).all() and (gd[G + off + x.nbytes:] == 0x5A).all(), "dequantize wrote outside dst"
+
+
+def test_host_api_rejects_device_pointers(ggq):
+    import ctypes, torch
+    from gguf_b200._lib import lib
+    d = torch.zeros(64, dtype=torch.float32, device="cuda")
+    out = np.zeros(2 * 34, np.uint8)
+    rc = lib().ggq_quantize_slice(8, 0, out.ctypes.data, 2, d.data_ptr(), 64)
+    assert rc == -3 and b"device pointer" in lib().ggq_last_error()

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "dequant_kernel.cuh"
+#include "ggq_kernels.h"
 
 using namespace ggq;
 
@@ -55,11 +56,11 @@ void run_variant(const char *tname, size_t n_elems, uint8_t *const *in, void *co
     const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
     size_t grid = MODE == 0 ? (size_t)g_sms * occ : ntiles;
     if (grid > ntiles) grid = ntiles;
-    for (int i = 0; i < 3; i++) kern<<<(unsigned)grid, THREADS, SMEM>>>(in[i % NSETS], (typename FT::raw *)out[i % NSETS], nblocks);
+    for (int i = 0; i < 3; i++) CK(launch_pdl(kern, (unsigned)grid, THREADS, SMEM, (cudaStream_t)0, (const uint8_t *)in[i % NSETS], (typename FT::raw *)out[i % NSETS], nblocks));
     CK(cudaDeviceSynchronize());
     Timer t;
     t.start();
-    for (int i = 0; i < iters; i++) kern<<<(unsigned)grid, THREADS, SMEM>>>(in[i % NSETS], (typename FT::raw *)out[i % NSETS], nblocks);
+    for (int i = 0; i < iters; i++) CK(launch_pdl(kern, (unsigned)grid, THREADS, SMEM, (cudaStream_t)0, (const uint8_t *)in[i % NSETS], (typename FT::raw *)out[i % NSETS], nblocks));
     const float ms = t.stop();
     CK(cudaGetLastError());
     const double bytes = (double)nblocks * TR::BYTES + (double)n_elems * FT::SIZE;
@@ -104,39 +105,22 @@ int main(int argc, char **argv) {
     }
 
 #define V(T, NAME, N, TILE, ST, THR, MINB, MODE, SP) run_variant<T, F16, TILE, ST, THR, MINB, MODE, SP>(NAME, N, in, out, iters)
+#define SWEEP(T, NAME, N)                      \
+    V(T, NAME, N, 8192, 3, 256, 3, 0, 0);      \
+    V(T, NAME, N, 8192, 2, 256, 3, 0, 0);      \
+    V(T, NAME, N, 8192, 4, 256, 3, 0, 0);      \
+    V(T, NAME, N, 16384, 3, 256, 3, 0, 0);     \
+    V(T, NAME, N, 16384, 2, 256, 3, 0, 0);     \
+    V(T, NAME, N, 4096, 3, 128, 6, 0, 0);      \
+    V(T, NAME, N, 8192, 3, 128, 6, 0, 0);      \
+    V(T, NAME, N, 16384, 3, 512, 1, 0, 0);     \
+    V(T, NAME, N, 8192, 3, 256, 4, 0, 0);      \
+    V(T, NAME, N, 8192, 3, 256, 2, 0, 0);
     for (size_t n : {FFN, ATTN}) {
-        // shipped
-        V(T_Q4_0, "Q4_0", n, 16384, 3, 256, 3, 0, 0);
-        // tile / stage sweep, persistent ring
-        V(T_Q4_0, "Q4_0", n, 8192, 3, 256, 3, 0, 0);
-        V(T_Q4_0, "Q4_0", n, 4096, 3, 256, 3, 0, 0);
-        V(T_Q4_0, "Q4_0", n, 8192, 2, 256, 3, 0, 0);
-        V(T_Q4_0, "Q4_0", n, 4096, 2, 256, 4, 0, 0);
-        V(T_Q4_0, "Q4_0", n, 4096, 4, 128, 8, 0, 0);
-        V(T_Q4_0, "Q4_0", n, 8192, 3, 512, 2, 0, 0);
-        V(T_Q4_0, "Q4_0", n, 16384, 2, 512, 2, 0, 0);
-        // streaming stores
-        V(T_Q4_0, "Q4_0", n, 16384, 3, 256, 3, 0, 1);
-        V(T_Q4_0, "Q4_0", n, 8192, 3, 256, 3, 0, 1);
-        // one tile per CTA
-        V(T_Q4_0, "Q4_0", n, 4096, 1, 256, 4, 1, 0);
-        V(T_Q4_0, "Q4_0", n, 8192, 1, 256, 4, 1, 0);
-        V(T_Q4_0, "Q4_0", n, 2048, 1, 128, 8, 1, 0);
-        V(T_Q4_0, "Q4_0", n, 4096, 1, 128, 8, 1, 0);
-        V(T_Q4_0, "Q4_0", n, 4096, 1, 256, 4, 1, 1);
-        // other headline types: shipped + best guesses
-        V(T_Q8_0, "Q8_0", n, 8192, 3, 256, 3, 0, 0);
-        V(T_Q8_0, "Q8_0", n, 4096, 3, 256, 3, 0, 0);
-        V(T_Q8_0, "Q8_0", n, 4096, 1, 256, 4, 1, 0);
-        V(T_Q8_0, "Q8_0", n, 8192, 3, 256, 3, 0, 1);
-        V(T_Q4K, "Q4K", n, 16384, 3, 256, 3, 0, 0);
-        V(T_Q4K, "Q4K", n, 8192, 3, 256, 3, 0, 0);
-        V(T_Q4K, "Q4K", n, 4096, 1, 256, 4, 1, 0);
-        V(T_Q4K, "Q4K", n, 16384, 3, 256, 3, 0, 1);
-        V(T_Q6K, "Q6K", n, 16384, 3, 256, 3, 0, 0);
-        V(T_Q6K, "Q6K", n, 8192, 3, 256, 3, 0, 0);
-        V(T_Q6K, "Q6K", n, 4096, 1, 256, 4, 1, 0);
-        V(T_Q6K, "Q6K", n, 16384, 3, 256, 3, 0, 1);
+        SWEEP(T_Q4_0, "Q4_0", n)
+        SWEEP(T_Q8_0, "Q8_0", n)
+        SWEEP(T_Q4K, "Q4K", n)
+        SWEEP(T_Q6K, "Q6K", n)
     }
     return 0;
 }
