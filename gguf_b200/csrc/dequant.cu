@@ -5,7 +5,7 @@
 // dequant_kernel.cuh).
 //
 // Shape of the kernel (HBM-bound streaming codec, no tensor cores):
-//   * persistent CTAs, static round-robin over tiles of TILE_ELEMS elements;
+//   * persistent CTAs, static round-robin over tiles of TILE_ELEMS elements (size-adaptive, see below);
 //   * the packed bytes of a tile are one contiguous range -> one 1-D bulk async copy (TMA engine,
 //     `cp.async.bulk`, SASS UBLKCP) per tile into a STAGES-deep shared-memory ring guarded by
 //     mbarriers, issued STAGES tiles ahead by one thread — no LSU instructions or registers spent on loads;
@@ -18,32 +18,56 @@
 
 namespace ggq {
 
-// shipped configuration (chosen with tools/dq_sweep.cu)
-constexpr int DQ_THREADS = 256;
-constexpr int DQ_STAGES = 3;
-constexpr int DQ_MINB = 3;
-constexpr int DQ_MODE = 0;
-constexpr int DQ_SP = 0;
-template <uint32_t T> struct DqTile { static constexpr int ELEMS = 8192; };
-template <> struct DqTile<T_Q6K> { static constexpr int ELEMS = 16384; };
+// Shipped configurations, chosen with tools/dq_sweep.cu (profiles/r01_dq_sweep_pdl*.txt; repeatable to
+// +-0.3 %).  Tensors of >= DQ_BIG_ELEMS elements take the BIG config (bigger tiles, fewer stages, 512-
+// thread CTAs: less per-tile overhead once ramp/tail no longer matter), smaller ones the SMALL config
+// (more, smaller tiles: better balance on 8-10 us launches).
+struct DqCfgDefault { static constexpr int TILE = 8192, STAGES = 3, THREADS = 256, MINB = 3; };
+template <uint32_t T> struct DqBig : DqCfgDefault {};
+template <uint32_t T> struct DqSmall : DqCfgDefault {};
+struct DqCfg32k2x512 { static constexpr int TILE = 32768, STAGES = 2, THREADS = 512, MINB = 1; };
+struct DqCfg16k3x512 { static constexpr int TILE = 16384, STAGES = 3, THREADS = 512, MINB = 1; };
+struct DqCfg16k2x512 { static constexpr int TILE = 16384, STAGES = 2, THREADS = 512, MINB = 1; };
+struct DqCfg16k3x256 { static constexpr int TILE = 16384, STAGES = 3, THREADS = 256, MINB = 3; };
+struct DqCfg8k2x256 { static constexpr int TILE = 8192, STAGES = 2, THREADS = 256, MINB = 3; };
+template <> struct DqBig<T_Q8_0> : DqCfg32k2x512 {};
+template <> struct DqBig<T_Q8_1> : DqCfg32k2x512 {};
+template <> struct DqBig<T_Q8K> : DqCfg32k2x512 {};
+template <> struct DqSmall<T_Q8_0> : DqCfg8k2x256 {};
+template <> struct DqSmall<T_Q8_1> : DqCfg8k2x256 {};
+template <> struct DqSmall<T_Q8K> : DqCfg8k2x256 {};
+template <> struct DqBig<T_Q4K> : DqCfg16k3x512 {};
+template <> struct DqBig<T_Q5K> : DqCfg32k2x512 {};
+template <> struct DqBig<T_Q3K> : DqCfg16k3x256 {};
+template <> struct DqBig<T_Q2K> : DqCfg16k2x512 {};
+template <> struct DqBig<T_Q6K> : DqCfg16k3x256 {};
+template <> struct DqSmall<T_Q6K> : DqCfg16k3x256 {};
+constexpr size_t DQ_BIG_ELEMS = size_t(32) << 20;
+constexpr int DQ_MODE = 0, DQ_SP = 0;
+
+template <uint32_t T, class FT, class CFG>
+static cudaError_t launch_dequant_cfg(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
+    using TR = BlockTraits<T>;
+    constexpr int TILE_BLOCKS = CFG::TILE / TR::ELEMS;
+    constexpr int SMEM = dequant_smem_bytes<T, CFG::TILE, CFG::STAGES, DQ_MODE>();
+    auto kern = dequant_kernel<T, FT, CFG::TILE, CFG::STAGES, CFG::THREADS, CFG::MINB, DQ_MODE, DQ_SP>;
+    static int occ_cache[MAX_DEVICES];  // per instantiation, per device
+    int ctas_per_sm = 0;
+    cudaError_t e = cached_occupancy(kern, CFG::THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
+    if (e != cudaSuccess) return e;
+    const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
+    size_t grid = (size_t)dev.sm_count * ctas_per_sm;
+    if (grid > ntiles) grid = ntiles;
+    return launch_pdl(kern, (unsigned)grid, CFG::THREADS, SMEM, stream, static_cast<const uint8_t *>(src),
+                      static_cast<typename FT::raw *>(dst), nblocks);
+}
 
 template <uint32_t T, class FT>
 static cudaError_t launch_dequant(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
-    using TR = BlockTraits<T>;
-    constexpr int TILE = DqTile<T>::ELEMS;
-    constexpr int TILE_BLOCKS = TILE / TR::ELEMS;
-    constexpr int SMEM = dequant_smem_bytes<T, TILE, DQ_STAGES, DQ_MODE>();
-    auto kern = dequant_kernel<T, FT, TILE, DQ_STAGES, DQ_THREADS, DQ_MINB, DQ_MODE, DQ_SP>;
-    static int occ_cache[MAX_DEVICES];  // per (T, FT) instantiation, per device
-    int ctas_per_sm = 0;
-    cudaError_t e = cached_occupancy(kern, DQ_THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
-    if (e != cudaSuccess) return e;
-    const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
-    size_t grid = DQ_MODE == 0 ? (size_t)dev.sm_count * ctas_per_sm : ntiles;
-    if (grid > ntiles) grid = ntiles;
-    return launch_pdl(kern, (unsigned)grid, DQ_THREADS, SMEM, stream, static_cast<const uint8_t *>(src),
-                      static_cast<typename FT::raw *>(dst), nblocks);
+    if (nblocks * (size_t)BlockTraits<T>::ELEMS >= DQ_BIG_ELEMS) return launch_dequant_cfg<T, FT, DqBig<T>>(src, dst, nblocks, stream, dev);
+    return launch_dequant_cfg<T, FT, DqSmall<T>>(src, dst, nblocks, stream, dev);
 }
+
 template <uint32_t T>
 static cudaError_t launch_dequant_fdt(uint32_t fdt, const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
     switch (fdt) {

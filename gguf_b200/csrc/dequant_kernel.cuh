@@ -27,8 +27,22 @@ template <class FT, int SP> __device__ __forceinline__ void emit_p(typename FT::
 // ---- word-level helpers -----------------------------------------------------------------------
 // NW 32-bit words from shared memory at ALIGN-byte alignment
 template <int NW, int ALIGN> __device__ __forceinline__ void lds_words(const uint8_t *p, uint32_t (&w)[NW]) {
+    if constexpr (ALIGN >= 4) {
 #pragma unroll
-    for (int i = 0; i < NW; i++) w[i] = lds32<ALIGN>(p + 4 * i);
+        for (int i = 0; i < NW; i++) w[i] = *reinterpret_cast<const uint32_t *>(p + 4 * i);
+    } else {
+        // 2-byte aligned (18/22/34/110/210/290-byte blocks): NW+1 aligned words and a funnel shift
+        // instead of 2*NW halfword loads.  May touch up to 2 bytes before / 4 bytes after the range:
+        // always inside the stage ring, which is padded by 16 bytes (dequant_smem_bytes).
+        const uint32_t a = smem_u32(p);
+        const uint32_t sh = (a & 2u) << 3;
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p - (a & 2u));
+        uint32_t t[NW + 1];
+#pragma unroll
+        for (int i = 0; i <= NW; i++) t[i] = q[i];
+#pragma unroll
+        for (int i = 0; i < NW; i++) w[i] = __funnelshift_r(t[i], t[i + 1], sh);
+    }
 }
 // exact float(byte k of w) - bias: PRMT drops the byte into the mantissa of 2^23, one FADD removes it
 __device__ __forceinline__ float bytef(uint32_t w, int k, float bias) {
@@ -392,7 +406,7 @@ dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ d
 }
 
 template <uint32_t T, int TILE_ELEMS, int STAGES, int MODE> constexpr int dequant_smem_bytes() {
-    return 128 + (MODE == 0 ? STAGES : 1) * (TILE_ELEMS / BlockTraits<T>::ELEMS) * BlockTraits<T>::BYTES;
+    return 128 + (MODE == 0 ? STAGES : 1) * (TILE_ELEMS / BlockTraits<T>::ELEMS) * BlockTraits<T>::BYTES + 16;
 }
 
 }  // namespace ggq

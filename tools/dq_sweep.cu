@@ -108,19 +108,19 @@ int main(int argc, char **argv) {
 #define SWEEP(T, NAME, N)                      \
     V(T, NAME, N, 8192, 3, 256, 3, 0, 0);      \
     V(T, NAME, N, 8192, 2, 256, 3, 0, 0);      \
-    V(T, NAME, N, 8192, 4, 256, 3, 0, 0);      \
     V(T, NAME, N, 16384, 3, 256, 3, 0, 0);     \
     V(T, NAME, N, 16384, 2, 256, 3, 0, 0);     \
-    V(T, NAME, N, 4096, 3, 128, 6, 0, 0);      \
-    V(T, NAME, N, 8192, 3, 128, 6, 0, 0);      \
+    V(T, NAME, N, 16384, 2, 512, 1, 0, 0);     \
     V(T, NAME, N, 16384, 3, 512, 1, 0, 0);     \
-    V(T, NAME, N, 8192, 3, 256, 4, 0, 0);      \
-    V(T, NAME, N, 8192, 3, 256, 2, 0, 0);
-    for (size_t n : {FFN, ATTN}) {
-        SWEEP(T_Q4_0, "Q4_0", n)
-        SWEEP(T_Q8_0, "Q8_0", n)
-        SWEEP(T_Q4K, "Q4K", n)
-        SWEEP(T_Q6K, "Q6K", n)
-    }
+    V(T, NAME, N, 8192, 2, 512, 1, 0, 0);      \
+    V(T, NAME, N, 32768, 2, 512, 1, 0, 0);
+    for (int rep = 0; rep < 3; rep++)
+        for (size_t n : {FFN, ATTN}) {
+            SWEEP(T_Q8_0, "Q8_0", n)
+            SWEEP(T_Q2K, "Q2K", n)
+            SWEEP(T_Q3K, "Q3K", n)
+            SWEEP(T_Q4K, "Q4K", n)
+            SWEEP(T_Q5K, "Q5K", n)
+        }
     return 0;
 }
