@@ -49,20 +49,23 @@ template <> struct Row<F32> {
 };
 template <> struct Row<BF16> {
     float x[32];
+    uint32_t raw[16];  // bf16 pairs (x[2k], x[2k+1])
     __device__ __forceinline__ void zero() {
 #pragma unroll
         for (int k = 0; k < 32; k++) x[k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 16; k++) raw[k] = 0u;
     }
     __device__ __forceinline__ void load(const uint8_t *s) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const uint4 v = *reinterpret_cast<const uint4 *>(s + 16 * i);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            raw[4 * i] = v.x; raw[4 * i + 1] = v.y; raw[4 * i + 2] = v.z; raw[4 * i + 3] = v.w;
+        }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                x[8 * i + 2 * k] = __uint_as_float(w[k] << 16);
-                x[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
-            }
+        for (int k = 0; k < 16; k++) {
+            x[2 * k] = __uint_as_float(raw[k] << 16);
+            x[2 * k + 1] = __uint_as_float(raw[k] & 0xFFFF0000u);
         }
     }
 };
@@ -144,6 +147,39 @@ template <> __device__ __forceinline__ void row_min_max<F16>(const Row<F16> &r, 
     }
     mn = fminf(F32_MAX, fminf(__low2float(lo), __high2float(lo)));
     mx = fmaxf(-F32_MAX, fmaxf(__low2float(hi), __high2float(hi)));
+}
+
+// bf16 input: the same packed folds with the bf16x2 min/max instructions (NaN operands are dropped)
+__device__ __forceinline__ float bf_lo(__nv_bfloat162 v) { return __uint_as_float((*reinterpret_cast<uint32_t *>(&v)) << 16); }
+__device__ __forceinline__ float bf_hi(__nv_bfloat162 v) { return __uint_as_float((*reinterpret_cast<uint32_t *>(&v)) & 0xFFFF0000u); }
+__device__ __forceinline__ __nv_bfloat162 bf_pair(uint32_t w) { return *reinterpret_cast<const __nv_bfloat162 *>(&w); }
+template <> __device__ __forceinline__ float row_max_abs<BF16>(const Row<BF16> &r) {
+    __nv_bfloat162 a = bf_pair(0u);
+#pragma unroll
+    for (int k = 0; k < 16; k++) a = __hmax2(a, bf_pair(r.raw[k] & 0x7FFF7FFFu));
+    return fmaxf(bf_lo(a), bf_hi(a));
+}
+template <> __device__ __forceinline__ void row_pos_neg<BF16>(const Row<BF16> &r, float &P, float &N) {
+    __nv_bfloat162 p = bf_pair(0u), n = p;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const __nv_bfloat162 v = bf_pair(r.raw[k]);
+        p = __hmax2(p, v);
+        n = __hmin2(n, v);
+    }
+    P = fmaxf(bf_lo(p), bf_hi(p));
+    N = fminf(bf_lo(n), bf_hi(n));
+}
+template <> __device__ __forceinline__ void row_min_max<BF16>(const Row<BF16> &r, float &mn, float &mx) {
+    __nv_bfloat162 lo = bf_pair(0x7F807F80u), hi = bf_pair(0xFF80FF80u);  // +inf, -inf
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const __nv_bfloat162 v = bf_pair(r.raw[k]);
+        lo = __hmin2(lo, v);
+        hi = __hmax2(hi, v);
+    }
+    mn = fminf(F32_MAX, fminf(bf_lo(lo), bf_hi(lo)));
+    mx = fmaxf(-F32_MAX, fmaxf(bf_lo(hi), bf_hi(hi)));
 }
 
 // max_by_abs (structs.rs:96-100) over G lanes x 32 elements: the FIRST x with strictly greatest |x|.
@@ -283,16 +319,21 @@ template <> struct Encoder<T_Q4_1> {
     }
 };
 
-// 5-bit codes (< 32, low byte of c[]) -> qh (bit i = bit 4 of code i) and the 16 nibble bytes
+// 5-bit codes (< 32, low byte of c[]) -> qh (bit i = bit 4 of code i) and the 16 nibble bytes, done on
+// words of four codes: low nibbles by mask, the four high bits of a word are compressed to a nibble
+// with one multiply ((h0 + h1<<8 + h2<<16 + h3<<24) * 0x01020408 puts h0..h3 at bits 24..27, no carries).
 __device__ __forceinline__ void pack5(const uint32_t *c, uint32_t &qh, uint32_t *w) {
-    uint32_t n[32];
+    uint32_t lo[8];
     qh = 0;
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
-        qh |= ((c[i] >> 4) & 1u) << i;
-        n[i] = c[i] & 15u;
+    for (int k = 0; k < 8; k++) {
+        const uint32_t W = gather_b0(c[4 * k], c[4 * k + 1], c[4 * k + 2], c[4 * k + 3]);
+        lo[k] = W & 0x0F0F0F0Fu;
+        const uint32_t hb = (W >> 4) & 0x01010101u;
+        qh |= ((hb * 0x01020408u) >> 24) << (4 * k);
     }
-    nibble_bytes(n, w);
+#pragma unroll
+    for (int j = 0; j < 4; j++) w[j] = lo[j] | (lo[j + 4] << 4);  // byte i = code[i] & 15 | (code[i+16] & 15) << 4
 }
 
 // q5_0.rs:26-58
@@ -396,9 +437,11 @@ template <> struct Encoder<T_Q8K> {
             int q[32];
 #pragma unroll
             for (int i = 0; i < 32; i++) {
-                // (x*recip).round().min(127.) as i8 : NaN.round() is NaN and NaN.min(127.) is 127
+                // (x*recip).round().min(127.) as i8 : NaN.round() is NaN and NaN.min(127.) is 127.
+                // trunc(min(t, 127)) == min(trunc(t), 127) and fminf drops a NaN t, so no branch.
                 const float p = __fmul_rn(r.x[i], rc);
-                q[i] = (p != p) ? 127 : min(round_half_away(p), 127);
+                const float h = __uint_as_float((__float_as_uint(p) & 0x80000000u) | 0x3F000000u);  // copysign(0.5, p)
+                q[i] = __float2int_rz(fminf(__fadd_rz(p, h), 127.0f));
             }
 #pragma unroll
             for (int k = 0; k < 8; k++) w[k] = pack_sat_s8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
