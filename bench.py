@@ -101,6 +101,31 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank to the CPUs nearest its GPU (NVML affinity) BEFORE any pinned allocation, so the
+    staging buffers are first-touched on the local NUMA node.  Best effort; returns a description."""
+    if os.environ.get("GGQ_BENCH_NO_BIND"):
+        return "disabled"
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [i * 64 + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            return f"{len(allowed)} cpus [{allowed[0]}..{allowed[-1]}]"
+        return "no narrower affinity reported"
+    except Exception as e:  # noqa: BLE001
+        return f"unavailable ({type(e).__name__})"
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -167,6 +192,7 @@ def ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else "single rank"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = lib()
@@ -306,7 +332,7 @@ def ours(args, rank, world, local_rank):
             "dtype": "u8/f32->f16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "bytes_per_step_per_gpu": step_bytes,
                        "l2": "per-step footprint (packed+f16 of 8 tensors = %.0f MB) exceeds the 126 MB L2; no flush needed" % (step_bytes / 1e6),
-                       "sharding": "by tensor, one replica of the workload per GPU, no collective"},
+                       "sharding": "by tensor, one replica of the workload per GPU, no collective", "cpu_binding_rank0": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "frac_of_peak_whole_step": value / world / peak, "per_kernel": per_kernel,
         }
