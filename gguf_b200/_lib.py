@@ -34,6 +34,11 @@ SYMBOLS = [
 
 
 
+class SliceJob(_c.Structure):
+    _fields_ = [("type", _c.c_uint32), ("fdt", _c.c_uint32), ("quantize", _c.c_int), ("dst", _c.c_void_p), ("dst_len", _c.c_size_t),
+                ("src", _c.c_void_p), ("src_len", _c.c_size_t)]
+
+
 class ConvertStats(_c.Structure):
     _fields_ = [("n_tensors", _c.c_uint64), ("n_cast_tensors", _c.c_uint64), ("cast_elems", _c.c_uint64), ("bytes_in", _c.c_uint64),
                 ("bytes_out", _c.c_uint64), ("seconds_plan", _c.c_double), ("seconds_convert", _c.c_double),
@@ -41,6 +46,7 @@ class ConvertStats(_c.Structure):
 
 
 SYMBOLS += [
+    ("ggq_slices", _c.c_int, [_c.POINTER(SliceJob), _c.c_size_t]),
     ("ggq_convert_gguf", _c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_int, _c.POINTER(ConvertStats)]),
     ("ggq_convert_last_error", _c.c_char_p, []),
 ]

@@ -295,59 +295,79 @@ void parallel_memcpy(void *dst, const void *src, size_t n) {
 //   direct_src / direct_dst  non-null => pinned caller memory, DMA straight from / to it;
 //   otherwise read(pinned, byte_off, nbytes) fills a pinned bounce buffer and
 //   write(pinned, byte_off, nbytes) drains one (memcpy for pageable memory, pread/pwrite for files).
-int run_chain_io(const std::vector<uint32_t> &chain, size_t n_elems, const ggq::ChainIO &io) {
-    if (n_elems == 0) return GGQ_OK;
-    const uint32_t t_in = chain.front(), t_out = chain.back();
+struct ChainJob {
+    std::vector<uint32_t> chain;  // >= 2 types
+    size_t n_elems;
+    ggq::ChainIO io;
+};
+
+// Streams every job, back to back, through ONE pipeline: the D2H of job k's last chunks overlaps the
+// H2D / kernels of job k+1's first chunks (no drain between tensors).
+int run_jobs_io(const std::vector<ChainJob> &jobs) {
+    struct Chunk { uint32_t job; size_t e0, e1; };
+    std::vector<Chunk> chunks;
+    // Chunk boundaries (elements).  The first chunks of the call are small (1, 2, 4 Mi elements) so
+    // the first D2H starts early; steady state uses CHUNK_ELEMS.
+    size_t ramp = FIRST_CHUNK_ELEMS;
+    for (uint32_t j = 0; j < jobs.size(); j++)
+        for (size_t e = 0; e < jobs[j].n_elems;) {
+            const size_t n = std::min(jobs[j].n_elems - e, ramp);
+            chunks.push_back({j, e, e + n});
+            e += n;
+            ramp = std::min(ramp * 2, CHUNK_ELEMS);
+        }
+    if (chunks.empty()) return GGQ_OK;
     DevInfo dev;
     int rc = resolve_device(&dev);
     if (rc != GGQ_OK) return rc;
     Pipeline *pl = nullptr;
     if ((rc = acquire_pipeline(dev.device, &pl)) != GGQ_OK) return rc;
 
-    // Chunk boundaries (elements).  The first chunks are small (1, 2, 4 Mi elements) so the first D2H
-    // starts ~0.1 ms earlier on every call; steady state uses CHUNK_ELEMS.
-    std::vector<size_t> bound{0};
-    for (size_t sz = FIRST_CHUNK_ELEMS; bound.back() < n_elems; sz = std::min(sz * 2, CHUNK_ELEMS)) bound.push_back(std::min(n_elems, bound.back() + sz));
-    const size_t nchunks = bound.size() - 1;
-    const bool pin_in = io.direct_src != nullptr, pin_out = io.direct_dst != nullptr;
-
-    // lazily allocate bounce buffers only when they are needed
+    // lazily allocate bounce buffers only when some job needs them
+    bool need_in = false, need_out = false;
+    for (const auto &j : jobs) { need_in |= !j.io.direct_src; need_out |= !j.io.direct_dst; }
     cudaError_t e = cudaSuccess;
     for (auto &s : pl->slots) {
-        if (!pin_in && !s.h_in && (e = cudaHostAlloc(&s.h_in, SLOT_BYTES, cudaHostAllocDefault)) != cudaSuccess) break;
-        if (!pin_out && !s.h_out && (e = cudaHostAlloc(&s.h_out, SLOT_BYTES, cudaHostAllocDefault)) != cudaSuccess) break;
+        if (need_in && !s.h_in && (e = cudaHostAlloc(&s.h_in, SLOT_BYTES, cudaHostAllocDefault)) != cudaSuccess) break;
+        if (need_out && !s.h_out && (e = cudaHostAlloc(&s.h_out, SLOT_BYTES, cudaHostAllocDefault)) != cudaSuccess) break;
     }
     if (e != cudaSuccess) {
         release_pipeline(pl);
         return fail_cuda(e, "cudaHostAlloc");
     }
 
+    const size_t nchunks = chunks.size();
     bool io_ok = true;
     for (size_t c = 0; c < nchunks + NSLOTS && e == cudaSuccess && io_ok; c++) {
         Slot &s = pl->slots[c % NSLOTS];
         if (c >= NSLOTS) {  // retire chunk c - NSLOTS
-            const size_t r = c - NSLOTS;
+            const Chunk &r = chunks[c - NSLOTS];
+            const ChainJob &rj = jobs[r.job];
             if ((e = cudaEventSynchronize(s.done)) != cudaSuccess) break;
-            if (!pin_out) io_ok = io.write(s.h_out, type_nbytes(t_out, bound[r]), type_nbytes(t_out, bound[r + 1] - bound[r]));
+            const uint32_t t_out = rj.chain.back();
+            if (!rj.io.direct_dst) io_ok = rj.io.write(s.h_out, type_nbytes(t_out, r.e0), type_nbytes(t_out, r.e1 - r.e0));
         }
         if (c < nchunks && io_ok) {
-            const size_t ne = bound[c + 1] - bound[c];
-            const size_t in_off = type_nbytes(t_in, bound[c]), out_off = type_nbytes(t_out, bound[c]);
+            const Chunk &k = chunks[c];
+            const ChainJob &job = jobs[k.job];
+            const uint32_t t_in = job.chain.front(), t_out = job.chain.back();
+            const size_t ne = k.e1 - k.e0;
+            const size_t in_off = type_nbytes(t_in, k.e0), out_off = type_nbytes(t_out, k.e0);
             const char *hsrc;
-            if (pin_in) {
-                hsrc = static_cast<const char *>(io.direct_src) + in_off;
+            if (job.io.direct_src) {
+                hsrc = static_cast<const char *>(job.io.direct_src) + in_off;
             } else {
-                if (!(io_ok = io.read(s.h_in, in_off, type_nbytes(t_in, ne)))) break;
+                if (!(io_ok = job.io.read(s.h_in, in_off, type_nbytes(t_in, ne)))) break;
                 hsrc = static_cast<const char *>(s.h_in);
             }
             if ((e = cudaMemcpyAsync(s.d_a, hsrc, type_nbytes(t_in, ne), cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) break;
             void *cur = s.d_a, *nxt = s.d_b;
-            for (size_t h = 0; h + 1 < chain.size(); h++) {
-                if ((e = enqueue_hop(chain[h], chain[h + 1], nxt, cur, ne, s.stream, dev)) != cudaSuccess) break;
+            for (size_t h = 0; h + 1 < job.chain.size(); h++) {
+                if ((e = enqueue_hop(job.chain[h], job.chain[h + 1], nxt, cur, ne, s.stream, dev)) != cudaSuccess) break;
                 std::swap(cur, nxt);
             }
             if (e != cudaSuccess) break;
-            void *hdst = pin_out ? static_cast<void *>(static_cast<char *>(io.direct_dst) + out_off) : s.h_out;
+            void *hdst = job.io.direct_dst ? static_cast<void *>(static_cast<char *>(job.io.direct_dst) + out_off) : s.h_out;
             if ((e = cudaMemcpyAsync(hdst, cur, type_nbytes(t_out, ne), cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) break;
             if ((e = cudaEventRecord(s.done, s.stream)) != cudaSuccess) break;
         }
@@ -359,6 +379,35 @@ int run_chain_io(const std::vector<uint32_t> &chain, size_t n_elems, const ggq::
         return e != cudaSuccess ? fail_cuda(e, "host cast pipeline") : fail(GGQ_ERR_INVALID, "I/O callback failed in the cast pipeline");
     }
     release_pipeline(pl);
+    return GGQ_OK;
+}
+
+// Runs one cast chain over `n_elems` elements: chunks flow through NSLOTS (stream, device ping-pong,
+// pinned in/out) slots so H2D(c+1), kernels(c) and D2H(c-1) overlap; intermediates of a multi-hop chain
+// never leave the device.  `io` supplies and consumes the bytes:
+//   direct_src / direct_dst  non-null => pinned caller memory, DMA straight from / to it;
+//   otherwise read(pinned, byte_off, nbytes) fills a pinned bounce buffer and
+//   write(pinned, byte_off, nbytes) drains one (memcpy for pageable memory, pread/pwrite for files).
+int run_chain_io(const std::vector<uint32_t> &chain, size_t n_elems, const ggq::ChainIO &io) {
+    if (n_elems == 0) return GGQ_OK;
+    std::vector<ChainJob> jobs(1);
+    jobs[0].chain = chain;
+    jobs[0].n_elems = n_elems;
+    jobs[0].io = io;
+    return run_jobs_io(jobs);
+}
+
+// memcpy-backed ChainIO over caller memory (pinned => direct DMA)
+int make_mem_io(void *dst, const void *src, ggq::ChainIO *io) {
+    const cudaMemoryType ks = pointer_kind(src), kd = pointer_kind(dst);
+    if (ks == cudaMemoryTypeDevice || kd == cudaMemoryTypeDevice)
+        return fail(GGQ_ERR_INVALID, "device pointer passed to a host-pointer entry point (use the *_device variants)");
+    io->direct_src = ks == cudaMemoryTypeHost ? src : nullptr;
+    io->direct_dst = kd == cudaMemoryTypeHost ? dst : nullptr;
+    const char *s0 = static_cast<const char *>(src);
+    char *d0 = static_cast<char *>(dst);
+    io->read = [s0](void *pinned, size_t off, size_t n) { parallel_memcpy(pinned, s0 + off, n); return true; };
+    io->write = [d0](const void *pinned, size_t off, size_t n) { parallel_memcpy(d0 + off, pinned, n); return true; };
     return GGQ_OK;
 }
 
@@ -513,6 +562,26 @@ int ggq_dequantize_slice_device(uint32_t type, uint32_t fdt, void *dst, size_t d
     Plan p;
     int rc = plan_dequantize(type, fdt, dst_elems, src_blocks, &p);
     return rc != GGQ_OK ? rc : run_device(false, p, dst, src, stream);
+}
+
+int ggq_slices(const struct ggq_slice_job *jobs, size_t n_jobs) {
+    if (n_jobs && !jobs) return fail(GGQ_ERR_INVALID, "null job table");
+    std::vector<ChainJob> cj;
+    for (size_t i = 0; i < n_jobs; i++) {
+        const ggq_slice_job &j = jobs[i];
+        Plan p;
+        int rc = j.quantize ? plan_quantize(j.type, j.fdt, j.dst_len, j.src_len, &p) : plan_dequantize(j.type, j.fdt, j.dst_len, j.src_len, &p);
+        if (rc != GGQ_OK) return rc;  // nothing has been computed yet: all jobs are validated first
+        if (p.nblocks == 0) continue;
+        if (!j.dst || !j.src) return fail(GGQ_ERR_INVALID, "null pointer with non-zero length");
+        ChainJob c;
+        c.chain = j.quantize ? std::vector<uint32_t>{p.fdt, p.ti->type} : std::vector<uint32_t>{p.ti->type, p.fdt};
+        if (c.chain[0] == c.chain[1]) c.chain.insert(c.chain.begin() + 1, GGQ_F32);
+        c.n_elems = p.nblocks * p.ti->elems;
+        if ((rc = make_mem_io(j.dst, j.src, &c.io)) != GGQ_OK) return rc;
+        cj.push_back(std::move(c));
+    }
+    return run_jobs_io(cj);
 }
 
 int ggq_cast(const uint32_t *types, int n_types, void *dst, const void *src, size_t n_elems) {

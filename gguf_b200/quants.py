@@ -122,6 +122,28 @@ def dequantize(ty, src, fdt=F32):
     return dst
 
 
+def slices(jobs):
+    """`ggq_slices`: several slice calls streamed through one pipeline, as ONE synchronous call.
+    `jobs` is a list of ("quantize" | "dequantize", type, dst_array, src_array[, fdt]) with the same
+    array conventions as quantize_slice / dequantize_slice.  Raises like they do; validates all first."""
+    from ._lib import SliceJob
+    arr = (SliceJob * len(jobs))()
+    keep = []
+    for i, job in enumerate(jobs):
+        kind, ty, dst, src = job[:4]
+        fdt = job[4] if len(job) > 4 else None
+        if kind == "quantize":
+            fdt = _fdt_of(src, fdt)
+            arr[i] = SliceJob(ty, fdt, 1, dst.ctypes.data, _blocks_len(dst, ty), src.ctypes.data, _float_len(src, fdt))
+        elif kind == "dequantize":
+            fdt = _fdt_of(dst, fdt)
+            arr[i] = SliceJob(ty, fdt, 0, dst.ctypes.data, _float_len(dst, fdt), src.ctypes.data, _blocks_len(src, ty))
+        else:
+            raise ValueError(kind)
+        keep.append((dst, src))
+    _check(lib().ggq_slices(arr, len(jobs)))
+
+
 # ---- device-pointer API (torch tensors or raw addresses) ------------------------------------------
 def _ptr(x):
     return x.data_ptr() if hasattr(x, "data_ptr") else int(x)

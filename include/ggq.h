@@ -89,6 +89,23 @@ int ggq_quantize_slice(uint32_t type, uint32_t fdt, void *dst, size_t dst_blocks
 int ggq_dequantize_slice(uint32_t type, uint32_t fdt, void *dst, size_t dst_elems,
                          const void *src, size_t src_blocks);
 
+/* Several slice calls as ONE synchronous call: the jobs stream back to back through a single
+ * H2D -> kernel -> D2H pipeline, so the copies of job k+1 start while job k is still draining (a
+ * sequence of the calls above drains the pipeline between tensors: ~0.2 ms of idle PCIe per call).
+ * Every job is validated first with the checks and order of its slice call; the first failing job's
+ * status is returned and nothing is computed.  This is what the per-shard writer loop of
+ * ggus/src/write/file_writer.rs:121-134 becomes when it hands the library all of a shard's tensors. */
+struct ggq_slice_job {
+    uint32_t type;     /* block type */
+    uint32_t fdt;      /* float-side type */
+    int quantize;      /* non-zero: quantize_slice(dst: blocks, src: elements); zero: dequantize_slice */
+    void *dst;
+    size_t dst_len;    /* blocks when quantizing, elements when dequantizing */
+    const void *src;
+    size_t src_len;    /* elements when quantizing, blocks when dequantizing */
+};
+int ggq_slices(const struct ggq_slice_job *jobs, size_t n_jobs);
+
 /* ---- device-pointer slice API (device-resident chains, pipelining, kernel timing) ---------- */
 
 /* Same contracts, but `dst`/`src` are device pointers on the current device and the work is

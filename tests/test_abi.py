@@ -85,3 +85,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle|ggo_[a-z]", txt, flags=re.M), f
+
+
+def test_slices_validates_every_job_before_computing(ggq):
+    """ggq_slices: the first failing job's QuantizeError is returned and nothing runs (works without a GPU)."""
+    ok = ("quantize", ggq.Q8_0, np.zeros(2 * 34, np.uint8), np.zeros(64, np.float32))
+    bad_len = ("dequantize", ggq.Q8_0, np.zeros(64, np.float32), np.zeros(3 * 34, np.uint8))
+    bad_div = ("quantize", ggq.Q4K, np.zeros(144, np.uint8), np.zeros(255, np.float32))
+    with pytest.raises(ggq.QuantizeError) as e:
+        ggq.slices([ok, bad_len, bad_div])
+    assert e.value.kind == "LengthMismatch"
+    with pytest.raises(ggq.QuantizeError) as e:
+        ggq.slices([bad_div, bad_len])
+    assert e.value.kind == "Indivisible"
+    ggq.slices([])

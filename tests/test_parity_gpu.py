@@ -307,3 +307,34 @@ def test_host_api_rejects_device_pointers(ggq):
     out = np.zeros(2 * 34, np.uint8)
     rc = lib().ggq_quantize_slice(8, 0, out.ctypes.data, 2, d.data_ptr(), 64)
     assert rc == -3 and b"device pointer" in lib().ggq_last_error()
+
+
+def test_batched_slices_match_oracle(ggq, oracle):
+    """ggq_slices: mixed quantize / dequantize jobs of different types and sizes (one spanning several
+    pipeline chunks) streamed through one pipeline; pinned and pageable buffers mixed."""
+    specs = [("quantize", 2, 32 * 5000, F16), ("quantize", 12, 256 * 900, F32), ("dequantize", 8, 32 * 70001, F16),
+             ("quantize", 8, (1 << 21) + 32 * 7, BF16), ("dequantize", 14, 256 * 33, F32), ("dequantize", 3, (1 << 22) + 64, F16)]
+    jobs, checks, pins = [], [], []
+    for i, (kind, ty, n, fdt) in enumerate(specs):
+        e, b = oracle.block_info(ty)
+        x = to_fdt(gaussian(n, 600 + i), fdt)
+        if kind == "quantize":
+            want = oracle.quantize(ty, fdt, x, threads=8)
+            if i % 2 == 0:
+                pb = ggq.PinnedBuffer(want.nbytes); pins.append(pb); dst = pb.array
+            else:
+                dst = np.zeros(want.nbytes, np.uint8)
+            jobs.append((kind, ty, dst, x, fdt))
+            checks.append((dst, want, ty, b))
+        else:
+            blocks = oracle.quantize(ty, F32, gaussian(n, 700 + i), threads=8)
+            want = oracle.dequantize(ty, fdt, blocks, threads=8)
+            dst = np.zeros(n, want.dtype)
+            jobs.append((kind, ty, dst, blocks, fdt))
+            checks.append((dst, want, None, None))
+    ggq.slices(jobs)
+    for dst, want, ty, b in checks:
+        if ty is None:
+            assert same_floats(dst, want)
+        else:
+            assert same_blocks(dst, want, ty, b)
