@@ -28,6 +28,7 @@ SYMBOLS = [
     ("ggq_type_nbytes", _c.c_size_t, [_c.c_uint32, _c.c_size_t]),
     ("ggq_host_alloc", _c.c_void_p, [_c.c_size_t]),
     ("ggq_host_free", None, [_c.c_void_p]),
+    ("ggq_shutdown", None, []),
     ("ggq_launch_count", _c.c_uint64, []),
     ("ggq_version", _c.c_char_p, []),
 ]

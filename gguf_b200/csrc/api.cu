@@ -5,6 +5,7 @@
 // point fails with GGQ_ERR_CUDA.
 #include "../../include/ggq.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <condition_variable>
@@ -581,7 +582,35 @@ int ggq_slices(const struct ggq_slice_job *jobs, size_t n_jobs) {
         if ((rc = make_mem_io(j.dst, j.src, &c.io)) != GGQ_OK) return rc;
         cj.push_back(std::move(c));
     }
-    return run_jobs_io(cj);
+    // by-tensor sharding over the configured GPUs (largest first, least-loaded device); no collective
+    const int ndev = (t_device >= 0) ? 1 : g_shard_devices.load();
+    if (ndev <= 1 || cj.size() < 2) return run_jobs_io(cj);
+    std::vector<size_t> order(cj.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cj[a].n_elems != cj[b].n_elems ? cj[a].n_elems > cj[b].n_elems : a < b; });
+    std::vector<std::vector<ChainJob>> per_dev(ndev);
+    std::vector<size_t> load(ndev, 0);
+    for (size_t i : order) {
+        const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[d] += cj[i].n_elems;
+        per_dev[d].push_back(std::move(cj[i]));
+    }
+    std::vector<int> rcs(ndev, GGQ_OK);
+    std::vector<std::string> errs(ndev);
+    auto dev_fn = [&](int d) {
+        t_device = d;
+        rcs[d] = run_jobs_io(per_dev[d]);
+        if (rcs[d] != GGQ_OK) errs[d] = t_err;
+    };
+    const int saved = t_device;
+    std::vector<std::thread> th;
+    for (int d = 1; d < ndev; d++) th.emplace_back(dev_fn, d);
+    dev_fn(0);
+    t_device = saved;
+    for (auto &t : th) t.join();
+    for (int d = 0; d < ndev; d++)
+        if (rcs[d] != GGQ_OK) return fail(rcs[d], errs[d]);
+    return GGQ_OK;
 }
 
 int ggq_cast(const uint32_t *types, int n_types, void *dst, const void *src, size_t n_elems) {
@@ -607,6 +636,22 @@ void *ggq_host_alloc(size_t bytes) {
 }
 void ggq_host_free(void *p) {
     if (p) cudaFreeHost(p);
+}
+
+void ggq_shutdown(void) {
+    std::vector<Pipeline *> idle;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        idle.swap(g_pool);
+    }
+    int cur = -1;
+    cudaGetDevice(&cur);
+    for (Pipeline *p : idle) {
+        cudaSetDevice(p->device);
+        destroy_pipeline(p);
+    }
+    if (cur >= 0) cudaSetDevice(cur);
+    cudaGetLastError();
 }
 
 uint64_t ggq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

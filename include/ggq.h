@@ -159,6 +159,11 @@ const char *ggq_convert_last_error(void);
 void *ggq_host_alloc(size_t bytes);
 void ggq_host_free(void *p);
 
+/* Releases the idle stream pipelines (device staging buffers, pinned bounce buffers, streams) the host
+ * entry points keep pooled between calls.  Safe at any time; pipelines in use are not touched and the
+ * pool refills on demand. */
+void ggq_shutdown(void);
+
 /* Number of kernel launches issued by this library since load (all threads); for harnesses. */
 uint64_t ggq_launch_count(void);
 

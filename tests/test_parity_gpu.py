@@ -332,9 +332,30 @@ def test_batched_slices_match_oracle(ggq, oracle):
             dst = np.zeros(n, want.dtype)
             jobs.append((kind, ty, dst, blocks, fdt))
             checks.append((dst, want, None, None))
-    ggq.slices(jobs)
+    from gguf_b200._lib import lib
+    for ndev in (1, 0):   # single device, then by-tensor sharding over every visible GPU
+        for dst, *_ in checks:
+            dst[...] = 0
+        assert lib().ggq_set_shard_devices(ndev) >= 1
+        try:
+            ggq.slices(jobs)
+        finally:
+            lib().ggq_set_shard_devices(1)
+        _check_slices(checks)
+
+
+def _check_slices(checks):
     for dst, want, ty, b in checks:
         if ty is None:
             assert same_floats(dst, want)
         else:
             assert same_blocks(dst, want, ty, b)
+
+
+def test_shutdown_releases_and_pool_refills(ggq, oracle):
+    from gguf_b200._lib import lib
+    x = gaussian(32 * 1000, 77)
+    a = ggq.quantize(8, x)
+    lib().ggq_shutdown()
+    lib().ggq_shutdown()
+    assert np.array_equal(ggq.quantize(8, x), a) and np.array_equal(a, oracle.quantize(8, F32, x))
