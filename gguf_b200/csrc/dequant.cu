@@ -51,7 +51,7 @@ static cudaError_t launch_dequant_cfg(const void *src, void *dst, size_t nblocks
     constexpr int TILE_BLOCKS = CFG::TILE / TR::ELEMS;
     constexpr int SMEM = dequant_smem_bytes<T, CFG::TILE, CFG::STAGES, DQ_MODE>();
     auto kern = dequant_kernel<T, FT, CFG::TILE, CFG::STAGES, CFG::THREADS, CFG::MINB, DQ_MODE, DQ_SP>;
-    static int occ_cache[MAX_DEVICES];  // per instantiation, per device
+    static std::atomic<int> occ_cache[MAX_DEVICES];  // per instantiation, per device
     int ctas_per_sm = 0;
     cudaError_t e = cached_occupancy(kern, CFG::THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
     if (e != cudaSuccess) return e;

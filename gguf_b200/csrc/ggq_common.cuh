@@ -79,18 +79,6 @@ struct F32 { using raw = float;    static constexpr int SIZE = 4; static constex
 struct F16 { using raw = uint16_t; static constexpr int SIZE = 2; static constexpr int V = 8; };
 struct BF16 { using raw = uint16_t; static constexpr int SIZE = 2; static constexpr int V = 8; };
 
-// narrow one f32 result to the float-side type (lib.rs:70-73, 87-89)
-template <class FT> __device__ __forceinline__ typename FT::raw narrow(float f);
-template <> __device__ __forceinline__ float narrow<F32>(float f) { return f; }
-template <> __device__ __forceinline__ uint16_t narrow<F16>(float f) { return f2h(f); }
-template <> __device__ __forceinline__ uint16_t narrow<BF16>(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
-
-// widen one float-side element to f32 (lib.rs:66-69, 82-84); exact
-template <class FT> __device__ __forceinline__ float widen(typename FT::raw v);
-template <> __device__ __forceinline__ float widen<F32>(float v) { return v; }
-template <> __device__ __forceinline__ float widen<F16>(uint16_t v) { return h2f(v); }
-template <> __device__ __forceinline__ float widen<BF16>(uint16_t v) { return __uint_as_float((uint32_t)v << 16); }
-
 // Store FT::V consecutive results (one 16-byte vector when `vec`, element stores otherwise).
 template <class FT> __device__ __forceinline__ void emit(typename FT::raw *p, const float *v, bool vec);
 template <> __device__ __forceinline__ void emit<F32>(float *p, const float *v, bool vec) {
@@ -176,15 +164,6 @@ template <int ALIGN> __device__ __forceinline__ uint32_t lds32(const uint8_t *p)
     if constexpr (ALIGN >= 4) return *reinterpret_cast<const uint32_t *>(p);
     else return lds16(p) | (lds16(p + 2) << 16);
 }
-template <int ALIGN> __device__ __forceinline__ void sts32(uint8_t *p, uint32_t v) {
-    if constexpr (ALIGN >= 4) {
-        *reinterpret_cast<uint32_t *>(p) = v;
-    } else {
-        *reinterpret_cast<uint16_t *>(p) = (uint16_t)(v & 0xFFFFu);
-        *reinterpret_cast<uint16_t *>(p + 2) = (uint16_t)(v >> 16);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk async copies (TMA engine; SASS UBLKCP)
 // ---------------------------------------------------------------------------------------------

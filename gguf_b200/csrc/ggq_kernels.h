@@ -1,6 +1,8 @@
 // ggq_kernels.h — internal launch entry points shared by the kernel TUs and the C-ABI layer.
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -24,8 +26,8 @@ cudaError_t cast_elems(uint32_t src_dt, uint32_t dst_dt, const void *src, void *
 
 // occupancy cache helper: resident CTAs per SM for `kern`, after raising its dynamic smem limit.
 template <class K>
-static inline cudaError_t cached_occupancy(K kern, int threads, int smem, int device, int *cache, int *out) {
-    int v = cache[device];
+static inline cudaError_t cached_occupancy(K kern, int threads, int smem, int device, std::atomic<int> *cache, int *out) {
+    int v = cache[device].load(std::memory_order_relaxed);  // racing first callers compute the same value
     if (v == 0) {
         cudaError_t e = cudaSuccess;
         if (smem > 0) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -34,7 +36,7 @@ static inline cudaError_t cached_occupancy(K kern, int threads, int smem, int de
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
         if (e != cudaSuccess) return e;
         v = n > 0 ? n : 1;
-        cache[device] = v;
+        cache[device].store(v, std::memory_order_relaxed);
     }
     *out = v;
     return cudaSuccess;

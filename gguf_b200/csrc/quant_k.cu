@@ -33,7 +33,6 @@ __device__ __forceinline__ int nearest_int(float v) {
 __device__ __forceinline__ float i2f_small(int l) { return u2f_biased((uint32_t)(l + 64), 64.0f); }
 
 template <int NW> __device__ __forceinline__ void set_code(uint32_t (&w)[NW], int i, int l) { w[i >> 2] |= (uint32_t)(l & 0xFF) << (8 * (i & 3)); }
-template <int NW> __device__ __forceinline__ int get_code(const uint32_t (&w)[NW], int i) { return (int)((w[i >> 2] >> (8 * (i & 3))) & 0xFF); }
 
 // Rounding without leaving the FP pipes.  On upstream's domain (|v| <= 4194303, its assert)
 //   clamp(nearest_int(v), lo, hi) == rint(clamp(v, lo, hi))            (rint is monotone, lo/hi integers)
@@ -544,7 +543,7 @@ template <uint32_t T, class FT>
 static cudaError_t launch_quant_k(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
     constexpr int SBW = 32 / (256 / KQuant<T>::SUB);
     auto kern = quant_k_kernel<T, FT>;
-    static int occ_cache[MAX_DEVICES];
+    static std::atomic<int> occ_cache[MAX_DEVICES];
     int ctas_per_sm = 0;
     cudaError_t e = cached_occupancy(kern, KQ_THREADS, 0, dev.device, occ_cache, &ctas_per_sm);
     if (e != cudaSuccess) return e;

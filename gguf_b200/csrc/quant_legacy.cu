@@ -562,7 +562,7 @@ static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cuda
     constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = QL_THREADS / RPB;
     constexpr int SMEM = QS * QL_THREADS * (32 * FT::SIZE + 16) + 2 * ((TILE_BLOCKS * TR::BYTES + 15) & ~15);
     auto kern = quant_rows_kernel<T, FT, QS>;
-    static int occ_cache[MAX_DEVICES];
+    static std::atomic<int> occ_cache[MAX_DEVICES];
     int ctas_per_sm = 0;
     cudaError_t e = cached_occupancy(kern, QL_THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
     if (e != cudaSuccess) return e;
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(CAST_THREADS) cast_kernel(const typename ST::r
 template <class ST, class DT>
 static cudaError_t launch_cast(const void *src, void *dst, size_t n, cudaStream_t stream, DevInfo dev) {
     auto kern = cast_kernel<ST, DT>;
-    static int occ_cache[MAX_DEVICES];
+    static std::atomic<int> occ_cache[MAX_DEVICES];
     int ctas_per_sm = 0;
     cudaError_t e = cached_occupancy(kern, CAST_THREADS, 0, dev.device, occ_cache, &ctas_per_sm);
     if (e != cudaSuccess) return e;

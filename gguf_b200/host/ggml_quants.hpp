@@ -14,6 +14,7 @@
 #pragma once
 
 #include <array>
+#include <initializer_list>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -115,5 +116,22 @@ template <class Blk, class T> struct Quantize {
         return out;
     }
 };
+
+// ---- the caller of the slice API: `cast(row, data, from, to)` (xtask/src/utils/operator/cast.rs:93-138) ----
+// `types` lists the GGmlType ids from the source type to the destination type (two entries for a
+// plain cast, more for a chained `--steps "a -> b -> c"`); intermediates stay on the device.
+inline Result cast(std::initializer_list<uint32_t> types, void *dst, const void *src, size_t n_elems) {
+    return Result(ggq_cast(types.begin(), (int)types.size(), dst, src, n_elems));
+}
+// `GGmlType::size().elements_to_bytes` for a flat element count (ggus/src/tensor.rs:83-96)
+inline size_t type_nbytes(uint32_t type, size_t n_elems) { return ggq_type_nbytes(type, n_elems); }
+
+// `xtask convert FILE -x STEPS` for `cast:` steps (xtask/src/convert.rs:24-58); throws on failure.
+inline ggq_convert_stats convert(const std::string &file, const std::string &out, const std::string &steps, int n_devices = 0) {
+    ggq_convert_stats st{};
+    const int rc = ggq_convert_gguf(file.c_str(), out.c_str(), steps.c_str(), n_devices, &st);
+    if (rc != GGQ_OK) throw std::runtime_error(std::string("convert: ") + ggq_convert_last_error());
+    return st;
+}
 
 }  // namespace ggml_quants

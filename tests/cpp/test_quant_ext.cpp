@@ -94,6 +94,18 @@ int main(int argc, char **argv) {
         QuantExt<f16, float>::dequantize_slice(y.data(), 64, hb.data(), 64).unwrap(); // f16 -> f32 cast
         for (int i = 0; i < 64; i++) CHECK(std::fabs(x[i] - y[i]) <= 4.5e-3f);
     }
+    if (!no_gpu) {
+        // cast.rs:132-135 leaves Q8_0 -> F16 as todo!(); the library implements every pair
+        std::vector<float> x(64, 0.25f), y(64);
+        std::vector<Q8_0> q(2);
+        QuantExt<Q8_0, float>::quantize_slice(q.data(), 2, x.data(), 64).unwrap();
+        std::vector<f16> h(64);
+        cast({GGQ_Q8_0, GGQ_F16}, h.data(), q.data(), 64).unwrap();
+        cast({GGQ_F16, GGQ_F32}, y.data(), h.data(), 64).unwrap();
+        for (int i = 0; i < 64; i++) CHECK(std::fabs(y[i] - 0.25f) <= 4.5e-3f);
+        CHECK(cast({GGQ_Q8_0, GGQ_F16}, h.data(), q.data(), 31).unwrap_err() == QuantizeError::Indivisible);
+        CHECK(type_nbytes(GGQ_Q4K, 512) == 288 && type_nbytes(GGQ_Q4K, 100) == 0);
+    }
     std::printf(failures ? "%d FAILURES\n" : "all ok%.0d\n", failures);
     return failures ? 1 : 0;
 }
