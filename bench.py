@@ -279,7 +279,7 @@ def ours(args, rank, world, local_rank):
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": f"{dom['kernel']} {dom['shape']}", "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": dom["GBps"] / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"],
+                "frac": dom["GBps"] / peak, "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8000_GBps": dom["GBps"] / 8000.0, "algorithmic_bytes_per_launch": dom["bytes"],
                 "avg_launch_us": dom["us"], "method": f"{R} back-to-back launches between two CUDA events on the launch stream, {NSETS} rotating buffer sets"}
 
     # ---- e2e: host C ABI with pinned host buffers (H2D + kernel + D2H in the timing) ----
