@@ -21,7 +21,6 @@
 
 namespace ggq {
 
-constexpr int QL_THREADS = 128;   // rows per tile
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr float F32_MAX = 3.40282347e+38f;
 
@@ -456,7 +455,8 @@ template <> struct Encoder<T_Q8K> {
 };
 
 // ---------------------------------------------------------------------------------------------
-template <uint32_t T, class FT, int QS>
+// QL_THREADS = rows per tile (one thread per row); chosen per type in launch_quant
+template <uint32_t T, class FT, int QS, int QL_THREADS>
 __global__ void __launch_bounds__(QL_THREADS)
 quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t nblocks) {
     using TR = BlockTraits<T>;
@@ -558,10 +558,13 @@ quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, si
 template <uint32_t T, class FT>
 static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
     using TR = BlockTraits<T>;
-    constexpr int QS = FT::SIZE == 4 ? 2 : 3;
+    // measured (tools/codec_sweep.py): 2 input stages beat 3 (more CTAs per SM hide the per-tile barrier);
+    // 128-row tiles are best for Q8_0 / Q8_1, 64-row tiles for the 4/5-bit types and Q8K
+    constexpr int QS = 2;
+    constexpr int QL_THREADS = (T == T_Q8_0 || T == T_Q8_1) ? 128 : 64;
     constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = QL_THREADS / RPB;
     constexpr int SMEM = QS * QL_THREADS * (32 * FT::SIZE + 16) + 2 * ((TILE_BLOCKS * TR::BYTES + 15) & ~15);
-    auto kern = quant_rows_kernel<T, FT, QS>;
+    auto kern = quant_rows_kernel<T, FT, QS, QL_THREADS>;
     static std::atomic<int> occ_cache[MAX_DEVICES];
     int ctas_per_sm = 0;
     cudaError_t e = cached_occupancy(kern, QL_THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
