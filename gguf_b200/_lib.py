@@ -43,12 +43,19 @@ class SliceJob(_c.Structure):
 class ConvertStats(_c.Structure):
     _fields_ = [("n_tensors", _c.c_uint64), ("n_cast_tensors", _c.c_uint64), ("cast_elems", _c.c_uint64), ("bytes_in", _c.c_uint64),
                 ("bytes_out", _c.c_uint64), ("seconds_plan", _c.c_double), ("seconds_convert", _c.c_double),
-                ("seconds_sync", _c.c_double), ("n_devices", _c.c_int)]
+                ("seconds_sync", _c.c_double), ("n_devices", _c.c_int), ("n_out_files", _c.c_int)]
+
+
+class ConvertOptions(_c.Structure):
+    _fields_ = [("n_devices", _c.c_int), ("max_tensors", _c.c_uint64), ("max_bytes", _c.c_uint64), ("no_tensor_first", _c.c_int),
+                ("no_data", _c.c_int)]
 
 
 SYMBOLS += [
     ("ggq_slices", _c.c_int, [_c.POINTER(SliceJob), _c.c_size_t]),
     ("ggq_convert_gguf", _c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_int, _c.POINTER(ConvertStats)]),
+    ("ggq_convert_gguf_ex", _c.c_int, [_c.POINTER(_c.c_char_p), _c.c_size_t, _c.c_char_p, _c.c_char_p, _c.POINTER(ConvertOptions),
+                                       _c.POINTER(ConvertStats)]),
     ("ggq_convert_last_error", _c.c_char_p, []),
 ]
 

@@ -22,7 +22,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -102,16 +104,75 @@ struct Mapping {
 
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+struct InFile {
+    Mapping map;
+    gguf::File f;
+    int fd = -1;
+    uint64_t data_off = 0;
+    ~InFile() { if (fd >= 0) close(fd); }
+};
+
+struct Tensor {                 // one tensor of the merged content (read.rs:49-59)
+    const gguf::TensorInfo *info;
+    int file;                   // index into the input files
+    std::vector<uint32_t> chain;
+    uint64_t out_nbytes;
+    int shard = 0;
+    uint64_t out_off = 0;
+};
+
+bool pread_all(int fd, void *buf, size_t n, uint64_t off) {
+    char *p = static_cast<char *>(buf);
+    while (n) {
+        ssize_t r = pread(fd, p, n, (off_t)off);
+        if (r <= 0) return false;
+        p += r; off += (uint64_t)r; n -= (size_t)r;
+    }
+    return true;
+}
+bool pwrite_all(int fd, const void *buf, size_t n, uint64_t off) {
+    const char *p = static_cast<const char *>(buf);
+    while (n) {
+        ssize_t r = pwrite(fd, p, n, (off_t)off);
+        if (r <= 0) return false;
+        p += r; off += (uint64_t)r; n -= (size_t)r;
+    }
+    return true;
+}
+
+// bytes of one tensor-info record (writer.rs:74-86)
+uint64_t info_bytes(const gguf::TensorInfo &t) { return 8 + t.name.size() + 4 + 8 * t.shape.size() + 4 + 8; }
+constexpr uint64_t ALIGNMENT_KV_BYTES = 8 + 17 + 4 + 4;  // "general.alignment": key string + type + u32
+
+// GGufFileSimulator / GGufTensorSimulator (ggus/src/write/simulator.rs:26-96)
+struct Simulator {
+    uint64_t alignment, written, n = 0;
+    std::vector<uint64_t> data;
+    Simulator(uint64_t align, uint64_t kv_bytes) : alignment(align), written(24 + ALIGNMENT_KV_BYTES + kv_bytes) {}
+    void write_tensor(const gguf::TensorInfo &t, uint64_t nbytes) { written += info_bytes(t); data.push_back(nbytes); }
+    uint64_t written_bytes() const {
+        uint64_t total = written;
+        for (uint64_t len : data) { total += gguf::pad(total, alignment); total += len; }
+        return total;
+    }
+};
+
 }  // namespace
 
 extern "C" {
 
 const char *ggq_convert_last_error(void) { return t_cerr.c_str(); }
 
-int ggq_convert_gguf(const char *in_path, const char *out_path, const char *steps, int n_devices, struct ggq_convert_stats *stats) {
+int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *out_path, const char *steps,
+                        const struct ggq_convert_options *opts, struct ggq_convert_stats *stats) {
     auto failc = [&](int code, const std::string &m) { t_cerr = m; return code; };
     try {
         const double t0 = now();
+        ggq_convert_options o{};
+        if (opts) o = *opts;
+        const uint64_t max_tensors = o.max_tensors ? o.max_tensors : UINT64_MAX;
+        const uint64_t max_bytes = o.max_bytes ? o.max_bytes : UINT64_MAX;
+        if (!in_paths || n_in == 0 || !out_path) return failc(GGQ_ERR_INVALID, "no input or output path");
         // ---- parse `--steps "a -> b -> c"` (convert.rs:38-51) ----
         std::vector<CastRule> rules;
         {
@@ -133,89 +194,118 @@ int ggq_convert_gguf(const char *in_path, const char *out_path, const char *step
                 pos = nx + 2;
             }
         }
-        // ---- map + parse the input (utils/mod.rs:42-46, read.rs:5-31) ----
-        int fd = open(in_path, O_RDONLY);
-        if (fd < 0) return failc(GGQ_ERR_INVALID, std::string("cannot open ") + in_path);
-        struct stat st;
-        fstat(fd, &st);
-        Mapping in;
-        in.len = (size_t)st.st_size;
-        in.p = (uint8_t *)mmap(nullptr, in.len, PROT_READ, MAP_PRIVATE, fd, 0);
-        close(fd);
-        if (in.p == MAP_FAILED) { in.p = nullptr; return failc(GGQ_ERR_INVALID, "mmap of the input failed"); }
-        gguf::File f = gguf::File::parse(in.p, in.len);
-        const std::string arch(f.get_str("general.architecture"));
+        // ---- map + parse every input shard and merge them (utils/mod.rs:42-46, read.rs:5-62) ----
+        std::vector<std::unique_ptr<InFile>> files;
+        uint64_t alignment = 0, bytes_in = 0;
+        std::vector<const gguf::MetaKV *> kvs;
+        std::set<std::string_view> kv_seen, name_seen;
+        std::vector<Tensor> tensors;
+        for (size_t i = 0; i < n_in; i++) {
+            auto in = std::make_unique<InFile>();
+            in->fd = open(in_paths[i], O_RDONLY);
+            if (in->fd < 0) return failc(GGQ_ERR_INVALID, std::string("cannot open ") + in_paths[i]);
+            struct stat st;
+            if (fstat(in->fd, &st) != 0) return failc(GGQ_ERR_INVALID, std::string("cannot stat ") + in_paths[i]);
+            in->map.len = (size_t)st.st_size;
+            in->map.p = (uint8_t *)mmap(nullptr, in->map.len, PROT_READ, MAP_PRIVATE, in->fd, 0);
+            if (in->map.p == MAP_FAILED) { in->map.p = nullptr; return failc(GGQ_ERR_INVALID, "mmap of the input failed"); }
+            in->f = gguf::File::parse(in->map.p, in->map.len);
+            in->data_off = (uint64_t)(in->f.data - in->map.p);
+            bytes_in += in->map.len;
+            alignment = std::max(alignment, in->f.alignment);                          // read.rs:34
+            for (const auto &kv : in->f.meta_kvs) {
+                if (kv.key == gguf::GENERAL_ALIGNMENT || kv.key.substr(0, 6) == "split.") continue;  // read.rs:37-39
+                if (!kv_seen.insert(kv.key).second) return failc(GGQ_ERR_INVALID, "DuplicateMetaKey(" + std::string(kv.key) + ")");
+                kvs.push_back(&kv);
+            }
+            for (const auto &t : in->f.tensors) {
+                if (!name_seen.insert(t.name).second) return failc(GGQ_ERR_INVALID, "DuplicateTensorName(" + std::string(t.name) + ")");
+                tensors.push_back(Tensor{&t, (int)i, {}, 0});
+            }
+            files.push_back(std::move(in));
+        }
+        std::string arch;
+        for (const auto &f : files) if (arch.empty()) arch = std::string(f->f.get_str("general.architecture"));
         if (!rules.empty() && arch != "llama" && arch != "gpt2" && arch != "qwen2" && arch != "clip")
             return failc(GGQ_ERR_UNSUPPORTED, "Unsupported architecture: " + arch);  // cast.rs:69
 
-        // ---- per-tensor type chains (cast.rs:73-90, applied once per step) ----
-        const size_t nt = f.tensors.size();
-        std::vector<std::vector<uint32_t>> chains(nt);
-        for (size_t i = 0; i < nt; i++) {
-            chains[i].push_back(f.tensors[i].type);
-            const int cls = classify(arch, f.tensors[i].name, f.tensors[i].shape.size());
+        // ---- per-tensor type chains (cast.rs:73-90, applied once per step) and output sizes ----
+        const size_t nt = tensors.size();
+        for (auto &t : tensors) {
+            const auto &ti = *t.info;
+            t.chain.push_back(ti.type);
+            const int cls = classify(arch, ti.name, ti.shape.size());
             for (const CastRule &r : rules)
-                if (r.has[cls] && r.ty[cls] != chains[i].back()) chains[i].push_back(r.ty[cls]);
-        }
-        // ---- plan the output (write.rs:23-51 simulator, single shard) ----
-        std::vector<const gguf::MetaKV *> kvs;
-        for (const auto &kv : f.meta_kvs)
-            if (kv.key != gguf::GENERAL_ALIGNMENT && kv.key.substr(0, 6) != "split.") kvs.push_back(&kv);  // read.rs:37-39
-        std::vector<gguf::OutTensor> outs(nt);
-        for (size_t i = 0; i < nt; i++) {
-            const auto &t = f.tensors[i];
-            const uint32_t ty = chains[i].back();
-            uint64_t nbytes = t.nbytes;
-            if (chains[i].size() > 1) {
+                if (r.has[cls] && r.ty[cls] != t.chain.back()) t.chain.push_back(r.ty[cls]);
+            t.out_nbytes = ti.nbytes;
+            if (t.chain.size() > 1) {
                 uint64_t be, bb;
-                if (!gguf::type_size(ty, &be, &bb)) return failc(GGQ_ERR_UNSUPPORTED, "unsupported target type");
-                if (t.shape.empty() || t.shape[0] % be)  // cast.rs:142-143 `assert_eq!(row % N, 0)`
-                    return failc(GGQ_ERR_INDIVISIBLE, "row of " + std::string(t.name) + " is not a multiple of the target block size");
-                nbytes = t.n_elems() / be * bb;
-                for (uint32_t c : chains[i])
-                    if (ggq_type_nbytes(c, t.n_elems()) == 0) return failc(GGQ_ERR_UNSUPPORTED, "cast chain of " + std::string(t.name) + " has an unsupported type");
+                if (!gguf::type_size(t.chain.back(), &be, &bb)) return failc(GGQ_ERR_UNSUPPORTED, "unsupported target type");
+                if (ti.shape.empty() || ti.shape[0] % be)  // cast.rs:142-143 `assert_eq!(row % N, 0)`
+                    return failc(GGQ_ERR_INDIVISIBLE, "row of " + std::string(ti.name) + " is not a multiple of the target block size");
+                t.out_nbytes = ti.n_elems() / be * bb;
+                for (uint32_t c : t.chain)
+                    if (ggq_type_nbytes(c, ti.n_elems()) == 0) return failc(GGQ_ERR_UNSUPPORTED, "cast chain of " + std::string(ti.name) + " has an unsupported type");
             }
-            outs[i] = {t.name, &t.shape, ty, nbytes, 0};
         }
-        gguf::Sink sim;
-        const uint64_t out_len = gguf::write_front(sim, f.alignment, kvs, outs);
-        const uint64_t front_len = sim.pos();
-
-        // ---- output file: front matter with one write, tensor bytes with pwrite at their final
-        // offsets; the gaps between tensors are the zero padding of writer.rs:95-100 (ftruncate) ----
-        unlink(out_path);
-        int ofd = open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-        if (ofd < 0) return failc(GGQ_ERR_INVALID, std::string("cannot create ") + out_path);
-        struct FdGuard { int fd; ~FdGuard() { if (fd >= 0) close(fd); } } og{ofd};
-        if (ftruncate(ofd, (off_t)out_len) != 0) return failc(GGQ_ERR_INVALID, "ftruncate failed");
+        // ---- plan the output shards (write.rs:23-51, with the simulator's byte accounting) ----
+        uint64_t kv_bytes = 0;
+        for (const auto *kv : kvs) kv_bytes += kv->raw_len;
+        std::vector<std::vector<size_t>> shards(1);
         {
+            Simulator sim(alignment, kv_bytes);
+            for (size_t i = 0; i < nt; i++) {
+                if (shards.size() == 1 && o.no_tensor_first) {
+                    sim = Simulator(alignment, 0);
+                    sim.write_tensor(*tensors[i].info, tensors[i].out_nbytes);
+                    shards.push_back({i});
+                    continue;
+                }
+                sim.write_tensor(*tensors[i].info, tensors[i].out_nbytes);
+                if (shards.back().size() < max_tensors && sim.written_bytes() < max_bytes) {
+                    shards.back().push_back(i);
+                } else {
+                    sim = Simulator(alignment, 0);
+                    sim.write_tensor(*tensors[i].info, tensors[i].out_nbytes);
+                    shards.push_back({i});
+                }
+            }
+        }
+        // ---- create the shard files: name-00001-of-0000N.gguf when N > 1 (ggus/src/name/shard.rs:30-39) ----
+        std::string base(out_path);
+        if (base.size() > 5 && base.substr(base.size() - 5) == ".gguf") base.resize(base.size() - 5);
+        struct OutFile { int fd = -1; uint64_t len = 0; ~OutFile() { if (fd >= 0) close(fd); } };
+        std::vector<std::unique_ptr<OutFile>> outs;
+        uint64_t bytes_out = 0;
+        for (size_t si = 0; si < shards.size(); si++) {
+            char suffix[64] = "";
+            if (shards.size() > 1) snprintf(suffix, sizeof suffix, "-%05zu-of-%05zu", si + 1, shards.size());
+            const std::string path = base + suffix + ".gguf";
+            std::vector<gguf::OutTensor> ot;
+            for (size_t i : shards[si]) ot.push_back({tensors[i].info->name, &tensors[i].info->shape, tensors[i].chain.back(), tensors[i].out_nbytes, 0});
+            const std::vector<const gguf::MetaKV *> none;
+            const auto &shard_kvs = si == 0 ? kvs : none;           // write.rs:72, 77-81
+            gguf::Sink sim;
+            uint64_t total = gguf::write_front(sim, alignment, shard_kvs, ot);
+            const uint64_t front_len = sim.pos();
+            if (o.no_data) total = front_len;                       // file_writer.rs:104-106: no data queued
             std::vector<uint8_t> front(front_len);
             gguf::Sink sink(front.data());
-            gguf::write_front(sink, f.alignment, kvs, outs);
-            if (pwrite(ofd, front.data(), front.size(), 0) != (ssize_t)front.size()) return failc(GGQ_ERR_INVALID, "write of the header failed");
+            gguf::write_front(sink, alignment, shard_kvs, ot);
+            auto of = std::make_unique<OutFile>();
+            unlink(path.c_str());
+            of->fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+            if (of->fd < 0) return failc(GGQ_ERR_INVALID, "cannot create " + path);
+            if (ftruncate(of->fd, (off_t)total) != 0) return failc(GGQ_ERR_INVALID, "ftruncate failed");  // gaps = zero padding
+            if (!pwrite_all(of->fd, front.data(), front.size(), 0)) return failc(GGQ_ERR_INVALID, "write of the header failed");
+            of->len = total;
+            bytes_out += total;
+            for (size_t k = 0; k < shards[si].size(); k++) {
+                tensors[shards[si][k]].shard = (int)si;
+                tensors[shards[si][k]].out_off = ot[k].file_offset;
+            }
+            outs.push_back(std::move(of));
         }
-        int ifd = open(in_path, O_RDONLY);
-        if (ifd < 0) return failc(GGQ_ERR_INVALID, std::string("cannot reopen ") + in_path);
-        FdGuard ig{ifd};
-        const uint64_t in_data_off = (uint64_t)(f.data - in.p);
-        auto pread_all = [](int fd, void *buf, size_t n, uint64_t off) {
-            char *p = static_cast<char *>(buf);
-            while (n) {
-                ssize_t r = pread(fd, p, n, (off_t)off);
-                if (r <= 0) return false;
-                p += r; off += (uint64_t)r; n -= (size_t)r;
-            }
-            return true;
-        };
-        auto pwrite_all = [](int fd, const void *buf, size_t n, uint64_t off) {
-            const char *p = static_cast<const char *>(buf);
-            while (n) {
-                ssize_t r = pwrite(fd, p, n, (off_t)off);
-                if (r <= 0) return false;
-                p += r; off += (uint64_t)r; n -= (size_t)r;
-            }
-            return true;
-        };
         const double t1 = now();
 
         // ---- convert: largest tensors first; WORKERS_PER_DEVICE threads per GPU, each with its own
@@ -224,16 +314,17 @@ int ggq_convert_gguf(const char *in_path, const char *out_path, const char *step
         if (const char *wenv = getenv("GGQ_CONVERT_WORKERS")) { const int v = atoi(wenv); if (v >= 1 && v <= 32) WORKERS_PER_DEVICE = v; }
         std::vector<size_t> order(nt);
         for (size_t i = 0; i < nt; i++) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return f.tensors[a].nbytes > f.tensors[b].nbytes; });
+        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tensors[a].info->nbytes > tensors[b].info->nbytes; });
         std::atomic<size_t> next{0};
         std::atomic<int> rc_all{GGQ_OK};
         std::atomic<uint64_t> cast_elems{0}, cast_tensors{0};
         std::string first_err;
         std::mutex err_mu;
         const int ndev_avail = ggq_device_count();
-        int ndev = n_devices <= 0 ? ndev_avail : std::min(n_devices, ndev_avail);
+        int ndev = o.n_devices <= 0 ? ndev_avail : std::min(o.n_devices, ndev_avail);
         bool need_gpu = false;
-        for (size_t i = 0; i < nt; i++) need_gpu |= chains[i].size() > 1;
+        for (const auto &t : tensors) need_gpu |= t.chain.size() > 1;
+        if (o.no_data) need_gpu = false;
         if (need_gpu && ndev < 1) return failc(GGQ_ERR_CUDA, "no CUDA device (libggq has no CPU fallback)");
         if (ndev < 1) ndev = 1;
         auto set_err = [&](int rc, const std::string &m) {
@@ -247,16 +338,17 @@ int ggq_convert_gguf(const char *in_path, const char *out_path, const char *step
             for (;;) {
                 const size_t k = next.fetch_add(1);
                 if (k >= nt || rc_all.load() != GGQ_OK) return;
-                const size_t i = order[k];
-                const auto &t = f.tensors[i];
-                const uint64_t src_off = in_data_off + t.offset, dst_off = outs[i].file_offset;
-                if (chains[i].size() == 1) {  // untouched tensor: byte copy
+                const Tensor &t = tensors[order[k]];
+                const auto &ti = *t.info;
+                const int ifd = files[t.file]->fd, ofd = outs[t.shard]->fd;
+                const uint64_t src_off = files[t.file]->data_off + ti.offset, dst_off = t.out_off;
+                if (t.chain.size() == 1) {  // untouched tensor: byte copy
                     constexpr size_t CH = size_t(8) << 20;
-                    copy_buf.resize(std::min<uint64_t>(CH, t.nbytes));
-                    for (uint64_t o = 0; o < t.nbytes; o += CH) {
-                        const size_t n = (size_t)std::min<uint64_t>(CH, t.nbytes - o);
-                        if (!pread_all(ifd, copy_buf.data(), n, src_off + o) || !pwrite_all(ofd, copy_buf.data(), n, dst_off + o)) {
-                            set_err(GGQ_ERR_INVALID, "I/O error copying " + std::string(t.name));
+                    copy_buf.resize(std::min<uint64_t>(CH, ti.nbytes));
+                    for (uint64_t off = 0; off < ti.nbytes; off += CH) {
+                        const size_t n = (size_t)std::min<uint64_t>(CH, ti.nbytes - off);
+                        if (!pread_all(ifd, copy_buf.data(), n, src_off + off) || !pwrite_all(ofd, copy_buf.data(), n, dst_off + off)) {
+                            set_err(GGQ_ERR_INVALID, "I/O error copying " + std::string(ti.name));
                             return;
                         }
                     }
@@ -265,35 +357,44 @@ int ggq_convert_gguf(const char *in_path, const char *out_path, const char *step
                 ggq::ChainIO io;
                 io.read = [&](void *pinned, size_t off, size_t n) { return pread_all(ifd, pinned, n, src_off + off); };
                 io.write = [&](const void *pinned, size_t off, size_t n) { return pwrite_all(ofd, pinned, n, dst_off + off); };
-                const int rc = ggq::cast_chain_io(chains[i].data(), (int)chains[i].size(), t.n_elems(), io);
-                if (rc != GGQ_OK) { set_err(rc, std::string(t.name) + ": " + ggq_last_error()); return; }
-                cast_elems += t.n_elems();
+                const int rc = ggq::cast_chain_io(t.chain.data(), (int)t.chain.size(), ti.n_elems(), io);
+                if (rc != GGQ_OK) { set_err(rc, std::string(ti.name) + ": " + ggq_last_error()); return; }
+                cast_elems += ti.n_elems();
                 cast_tensors += 1;
             }
         };
-        std::vector<std::thread> th;
-        const int nworkers = ndev * (need_gpu ? WORKERS_PER_DEVICE : 1);
-        for (int w = 1; w < nworkers; w++) th.emplace_back(worker, w % ndev);
-        worker(0);
-        for (auto &x : th) x.join();
-        if (rc_all.load() != GGQ_OK) return failc(rc_all.load(), first_err);
+        if (!o.no_data) {
+            std::vector<std::thread> th;
+            const int nworkers = ndev * (need_gpu ? WORKERS_PER_DEVICE : 1);
+            for (int w = 1; w < nworkers; w++) th.emplace_back(worker, w % ndev);
+            worker(0);
+            for (auto &x : th) x.join();
+            if (rc_all.load() != GGQ_OK) return failc(rc_all.load(), first_err);
+        }
         const double t2 = now();
-        const double t3 = t2;  // like the reference writer, no fsync: the page cache owns the rest
         if (stats) {
             stats->n_tensors = nt;
             stats->n_cast_tensors = cast_tensors.load();
             stats->cast_elems = cast_elems.load();
-            stats->bytes_in = in.len;
-            stats->bytes_out = out_len;
+            stats->bytes_in = bytes_in;
+            stats->bytes_out = bytes_out;
             stats->seconds_plan = t1 - t0;
             stats->seconds_convert = t2 - t1;
-            stats->seconds_sync = t3 - t2;
+            stats->seconds_sync = 0.0;  // like the reference writer, no fsync: the page cache owns the rest
             stats->n_devices = ndev;
+            stats->n_out_files = (int)outs.size();
         }
         return GGQ_OK;
     } catch (const std::exception &e) {
         return failc(GGQ_ERR_INVALID, e.what());
     }
+}
+
+int ggq_convert_gguf(const char *in_path, const char *out_path, const char *steps, int n_devices, struct ggq_convert_stats *stats) {
+    ggq_convert_options o{};
+    o.n_devices = n_devices;
+    const char *ins[1] = {in_path};
+    return ggq_convert_gguf_ex(ins, in_path ? 1 : 0, out_path, steps, &o, stats);
 }
 
 }  // extern "C"

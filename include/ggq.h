@@ -137,6 +137,16 @@ struct ggq_convert_stats {
     uint64_t n_tensors, n_cast_tensors, cast_elems, bytes_in, bytes_out;
     double seconds_plan, seconds_convert, seconds_sync;
     int n_devices;
+    int n_out_files;
+};
+
+/* `OutputArgs` of xtask (xtask/src/utils/output.rs:8-53); zero means "unlimited" / "off". */
+struct ggq_convert_options {
+    int n_devices;          /* <= 0: every visible GPU */
+    uint64_t max_tensors;   /* -t: max tensors per output shard */
+    uint64_t max_bytes;     /* -s: max bytes per output shard (the reference parses "4G", "512M", ...) */
+    int no_tensor_first;    /* --no-tensor-first: shard 1 carries only the metadata */
+    int no_data;            /* --no-data: write header, KVs and tensor infos only */
 };
 
 /* `xtask convert FILE --steps "cast:linear:q8_0 embd:q8_0 -> cast:linear:f32 ..."` —
@@ -149,6 +159,16 @@ struct ggq_convert_stats {
  * `split.*`), tensor infos, alignment-padded data.  `stats` may be NULL. */
 int ggq_convert_gguf(const char *in_path, const char *out_path, const char *steps, int n_devices,
                      struct ggq_convert_stats *stats);
+
+/* The same with the rest of the reference's pipeline around it: several input shards are merged as
+ * `Content::new` does (xtask/src/utils/read.rs:5-62: alignment = max, `general.alignment` and `split.*`
+ * dropped, duplicate keys / tensor names rejected) and the output is split into shards by the
+ * reference's planner (xtask/src/utils/write.rs:23-51 over the byte accounting of
+ * ggus/src/write/simulator.rs:75-96).  Shard i of N > 1 is written to
+ * "<out_path without .gguf>-0000i-of-0000N.gguf" (ggus/src/name/shard.rs:30-39); only shard 1 carries
+ * the metadata KVs (write.rs:72-81).  `opts` may be NULL (defaults: all GPUs, one shard). */
+int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *out_path, const char *steps,
+                        const struct ggq_convert_options *opts, struct ggq_convert_stats *stats);
 const char *ggq_convert_last_error(void);
 
 /* ---- memory helpers ------------------------------------------------------------------------ */

@@ -192,3 +192,112 @@ def test_cast_api_pairs_the_reference_leaves_unimplemented(ggq, oracle):
     assert lib().ggq_cast(chain, 2, out2.ctypes.data, q4.ctypes.data, x.size) == 0
     assert np.array_equal(out2, oracle.quantize(8, 0, oracle.dequantize(2, 0, q4)))
     assert lib().ggq_cast(chain, 2, out2.ctypes.data, q4.ctypes.data, 31) == 1  # Indivisible
+
+
+def _plan_reference(kvs, tensors, alignment, max_tensors=None, max_bytes=None, no_tensor_first=False):
+    """Independent restatement of xtask/src/utils/write.rs:23-51 + ggus/src/write/simulator.rs:75-96."""
+    from gguf_util import kv_bytes
+    pad = lambda p: (alignment - p % alignment) % alignment
+    kvb = sum(len(kv_bytes(k, t, v)) for k, t, v in kvs if k != "general.alignment" and not k.startswith("split."))
+    akv = 8 + len("general.alignment") + 4 + 4
+    info = lambda name, shape: 8 + len(name.encode()) + 4 + 8 * len(shape) + 4 + 8
+    max_tensors = max_tensors or 1 << 62
+    max_bytes = max_bytes or 1 << 62
+
+    class Sim:
+        def __init__(self, kvb):
+            self.w, self.data = 24 + akv + kvb, []
+        def write(self, t):
+            self.w += info(t[0], t[1]); self.data.append(len(t[3]))
+        def total(self):
+            tot = self.w
+            for n in self.data:
+                tot += pad(tot) + n
+            return tot
+    sim, shards = Sim(kvb), [[]]
+    for t in tensors:
+        if len(shards) == 1 and no_tensor_first:
+            sim = Sim(0); sim.write(t); shards.append([t[0]]); continue
+        sim.write(t)
+        if len(shards[-1]) < max_tensors and sim.total() < max_bytes:
+            shards[-1].append(t[0])
+        else:
+            sim = Sim(0); sim.write(t); shards.append([t[0]])
+    return shards
+
+
+@pytest.mark.parametrize("opts", [dict(max_tensors=3), dict(max_bytes="200K"), dict(max_bytes=150000, max_tensors=4),
+                                  dict(no_tensor_first=True), dict(no_tensor_first=True, max_tensors=5)])
+def test_output_sharding_follows_reference_planner(ggq, tmp_path, opts):
+    """Copy-only (no GPU needed): shard contents, names, KV placement and round trip through a merge."""
+    from gguf_b200.convert import convert, parse_mem_size
+    src = tmp_path / "in.gguf"
+    ts = llama_like(rng_seed=3)
+    write_gguf(src, KVS, ts, alignment=64)
+    st = convert(src, tmp_path / "model.gguf", "", **opts)
+    want = _plan_reference(KVS, ts, 64, opts.get("max_tensors"), parse_mem_size(opts.get("max_bytes")), opts.get("no_tensor_first", False))
+    n = len(want)
+    assert st["n_out_files"] == n and n > 1
+    paths = [tmp_path / f"model-{i + 1:05d}-of-{n:05d}.gguf" for i in range(n)]
+    by_name = {t[0]: t for t in ts}
+    for i, (path, names) in enumerate(zip(paths, want)):
+        kvs, tensors, alignment, _ = read_gguf(path)
+        assert alignment == 64 and list(tensors) == names
+        assert [k for k, _, _ in kvs] == (["general.alignment", "general.architecture", "general.name", "llama.block_count",
+                                           "tokenizer.ggml.tokens"] if i == 0 else ["general.alignment"])
+        for name in names:
+            assert tensors[name] == by_name[name][1:]
+    # merging the shards back (Content::new over several files) reproduces the single-file conversion
+    convert(src, tmp_path / "single.gguf", "")
+    convert(paths, tmp_path / "merged.gguf", "")
+    assert open(tmp_path / "single.gguf", "rb").read() == open(tmp_path / "merged.gguf", "rb").read()
+
+
+def test_no_data_writes_infos_only(ggq, tmp_path):
+    """--no-data (output.rs:22-24): header, KVs and tensor infos, no tensor bytes — how the reference's own
+    fixture test-files/TinyLlama-1.1B-Chat-v1.0-F16.gguf was produced."""
+    from gguf_b200.convert import convert
+    import struct
+    src, dst = tmp_path / "in.gguf", tmp_path / "nodata.gguf"
+    ts = llama_like()
+    write_gguf(src, KVS, ts, alignment=64)
+    st = convert(src, dst, "cast:linear:q8_0", no_data=True)   # types change in the infos, nothing is computed
+    blob = open(dst, "rb").read()
+    assert st["bytes_out"] == len(blob) and st["n_cast_tensors"] == 0
+    assert struct.unpack_from("<IQQ", blob, 4) == (3, len(ts), 5)
+    full = tmp_path / "full.gguf"
+    assert len(blob) < os.path.getsize(src) // 4
+    assert blob.count(b"blk.0.attn_q.weight") == 1
+
+
+def test_merge_rejects_duplicates_across_inputs(ggq, tmp_path):
+    from gguf_b200.convert import convert
+    a, b = tmp_path / "a.gguf", tmp_path / "b.gguf"
+    ts = llama_like()
+    write_gguf(a, KVS, ts[:4], alignment=64)
+    write_gguf(b, [("general.alignment", U32, 32)], ts[3:6], alignment=32)
+    with pytest.raises(ggq.GgqError) as e:
+        convert([a, b], tmp_path / "o.gguf", "")
+    assert "DuplicateTensorName" in str(e.value)
+    write_gguf(b, [("general.alignment", U32, 32), ("split.no", U32, 1)], ts[4:6], alignment=32)
+    st = convert([a, b], tmp_path / "o.gguf", "")
+    kvs, tensors, alignment, _ = read_gguf(tmp_path / "o.gguf")
+    assert alignment == 64 and list(tensors) == [t[0] for t in ts[:6]]   # alignment = max over inputs
+
+
+@pytest.mark.gpu
+def test_sharded_convert_with_cast_matches_oracle(ggq, oracle, tmp_path):
+    from gguf_b200.convert import convert
+    src = tmp_path / "in.gguf"
+    ts = llama_like(rng_seed=21)
+    write_gguf(src, KVS, ts, alignment=64)
+    st = convert(src, tmp_path / "q.gguf", "cast:linear:q4k embd:q6k", max_tensors=4)
+    n = st["n_out_files"]
+    want = _expect(oracle, ts, [dict(linear=12, embd=14)])
+    seen = {}
+    for i in range(n):
+        _, tensors, _, _ = read_gguf(tmp_path / f"q-{i + 1:05d}-of-{n:05d}.gguf")
+        seen.update(tensors)
+    assert list(seen) == [t[0] for t in ts]
+    for name, (shape, ty, data) in seen.items():
+        assert (ty, data) == want[name], name
