@@ -359,3 +359,35 @@ def test_shutdown_releases_and_pool_refills(ggq, oracle):
     lib().ggq_shutdown()
     lib().ggq_shutdown()
     assert np.array_equal(ggq.quantize(8, x), a) and np.array_equal(a, oracle.quantize(8, F32, x))
+
+
+def test_fuzz_random_small_cases(ggq, oracle):
+    """300 random (type, float side, direction, block count, pointer offset) cases through the device API,
+    each compared with the oracle bit for bit.  Block counts straddle the tile sizes of every kernel."""
+    import torch
+    rng = np.random.default_rng(20261018)
+    st = torch.cuda.current_stream().cuda_stream
+    sizes32 = [1, 2, 3, 7, 8, 9, 31, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 513, 1023, 1025, 2047, 4099]
+    sizes256 = [1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 65, 127, 129, 300]
+    for case in range(300):
+        ty = int(rng.choice(ALLQ))
+        fdt = int(rng.choice(FDTS))
+        n, b = oracle.block_info(ty)
+        nb = int(rng.choice(sizes32 if n == 32 else sizes256))
+        foff = int(rng.choice([0, 4, 8, 16])) if fdt == F32 else int(rng.choice([0, 2, 6, 16]))
+        poff = int(rng.choice([0, 2, 4, 16]))
+        scale = float(rng.choice([1e-3, 0.02, 1.0, 30.0]))
+        x = to_fdt(gaussian(n * nb, 5000 + case, scale), fdt)
+        want_q = oracle.quantize(ty, fdt, x)
+        src = torch.zeros(x.nbytes + 64, dtype=torch.uint8, device="cuda")
+        src[foff:foff + x.nbytes] = torch.from_numpy(x.view(np.uint8)).cuda()
+        q = torch.zeros(nb * b + 64, dtype=torch.uint8, device="cuda")
+        ggq.quantize_slice_device(ty, fdt, q.data_ptr() + poff, nb, src.data_ptr() + foff, n * nb, st)
+        d = torch.zeros(x.nbytes + 64, dtype=torch.uint8, device="cuda")
+        ggq.dequantize_slice_device(ty, fdt, d.data_ptr() + foff, n * nb, q.data_ptr() + poff, nb, st)
+        torch.cuda.synchronize()
+        gq = q.cpu().numpy()[poff:poff + nb * b]
+        assert same_blocks(gq, want_q, ty, b), (case, ty, fdt, nb, foff, poff)
+        want_d = oracle.dequantize(ty, fdt, want_q)
+        gd = d.cpu().numpy()[foff:foff + x.nbytes].view(want_d.dtype)
+        assert same_floats(gd, want_d), (case, ty, fdt, nb, foff, poff)
