@@ -310,7 +310,7 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
 
         // ---- convert: largest tensors first; WORKERS_PER_DEVICE threads per GPU, each with its own
         // stream pipeline, so one tensor's pread overlaps another's kernels / D2H / pwrite ----
-        int WORKERS_PER_DEVICE = 4;  // GGQ_CONVERT_WORKERS overrides (file I/O is the bound, not the GPU)
+        int WORKERS_PER_DEVICE = 8;  // GGQ_CONVERT_WORKERS overrides (file I/O is the bound, not the GPU)
         if (const char *wenv = getenv("GGQ_CONVERT_WORKERS")) { const int v = atoi(wenv); if (v >= 1 && v <= 32) WORKERS_PER_DEVICE = v; }
         std::vector<size_t> order(nt);
         for (size_t i = 0; i < nt; i++) order[i] = i;

@@ -52,6 +52,11 @@ for _ in range(2):
     if os.path.exists(dst): os.unlink(dst)
     t = time.time(); st = convert(src, dst, steps, gpus); runs.append(time.time() - t)
 print("gpu convert s/file:", ["%.2f" % r for r in runs], st, flush=True)
+# sharded output (-s 1G): each shard is its own inode, so the buffered writes no longer serialise
+import glob
+t = time.time(); st_sh = convert(src, os.path.join(tmp, "llama8b_sh.gguf"), steps, gpus, max_bytes="1G"); t_sharded = time.time() - t
+for f_ in glob.glob(os.path.join(tmp, "llama8b_sh-*.gguf")): os.unlink(f_)
+print("sharded (-s 1G):", "%.2f s" % t_sharded, st_sh["n_out_files"], "files", flush=True)
 
 # ---- verify a strided sample of super-blocks of every cast tensor against the oracle ----
 threads = os.cpu_count() or 1
@@ -81,6 +86,7 @@ cpu_rate = n_lin / cpu_seconds
 res = {"config": "Llama-3-8B-shaped synthetic F16 -> Q5_K (linear) / Q6_K (embd) whole-file convert (BASELINE configs[4] scaled from 70B / 8 GPUs)",
        "layers": layers, "tensors": len(shapes), "linear_elements": n_lin, "file_in_GB": os.path.getsize(src) / 1e9, "file_out_GB": out_size / 1e9,
        "gpu_seconds_per_file": min(runs), "gpu_runs": runs, "n_devices": st["n_devices"], "stats_last": st,
+       "gpu_seconds_per_file_sharded_1G": t_sharded, "sharded_files": st_sh["n_out_files"],
        "sampled_super_blocks": sampled, "mismatching_super_blocks": bad,
        "cpu_oracle_elements_per_second": cpu_rate, "cpu_threads": threads,
        "cpu_oracle_q5k_Melem_per_s": xb.size / t5 / 1e6, "cpu_oracle_q6k_Melem_per_s": xb.size / t6 / 1e6,

@@ -18,13 +18,22 @@ for nt in (1, 4):
     [x.start() for x in th]; [x.join() for x in th]
     dt = time.time() - t; os.close(fd)
     print(f"buffered pwrite, {nt} thread(s): {dt:.3f} s  {N/dt/1e9:.2f} GB/s", flush=True)
-fd = fresh(); mm = mmap.mmap(fd, N); view = np.frombuffer(mm, dtype=np.uint8); src = np.frombuffer(buf, dtype=np.uint8)
-def mc(lo, hi):
-    o = lo
-    while o < hi:
-        n = min(len(src), hi - o); view[o:o + n] = src[:n]; o += n
-t = time.time()
-th = [threading.Thread(target=mc, args=(N * k // 4, N * (k + 1) // 4)) for k in range(4)]
-[x.start() for x in th]; [x.join() for x in th]
-print(f"memcpy into MAP_SHARED mapping, 4 threads: {time.time()-t:.3f} s  {N/(time.time()-t)/1e9:.2f} GB/s")
-del view; mm.close(); os.close(fd); os.unlink(path)
+for nt in (4, 8, 16):
+    fd = fresh(); mm = mmap.mmap(fd, N); view = np.frombuffer(mm, dtype=np.uint8); src = np.frombuffer(buf, dtype=np.uint8)
+    def mc(lo, hi):
+        o = lo
+        while o < hi:
+            n = min(len(src), hi - o); view[o:o + n] = src[:n]; o += n
+    t = time.time()
+    th = [threading.Thread(target=mc, args=(N * k // nt, N * (k + 1) // nt)) for k in range(nt)]
+    [x.start() for x in th]; [x.join() for x in th]
+    dt = time.time() - t
+    print(f"memcpy into MAP_SHARED mapping, {nt} threads: {dt:.3f} s  {N/dt/1e9:.2f} GB/s", flush=True)
+    del view; mm.close(); os.close(fd)
+for nt in (8, 16):
+    fd = fresh(); t = time.time()
+    th = [threading.Thread(target=pw, args=(fd, N * k // nt, N * (k + 1) // nt)) for k in range(nt)]
+    [x.start() for x in th]; [x.join() for x in th]
+    dt = time.time() - t; os.close(fd)
+    print(f"buffered pwrite, {nt} thread(s): {dt:.3f} s  {N/dt/1e9:.2f} GB/s", flush=True)
+os.unlink(path)
