@@ -4,4 +4,6 @@ from .quants import (BF16, BLOCK_TYPES, F16, F32, FLOAT_TYPES, Q2K, Q3K, Q4_0, Q
                      Q8_1, Q8K, TYPE_NAMES, GgqError, PinnedBuffer, QuantizeError, block_info, dequantize,
                      dequantize_slice, dequantize_slice_device, quantize, quantize_slice, quantize_slice_device, slices)
 
+from .rearrange import ArrayLayout, concat, permute_qk, rearrange, rearrange_device, split
+
 __all__ = [n for n in dir() if not n.startswith("_")]

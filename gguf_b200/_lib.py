@@ -43,7 +43,7 @@ class SliceJob(_c.Structure):
 class ConvertStats(_c.Structure):
     _fields_ = [("n_tensors", _c.c_uint64), ("n_cast_tensors", _c.c_uint64), ("cast_elems", _c.c_uint64), ("bytes_in", _c.c_uint64),
                 ("bytes_out", _c.c_uint64), ("seconds_plan", _c.c_double), ("seconds_convert", _c.c_double),
-                ("seconds_sync", _c.c_double), ("n_devices", _c.c_int), ("n_out_files", _c.c_int)]
+                ("seconds_sync", _c.c_double), ("n_devices", _c.c_int), ("n_out_files", _c.c_int), ("n_rearranged_tensors", _c.c_uint64)]
 
 
 class ConvertOptions(_c.Structure):
@@ -51,7 +51,14 @@ class ConvertOptions(_c.Structure):
                 ("no_data", _c.c_int)]
 
 
+class Layout(_c.Structure):
+    """struct ggq_layout: ndarray-layout's ArrayLayout<4> (shape in units, strides / offset in bytes)."""
+    _fields_ = [("ndim", _c.c_uint32), ("shape", _c.c_uint64 * 4), ("strides", _c.c_int64 * 4), ("offset", _c.c_int64)]
+
+
 SYMBOLS += [
+    ("ggq_rearrange_device", _c.c_int, [_c.c_void_p, _c.POINTER(Layout), _c.c_void_p, _c.POINTER(Layout), _c.c_size_t, _c.c_void_p]),
+    ("ggq_rearrange", _c.c_int, [_c.c_void_p, _c.POINTER(Layout), _c.c_void_p, _c.POINTER(Layout), _c.c_size_t]),
     ("ggq_slices", _c.c_int, [_c.POINTER(SliceJob), _c.c_size_t]),
     ("ggq_convert_gguf", _c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_int, _c.POINTER(ConvertStats)]),
     ("ggq_convert_gguf_ex", _c.c_int, [_c.POINTER(_c.c_char_p), _c.c_size_t, _c.c_char_p, _c.c_char_p, _c.POINTER(ConvertOptions),

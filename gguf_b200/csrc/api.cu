@@ -495,9 +495,180 @@ int plan_cast(const uint32_t *types, int n_types, size_t n_elems, std::vector<ui
     return GGQ_OK;
 }
 
+// ---- rearrange (mem-rearrange's Rearranging) ---------------------------------------------------------
+int plan_rearrange(const ggq_layout *dl, const ggq_layout *sl, size_t unit, StridedLayout *d, StridedLayout *s) {
+    if (!dl || !sl) return fail(GGQ_ERR_INVALID, "null layout");
+    if (dl->ndim > GGQ_MAX_NDIM || sl->ndim > GGQ_MAX_NDIM) return fail(GGQ_ERR_INVALID, "layout has more than GGQ_MAX_NDIM dims");
+    if (unit == 0) return fail(GGQ_ERR_INVALID, "unit is zero");
+    if (dl->ndim != sl->ndim) return fail(GGQ_ERR_LENGTH_MISMATCH, "ShapeMismatch: dst and src layouts differ in ndim");
+    d->ndim = s->ndim = (int)dl->ndim;
+    d->offset = dl->offset;
+    s->offset = sl->offset;
+    for (uint32_t i = 0; i < dl->ndim; i++) {
+        if (dl->shape[i] != sl->shape[i]) return fail(GGQ_ERR_LENGTH_MISMATCH, "ShapeMismatch: dst and src layouts differ in shape");
+        if (dl->shape[i] > 1 && dl->strides[i] == 0) return fail(GGQ_ERR_INVALID, "dst layout has a zero stride on a dim of extent > 1");
+        d->shape[i] = s->shape[i] = dl->shape[i];
+        d->strides[i] = dl->strides[i];
+        s->strides[i] = sl->strides[i];
+    }
+    return GGQ_OK;
+}
+
+// [lo, hi) byte range a layout addresses relative to its base pointer; false when it addresses nothing
+bool layout_span(const ggq_layout &l, size_t unit, int64_t *lo, int64_t *hi, uint64_t *addressed) {
+    int64_t a = l.offset, b = l.offset;
+    uint64_t n = unit;
+    for (uint32_t i = 0; i < l.ndim; i++) {
+        if (l.shape[i] == 0) return false;
+        const int64_t ext = (int64_t)(l.shape[i] - 1) * l.strides[i];
+        (ext < 0 ? a : b) += ext;
+        n *= l.shape[i];
+    }
+    *lo = a;
+    *hi = b + (int64_t)unit;
+    *addressed = n;
+    return true;
+}
+
+int rearrange_on_stream(void *dst, const ggq_layout *dl, const void *src, const ggq_layout *sl, size_t unit, cudaStream_t st) {
+    StridedLayout d, s;
+    int rc = plan_rearrange(dl, sl, unit, &d, &s);
+    if (rc != GGQ_OK) return rc;
+    uint64_t launches = 0;
+    cudaError_t e = rearrange_strided(dst, d, src, s, unit, st, &launches);
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail_cuda(e, "rearrange");
+    return GGQ_OK;
+}
+
+std::once_flag g_pool_cfg[MAX_DEVICES];
+void configure_mem_pool(int device) {  // keep freed stream-ordered allocations cached instead of returning them to the OS
+    std::call_once(g_pool_cfg[device], [device] {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    });
+}
+
 }  // namespace
 
 namespace ggq {
+
+struct Resident::Impl {
+    DevInfo dev;
+    Pipeline *pl = nullptr;
+    cudaStream_t stream = nullptr;
+    std::vector<void *> live;
+};
+
+Resident::Resident() : impl_(new Impl()) {
+    if ((status_ = resolve_device(&impl_->dev)) != GGQ_OK) return;
+    if ((status_ = acquire_pipeline(impl_->dev.device, &impl_->pl)) != GGQ_OK) return;
+    impl_->stream = impl_->pl->slots[0].stream;
+    configure_mem_pool(impl_->dev.device);
+    cudaError_t e = cudaSuccess;
+    for (auto &s : impl_->pl->slots) {
+        if (!s.h_in && (e = cudaHostAlloc(&s.h_in, SLOT_BYTES, cudaHostAllocDefault)) != cudaSuccess) break;
+        if (!s.h_out && (e = cudaHostAlloc(&s.h_out, SLOT_BYTES, cudaHostAllocDefault)) != cudaSuccess) break;
+    }
+    if (e != cudaSuccess) status_ = fail_cuda(e, "cudaHostAlloc");
+}
+
+Resident::~Resident() {
+    if (impl_->pl) {
+        for (void *p : impl_->live) cudaFreeAsync(p, impl_->stream);
+        cudaStreamSynchronize(impl_->stream);
+        cudaGetLastError();
+        release_pipeline(impl_->pl);
+    }
+    delete impl_;
+}
+
+int Resident::alloc(size_t nbytes, void **d) {
+    cudaError_t e = cudaMallocAsync(d, nbytes ? nbytes : 1, impl_->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMallocAsync");
+    impl_->live.push_back(*d);
+    return GGQ_OK;
+}
+
+void Resident::free(void *d) {
+    auto it = std::find(impl_->live.begin(), impl_->live.end(), d);
+    if (it == impl_->live.end()) return;
+    impl_->live.erase(it);
+    cudaFreeAsync(d, impl_->stream);
+}
+
+// pread (or memcpy) chunk c+1 into a pinned buffer while chunk c's H2D runs
+int Resident::upload(void *d_dst, size_t nbytes, const ReadFn &read) {
+    constexpr size_t CH = size_t(16) << 20;
+    size_t c = 0;
+    for (size_t off = 0; off < nbytes; off += CH, c++) {
+        Slot &s = impl_->pl->slots[c % NSLOTS];
+        const size_t n = std::min(CH, nbytes - off);
+        cudaError_t e = cudaEventSynchronize(s.done);  // the H2D that last used this bounce buffer
+        if (e != cudaSuccess) return fail_cuda(e, "upload");
+        if (!read(s.h_in, off, n)) return fail(GGQ_ERR_INVALID, "I/O callback failed while uploading a tensor");
+        if ((e = cudaMemcpyAsync(static_cast<char *>(d_dst) + off, s.h_in, n, cudaMemcpyHostToDevice, impl_->stream)) != cudaSuccess ||
+            (e = cudaEventRecord(s.done, impl_->stream)) != cudaSuccess)
+            return fail_cuda(e, "upload");
+    }
+    return GGQ_OK;
+}
+
+// D2H of chunk c+1 and c+2 run while chunk c is handed to `write`
+int Resident::download(const void *d_src, size_t nbytes, const WriteFn &write) {
+    constexpr size_t CH = size_t(16) << 20;
+    const size_t nch = (nbytes + CH - 1) / CH;
+    for (size_t c = 0; c < nch + (NSLOTS - 1); c++) {
+        if (c < nch) {
+            Slot &s = impl_->pl->slots[c % NSLOTS];
+            const size_t off = c * CH, n = std::min(CH, nbytes - off);
+            cudaError_t e;
+            if ((e = cudaMemcpyAsync(s.h_out, static_cast<const char *>(d_src) + off, n, cudaMemcpyDeviceToHost, impl_->stream)) != cudaSuccess ||
+                (e = cudaEventRecord(s.done, impl_->stream)) != cudaSuccess)
+                return fail_cuda(e, "download");
+        }
+        if (c >= NSLOTS - 1) {
+            const size_t r = c - (NSLOTS - 1);
+            Slot &s = impl_->pl->slots[r % NSLOTS];
+            const size_t off = r * CH, n = std::min(CH, nbytes - off);
+            cudaError_t e = cudaEventSynchronize(s.done);
+            if (e != cudaSuccess) return fail_cuda(e, "download");
+            if (!write(s.h_out, off, n)) return fail(GGQ_ERR_INVALID, "I/O callback failed while downloading a tensor");
+        }
+    }
+    return GGQ_OK;
+}
+
+int Resident::cast(const uint32_t *types, int n_types, size_t n_elems, void *d_dst, const void *d_src) {
+    std::vector<uint32_t> chain;
+    int rc = plan_cast(types, n_types, n_elems, &chain);
+    if (rc != GGQ_OK) return rc;
+    if (chain.size() == 1) {
+        cudaError_t e = cudaMemcpyAsync(d_dst, d_src, type_nbytes(chain[0], n_elems), cudaMemcpyDeviceToDevice, impl_->stream);
+        return e == cudaSuccess ? GGQ_OK : fail_cuda(e, "cast (copy)");
+    }
+    const void *cur = d_src;
+    void *tmp_prev = nullptr;
+    for (size_t h = 0; h + 1 < chain.size(); h++) {
+        void *out = d_dst;
+        if (h + 2 < chain.size() && (rc = alloc(type_nbytes(chain[h + 1], n_elems), &out)) != GGQ_OK) return rc;
+        cudaError_t e = enqueue_hop(chain[h], chain[h + 1], out, cur, n_elems, impl_->stream, impl_->dev);
+        if (e != cudaSuccess) return fail_cuda(e, "cast");
+        if (tmp_prev) free(tmp_prev);
+        tmp_prev = out == d_dst ? nullptr : out;
+        cur = out;
+    }
+    return GGQ_OK;
+}
+
+int Resident::rearrange(void *d_dst, const ggq_layout &dl, const void *d_src, const ggq_layout &sl, size_t unit) {
+    return rearrange_on_stream(d_dst, &dl, d_src, &sl, unit, impl_->stream);
+}
+
 // internal (not part of the C ABI): used by convert.cpp to stream files through the pipeline
 int cast_chain_io(const uint32_t *types, int n_types, size_t n_elems, const ChainIO &io) {
     std::vector<uint32_t> chain;
@@ -619,6 +790,44 @@ int ggq_cast(const uint32_t *types, int n_types, void *dst, const void *src, siz
     return rc != GGQ_OK ? rc : run_chain_host(chain, dst, src, n_elems);
 }
 
+int ggq_rearrange_device(void *dst, const struct ggq_layout *dl, const void *src, const struct ggq_layout *sl, size_t unit, void *stream) {
+    StridedLayout d, s;
+    int rc = plan_rearrange(dl, sl, unit, &d, &s);  // validation first: no CUDA call is needed to reject a bad layout
+    if (rc != GGQ_OK) return rc;
+    if (!dst || !src) return fail(GGQ_ERR_INVALID, "null pointer");
+    DevInfo dev;
+    if ((rc = resolve_device(&dev)) != GGQ_OK) return rc;
+    return rearrange_on_stream(dst, dl, src, sl, unit, static_cast<cudaStream_t>(stream));
+}
+
+int ggq_rearrange(void *dst, const struct ggq_layout *dl, const void *src, const struct ggq_layout *sl, size_t unit) {
+    StridedLayout d, s;
+    int rc = plan_rearrange(dl, sl, unit, &d, &s);
+    if (rc != GGQ_OK) return rc;
+    int64_t dlo, dhi, slo, shi;
+    uint64_t dn, sn;
+    if (!layout_span(*dl, unit, &dlo, &dhi, &dn) || !layout_span(*sl, unit, &slo, &shi, &sn)) return GGQ_OK;  // empty shape
+    if (!dst || !src) return fail(GGQ_ERR_INVALID, "null pointer");
+    if (pointer_kind(src) == cudaMemoryTypeDevice || pointer_kind(dst) == cudaMemoryTypeDevice)
+        return fail(GGQ_ERR_INVALID, "device pointer passed to a host-pointer entry point (use ggq_rearrange_device)");
+    const size_t dbytes = (size_t)(dhi - dlo), sbytes = (size_t)(shi - slo);
+    const char *hs = static_cast<const char *>(src) + slo;
+    char *hd = static_cast<char *>(dst) + dlo;
+    ggq::Resident res;
+    if (res.status() != GGQ_OK) return res.status();
+    void *d_src = nullptr, *d_dst = nullptr;
+    if ((rc = res.alloc(sbytes, &d_src)) != GGQ_OK || (rc = res.alloc(dbytes, &d_dst)) != GGQ_OK) return rc;
+    if ((rc = res.upload(d_src, sbytes, [hs](void *pinned, size_t off, size_t n) { parallel_memcpy(pinned, hs + off, n); return true; })) != GGQ_OK) return rc;
+    if (dn != dbytes)  // the layout leaves holes in its span: keep what the caller has there
+        if ((rc = res.upload(d_dst, dbytes, [hd](void *pinned, size_t off, size_t n) { parallel_memcpy(pinned, hd + off, n); return true; })) != GGQ_OK) return rc;
+    // device buffers start at the lowest addressed byte: shift the offsets
+    ggq_layout dl2 = *dl, sl2 = *sl;
+    dl2.offset -= dlo;
+    sl2.offset -= slo;
+    if ((rc = res.rearrange(d_dst, dl2, d_src, sl2, unit)) != GGQ_OK) return rc;
+    return res.download(d_dst, dbytes, [hd](const void *pinned, size_t off, size_t n) { parallel_memcpy(hd + off, pinned, n); return true; });
+}
+
 size_t ggq_type_nbytes(uint32_t type, size_t n_elems) {
     size_t e, b;
     if (!type_geometry(type, &e, &b) || n_elems % e) return 0;
@@ -649,6 +858,11 @@ void ggq_shutdown(void) {
     for (Pipeline *p : idle) {
         cudaSetDevice(p->device);
         destroy_pipeline(p);
+    }
+    const int ndev = ggq_device_count();
+    for (int d = 0; d < ndev && d < MAX_DEVICES; d++) {  // give cached stream-ordered allocations back
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     }
     if (cur >= 0) cudaSetDevice(cur);
     cudaGetLastError();

@@ -1,6 +1,17 @@
-// convert.cpp — whole-file GGUF conversion on the GPUs: the `xtask convert --steps "cast:…->cast:…"`
-// path (/root/reference/xtask/src/convert.rs:24-58 → utils/mod.rs:36-59 → operator/cast.rs:28-138 →
-// utils/write.rs:6-100), restricted to `cast:` steps, the only operator that touches tensor values.
+// convert.cpp — whole-file GGUF conversion on the GPUs: the `xtask convert --steps "a -> b -> c"`
+// path (/root/reference/xtask/src/convert.rs:24-58 → utils/mod.rs:36-59 → operator/*.rs →
+// utils/write.rs:6-100) for the operators that touch tensor bytes: `cast:` (operator/cast.rs:28-138),
+// `merge-linear` / `split-linear` (operator/merge.rs) and `permute-qk` (operator/permute_qk.rs).
+//
+// Like the reference, operators do not move data when they are applied: each tensor becomes a small
+// expression (source bytes of a file, cast chain, concat, split, row permutation) that is evaluated
+// when the tensor is written (the reference's `DataPromise::lazy`, utils/mod.rs:104-138).  Expressions
+// are normalised while they are built — casts and splits commute with whole-row moves, so a split
+// of a file tensor is a sub-range of the file, a cast of a concat is a concat of casts, and a concat
+// along the slowest axis writes its parts next to each other — which leaves exactly two ways to
+// produce bytes: the streaming pipeline (file → pinned → H2D → cast kernels → D2H → file) and, for
+// tensors whose rows really are rearranged (permute-qk, 3-D expert merges), a device-resident
+// evaluation: upload, strided-copy kernels (rearrange.cu) and cast kernels, download.
 //
 // What changes against the reference pipeline:
 //   * all casts of a tensor are one device-resident chain (F16→Q8_0→F32→F16 never returns to the host
@@ -21,6 +32,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <initializer_list>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -30,6 +44,7 @@
 #include <vector>
 
 #include "../../include/ggq.h"
+#include "../host/array_layout.hpp"
 #include "../host/gguf.hpp"
 #include "ggq_internal.h"
 
@@ -112,14 +127,229 @@ struct InFile {
     ~InFile() { if (fd >= 0) close(fd); }
 };
 
-struct Tensor {                 // one tensor of the merged content (read.rs:49-59)
-    const gguf::TensorInfo *info;
-    int file;                   // index into the input files
-    std::vector<uint32_t> chain;
-    uint64_t out_nbytes;
+struct StepError { int code; std::string msg; };  // thrown while applying operators (the reference panics)
+
+// ---- tensor expressions ---------------------------------------------------------------------------
+struct Node;
+using NodeP = std::shared_ptr<const Node>;
+struct Node {
+    enum Kind { SOURCE, CAST, CONCAT, SPLIT, PERMUTE } kind = SOURCE;
+    uint32_t type = 0;
+    std::vector<uint64_t> shape;   // ggml order: shape[0] is the contiguous row
+    std::vector<NodeP> in;
+    int file = -1;                 // SOURCE: input file and absolute byte offset
+    uint64_t file_off = 0;
+    std::vector<uint32_t> chain;   // CAST: in[0]->type ... type
+    size_t axis = 0;               // CONCAT / SPLIT
+    uint64_t start = 0;            // SPLIT: first element along `axis`
+    uint64_t nh = 0;               // PERMUTE: heads
+};
+
+uint64_t count(const std::vector<uint64_t> &shape) { uint64_t n = 1; for (uint64_t d : shape) n *= d; return n; }
+// GGmlTypeSize::elements_to_bytes (ggus/src/tensor.rs:83-96)
+uint64_t nbytes_of(uint32_t type, const std::vector<uint64_t> &shape) {
+    uint64_t be = 1, bb = 1;
+    gguf::type_size(type, &be, &bb);
+    if (shape.empty()) return bb;
+    return count(shape) / be * bb;
+}
+uint64_t nbytes_of(const Node &n) { return nbytes_of(n.type, n.shape); }
+// merge.rs:359-364 `layout(ty, shape)`: shape[0] in blocks, element = one block
+ndl::ArrayLayout block_layout(uint32_t type, std::vector<uint64_t> shape, uint64_t *unit) {
+    uint64_t be = 1, bb = 1;
+    gguf::type_size(type, &be, &bb);
+    if (!shape.empty()) shape[0] /= be;
+    *unit = bb;
+    return ndl::ArrayLayout::new_contiguous(shape, bb);
+}
+// parts of a concat / split along `axis` sit next to each other in memory when no slower dim has extent > 1
+bool axis_is_slowest(const std::vector<uint64_t> &shape, size_t axis) {
+    for (size_t i = axis + 1; i < shape.size(); i++) if (shape[i] != 1) return false;
+    return true;
+}
+
+NodeP make_cast(const NodeP &x, uint32_t to, const std::string &name) {
+    if (x->type == to) return x;
+    uint64_t be, bb;
+    if (!gguf::type_size(to, &be, &bb) || ggq_type_nbytes(to, be) == 0 || ggq_type_nbytes(x->type, 256) == 0)
+        throw StepError{GGQ_ERR_UNSUPPORTED, "cast chain of " + name + " has an unsupported type"};
+    if (x->shape.empty() || x->shape[0] % be)  // cast.rs:142-143 `assert_eq!(row % N, 0)`
+        throw StepError{GGQ_ERR_INDIVISIBLE, "row of " + name + " is not a multiple of the target block size"};
+    auto n = std::make_shared<Node>();
+    if (x->kind == Node::CAST) {  // one chain: intermediates stay on the device
+        *n = *x;
+        n->chain.push_back(to);
+    } else if (x->kind == Node::CONCAT && axis_is_slowest(x->shape, x->axis)) {  // blocks never straddle rows
+        *n = *x;
+        for (auto &c : n->in) c = make_cast(c, to, name);
+    } else {
+        n->kind = Node::CAST;
+        n->shape = x->shape;
+        n->in = {x};
+        n->chain = {x->type, to};
+    }
+    n->type = to;
+    return n;
+}
+
+// merge.rs:288-325 `concat(axis, tensors)`
+NodeP make_concat(size_t axis, const std::vector<NodeP> &parts) {
+    auto n = std::make_shared<Node>();
+    n->kind = Node::CONCAT;
+    n->type = parts[0]->type;
+    n->shape = parts[0]->shape;
+    if (n->shape.size() == 1) axis = 0;
+    if (axis >= n->shape.size()) throw StepError{GGQ_ERR_INVALID, "concat: tensor has no axis " + std::to_string(axis)};
+    for (size_t k = 1; k < parts.size(); k++) {
+        const Node &t = *parts[k];
+        if (t.type != n->type) throw StepError{GGQ_ERR_INVALID, "concat: tensors of different types"};
+        if (t.shape.size() != n->shape.size()) throw StepError{GGQ_ERR_INVALID, "concat: tensors of different rank"};
+        for (size_t i = 0; i < n->shape.size(); i++) {
+            if (i == axis) n->shape[i] += t.shape[i];
+            else if (n->shape[i] != t.shape[i]) throw StepError{GGQ_ERR_INVALID, "concat: shapes differ off the concat axis"};
+        }
+    }
+    n->axis = axis;
+    n->in = parts;
+    return n;
+}
+
+// one part of merge.rs:327-357 `split(axis, tensor, parts)`
+NodeP make_split(const NodeP &x, size_t axis, uint64_t start, uint64_t len) {
+    std::vector<uint64_t> shape = x->shape;
+    shape[axis] = len;
+    if (x->kind == Node::SOURCE && axis_is_slowest(x->shape, axis)) {  // a byte range of the file
+        auto n = std::make_shared<Node>(*x);
+        std::vector<uint64_t> before = x->shape;
+        before[axis] = start;
+        n->file_off += nbytes_of(x->type, before);
+        n->shape = shape;
+        return n;
+    }
+    if (x->kind == Node::CAST) {  // split rows first, cast only what is kept
+        bool ok = axis > 0;
+        if (!ok) {
+            ok = true;
+            for (uint32_t t : x->chain) {
+                uint64_t be = 1, bb;
+                gguf::type_size(t, &be, &bb);
+                ok &= start % be == 0 && len % be == 0;
+            }
+        }
+        if (ok) {
+            auto n = std::make_shared<Node>(*x);
+            n->in = {make_split(x->in[0], axis, start, len)};
+            n->shape = shape;
+            return n;
+        }
+    }
+    if (x->kind == Node::CONCAT && x->axis == axis) {  // undoing a merge
+        uint64_t at = 0;
+        for (const NodeP &c : x->in) {
+            if (at == start && c->shape[axis] == len) return c;
+            at += c->shape[axis];
+        }
+    }
+    auto n = std::make_shared<Node>();
+    n->kind = Node::SPLIT;
+    n->type = x->type;
+    n->shape = shape;
+    n->in = {x};
+    n->axis = axis;
+    n->start = start;
+    return n;
+}
+std::vector<NodeP> split_parts(const NodeP &x, size_t axis, const std::vector<uint64_t> &parts) {
+    if (x->shape.size() == 1) axis = 0;
+    uint64_t sum = 0;
+    for (uint64_t p : parts) sum += p;
+    if (axis >= x->shape.size() || x->shape[axis] != sum) throw StepError{GGQ_ERR_INVALID, "split: parts do not add up to the axis"};  // merge.rs:333
+    uint64_t be = 1, bb;
+    gguf::type_size(x->type, &be, &bb);
+    std::vector<NodeP> out;
+    uint64_t at = 0;
+    for (uint64_t p : parts) {
+        if (axis == 0 && (at % be || p % be)) throw StepError{GGQ_ERR_INDIVISIBLE, "split: part is not a whole number of blocks"};
+        out.push_back(make_split(x, axis, at, p));
+        at += p;
+    }
+    return out;
+}
+
+// merge.rs:279-286 `distruct`
+void distruct(const Node &t, uint64_t *c, uint64_t *r) {
+    if (t.shape.size() == 1) { *c = 1; *r = t.shape[0]; }
+    else if (t.shape.size() == 2) { *c = t.shape[0]; *r = t.shape[1]; }
+    else throw StepError{GGQ_ERR_INVALID, "invalid tensor shape for a qkv operator (rank " + std::to_string(t.shape.size()) + ")"};
+}
+// merge.rs:239-250
+NodeP merge_qkv(const NodeP &q, const NodeP &k, const NodeP &v) {
+    uint64_t c, qr, kr, vr;
+    distruct(*q, &c, &qr); distruct(*k, &c, &kr); distruct(*v, &c, &vr);
+    if (kr == 0 || qr % kr != 0 || qr < kr || kr != vr) throw StepError{GGQ_ERR_INVALID, "merge-linear: q/k/v row counts do not fit"};
+    return make_concat(1, {q, k, v});
+}
+// merge.rs:267-272
+std::vector<NodeP> split_qkv(const NodeP &t, uint64_t nh, uint64_t nkvh) {
+    uint64_t c, r;
+    distruct(*t, &c, &r);
+    const uint64_t dh = r / (nh + nkvh * 2);
+    return split_parts(t, 1, {nh * dh, nkvh * dh, nkvh * dh});
+}
+// permute_qk.rs:46-69
+NodeP make_permute(const NodeP &x, uint64_t nh) {
+    uint64_t be = 1, bb;
+    gguf::type_size(x->type, &be, &bb);
+    uint64_t c, r;
+    if (x->shape.size() == 1) { c = 1; r = x->shape[0]; }
+    else if (x->shape.size() == 2) { c = x->shape[0]; r = x->shape[1]; }
+    else throw StepError{GGQ_ERR_UNSUPPORTED, "permute-qk of a tensor of rank > 2 (todo!() in the reference)"};
+    if (c % be) throw StepError{GGQ_ERR_INDIVISIBLE, "permute-qk: row is not a whole number of blocks"};  // tensor.rs:92
+    if (nh == 0 || r % (nh * 2)) throw StepError{GGQ_ERR_INVALID, "permute-qk: rows are not a multiple of 2 * heads"};
+    auto n = std::make_shared<Node>();
+    n->kind = Node::PERMUTE;
+    n->type = x->type;
+    n->shape = x->shape;
+    n->in = {x};
+    n->nh = nh;
+    return n;
+}
+
+bool has_kind(const Node &n, Node::Kind k) {
+    if (n.kind == k) return true;
+    for (const NodeP &c : n.in) if (has_kind(*c, k)) return true;
+    return false;
+}
+uint64_t cast_elems_of(const Node &n) {
+    uint64_t e = n.kind == Node::CAST ? count(n.shape) : 0;
+    for (const NodeP &c : n.in) e += cast_elems_of(*c);
+    return e;
+}
+
+struct Tensor {                 // one tensor of the content being built (utils/mod.rs:97-101)
+    std::string name;
+    NodeP node;
+    uint64_t out_nbytes = 0;
     int shard = 0;
     uint64_t out_off = 0;
 };
+
+// `NAME.(weight|bias)$` with NAME one of `alts` (the MERGE / SPLIT / QK regexes of merge.rs:8-10, permute_qk.rs:24-25)
+bool match_linear(const std::string &name, std::initializer_list<const char *> alts, std::string *pre, std::string *which, std::string *wb) {
+    std::string_view n(name), tail;
+    if (ends_with(n, ".weight")) tail = "weight";
+    else if (ends_with(n, ".bias")) tail = "bias";
+    else return false;
+    n.remove_suffix(tail.size() + 1);
+    for (const char *a : alts)
+        if (ends_with(n, a)) {
+            *pre = std::string(n.substr(0, n.size() - std::string_view(a).size()));
+            *which = a;
+            *wb = std::string(tail);
+            return true;
+        }
+    return false;
+}
 
 bool pread_all(int fd, void *buf, size_t n, uint64_t off) {
     char *p = static_cast<char *>(buf);
@@ -141,7 +371,7 @@ bool pwrite_all(int fd, const void *buf, size_t n, uint64_t off) {
 }
 
 // bytes of one tensor-info record (writer.rs:74-86)
-uint64_t info_bytes(const gguf::TensorInfo &t) { return 8 + t.name.size() + 4 + 8 * t.shape.size() + 4 + 8; }
+uint64_t info_bytes(const Tensor &t) { return 8 + t.name.size() + 4 + 8 * t.node->shape.size() + 4 + 8; }
 constexpr uint64_t ALIGNMENT_KV_BYTES = 8 + 17 + 4 + 4;  // "general.alignment": key string + type + u32
 
 // GGufFileSimulator / GGufTensorSimulator (ggus/src/write/simulator.rs:26-96)
@@ -149,13 +379,280 @@ struct Simulator {
     uint64_t alignment, written, n = 0;
     std::vector<uint64_t> data;
     Simulator(uint64_t align, uint64_t kv_bytes) : alignment(align), written(24 + ALIGNMENT_KV_BYTES + kv_bytes) {}
-    void write_tensor(const gguf::TensorInfo &t, uint64_t nbytes) { written += info_bytes(t); data.push_back(nbytes); }
+    void write_tensor(const Tensor &t) { written += info_bytes(t); data.push_back(t.out_nbytes); }
     uint64_t written_bytes() const {
         uint64_t total = written;
         for (uint64_t len : data) { total += gguf::pad(total, alignment); total += len; }
         return total;
     }
 };
+
+struct Step {
+    enum Kind { CAST, MERGE, SPLIT, PERMUTE } kind;
+    CastRule rule;
+};
+
+// GGufMetaMapExt::get_usize (ggus/src/metadata/collection.rs:40-72): any integer type, must fit usize
+bool get_usize(const std::vector<const gguf::MetaKV *> &kvs, const std::string &key, uint64_t *out, bool *exists) {
+    *exists = false;
+    for (const gguf::MetaKV *kv : kvs) {
+        if (kv->key != key) continue;
+        *exists = true;
+        int64_t sv = 0;
+        switch (kv->type) {
+            case gguf::U8: *out = kv->value[0]; return true;
+            case gguf::U16: { uint16_t v; memcpy(&v, kv->value, 2); *out = v; return true; }
+            case gguf::U32: { uint32_t v; memcpy(&v, kv->value, 4); *out = v; return true; }
+            case gguf::U64: { uint64_t v; memcpy(&v, kv->value, 8); *out = v; return true; }
+            case gguf::I8: sv = (int8_t)kv->value[0]; break;
+            case gguf::I16: { int16_t v; memcpy(&v, kv->value, 2); sv = v; break; }
+            case gguf::I32: { int32_t v; memcpy(&v, kv->value, 4); sv = v; break; }
+            case gguf::I64: { int64_t v; memcpy(&v, kv->value, 8); sv = v; break; }
+            default: return false;  // TypeMismatch
+        }
+        if (sv < 0) return false;  // OutOfRange
+        *out = (uint64_t)sv;
+        return true;
+    }
+    return false;
+}
+
+// `llm_attention_head_count` / `_kv` as merge.rs:41-46 and permute_qk.rs:13-18 read them
+void head_counts(const std::vector<const gguf::MetaKV *> &kvs, const std::string &arch, uint64_t *nh, uint64_t *nkvh) {
+    bool exists;
+    if (!get_usize(kvs, arch + ".attention.head_count", nh, &exists))
+        throw StepError{GGQ_ERR_INVALID, exists ? "bad type for " + arch + ".attention.head_count" : "NotExist: " + arch + ".attention.head_count"};
+    if (!get_usize(kvs, arch + ".attention.head_count_kv", nkvh, &exists)) {
+        if (exists) throw StepError{GGQ_ERR_INVALID, "bad type for " + arch + ".attention.head_count_kv"};
+        *nkvh = *nh;
+    }
+    if (*nh == 0 || *nkvh == 0) throw StepError{GGQ_ERR_INVALID, "attention head count is zero"};
+}
+
+// merge.rs:22-39 + the collectors of merge.rs:106-237.  Parts are gathered per name prefix and per
+// (layer kind, weight|bias); a group is emitted where its LAST part stood.  Incomplete groups are
+// appended unmerged at the end (the reference iterates a HashMap there, i.e. in arbitrary order; here:
+// first-seen order).
+void apply_merge(std::vector<Tensor> &tensors) {
+    struct Group { std::string pre, wb; int layer; NodeP part[3]; std::string name[3]; bool open = true; };
+    std::vector<Group> groups;
+    std::vector<Tensor> out;
+    for (Tensor &t : tensors) {
+        std::string pre, which, wb;
+        if (!match_linear(t.name, {"attn_q", "attn_k", "attn_v", "ffn_gate_exps", "ffn_up_exps", "ffn_gate", "ffn_up"}, &pre, &which, &wb)) {
+            out.push_back(std::move(t));
+            continue;
+        }
+        const int layer = which.rfind("attn_", 0) == 0 ? 0 : ends_with(which, "_exps") ? 2 : 1;
+        const int idx = which == "attn_q" || which == "ffn_gate" || which == "ffn_gate_exps" ? 0 : which == "attn_v" ? 2 : 1;
+        Group *g = nullptr;
+        for (Group &c : groups) if (c.open && c.pre == pre && c.wb == wb && c.layer == layer) g = &c;
+        if (!g) {
+            groups.push_back(Group{pre, wb, layer, {}, {}, true});
+            g = &groups.back();
+        }
+        g->part[idx] = t.node;
+        g->name[idx] = t.name;
+        const bool done = layer == 0 ? (g->part[0] && g->part[1] && g->part[2]) : (g->part[0] && g->part[1]);
+        if (!done) continue;
+        g->open = false;
+        Tensor m;
+        if (layer == 0) {
+            m.name = pre + "attn_qkv." + wb;
+            m.node = merge_qkv(g->part[0], g->part[1], g->part[2]);
+        } else {
+            if (layer == 1 && (g->part[0]->shape.size() < 2 || g->part[0]->shape[1] != g->part[1]->shape[1]))  // merge.rs:256
+                throw StepError{GGQ_ERR_INVALID, "merge-linear: ffn_gate and ffn_up differ in rows (" + g->name[0] + ")"};
+            m.name = pre + (layer == 1 ? "ffn_gate_up." : "ffn_gate_up_exps.") + wb;
+            m.node = make_concat(1, {g->part[0], g->part[1]});
+        }
+        out.push_back(std::move(m));
+    }
+    for (Group &g : groups)
+        if (g.open)
+            for (int i = 0; i < 3; i++)
+                if (g.part[i]) { Tensor t; t.name = g.name[i]; t.node = g.part[i]; out.push_back(std::move(t)); }
+    tensors = std::move(out);
+}
+
+// merge.rs:40-81.  SPLIT = (attn_qkv|ffn_gate_up).(weight|bias)$ — expert tensors are not matched.
+void apply_split(std::vector<Tensor> &tensors, uint64_t nh, uint64_t nkvh) {
+    std::vector<Tensor> out;
+    auto put = [&](const std::string &name, const NodeP &node) { Tensor t; t.name = name; t.node = node; out.push_back(std::move(t)); };
+    for (Tensor &t : tensors) {
+        std::string pre, which, wb;
+        if (!match_linear(t.name, {"attn_qkv", "ffn_gate_up"}, &pre, &which, &wb)) {
+            out.push_back(std::move(t));
+            continue;
+        }
+        if (which == "attn_qkv") {
+            auto p = split_qkv(t.node, nh, nkvh);
+            put(pre + "attn_q." + wb, p[0]);
+            put(pre + "attn_k." + wb, p[1]);
+            put(pre + "attn_v." + wb, p[2]);
+        } else {
+            if (t.node->shape.size() < 2) throw StepError{GGQ_ERR_INVALID, "split-linear: " + t.name + " has no second axis"};  // merge.rs:275
+            const uint64_t r = t.node->shape[1] / 2;
+            auto p = split_parts(t.node, 1, {r, r});
+            put(pre + "ffn_gate." + wb, p[0]);
+            put(pre + "ffn_up." + wb, p[1]);
+        }
+    }
+    tensors = std::move(out);
+}
+
+// permute_qk.rs:11-44
+void apply_permute(std::vector<Tensor> &tensors, uint64_t nh, uint64_t nkvh) {
+    for (Tensor &t : tensors) {
+        std::string pre, which, wb;
+        if (!match_linear(t.name, {"attn_qkv", "attn_q", "attn_k"}, &pre, &which, &wb)) continue;
+        if (which == "attn_q") t.node = make_permute(t.node, nh);
+        else if (which == "attn_k") t.node = make_permute(t.node, nkvh);
+        else {
+            auto p = split_qkv(t.node, nh, nkvh);
+            t.node = merge_qkv(make_permute(p[0], nh), make_permute(p[1], nkvh), p[2]);
+        }
+    }
+}
+
+// ---- producing a tensor's bytes ---------------------------------------------------------------------
+struct IoCtx {
+    const std::vector<int> *in_fds;
+    int out_fd;
+    std::vector<uint8_t> *copy_buf;
+    ggq::Resident *res;  // created on first use by the worker
+    std::function<ggq::Resident *()> resident;
+};
+
+// device-resident evaluation: the node's bytes end up, contiguous, at d_dst
+int eval_into(const Node &n, void *d_dst, IoCtx &io) {
+    ggq::Resident *res = io.resident();
+    if (!res) return GGQ_ERR_CUDA;
+    int rc = GGQ_OK;
+    auto with_child = [&](const Node &c, void **tmp) {
+        int r = res->alloc(nbytes_of(c), tmp);
+        return r != GGQ_OK ? r : eval_into(c, *tmp, io);
+    };
+    switch (n.kind) {
+        case Node::SOURCE: {
+            const int fd = (*io.in_fds)[n.file];
+            const uint64_t base = n.file_off;
+            return res->upload(d_dst, nbytes_of(n), [fd, base](void *pinned, size_t off, size_t len) { return pread_all(fd, pinned, len, base + off); });
+        }
+        case Node::CAST: {
+            void *tmp;
+            if ((rc = with_child(*n.in[0], &tmp)) != GGQ_OK) return rc;
+            rc = res->cast(n.chain.data(), (int)n.chain.size(), count(n.shape), d_dst, tmp);
+            res->free(tmp);
+            return rc;
+        }
+        case Node::CONCAT: {  // merge.rs:303-321
+            uint64_t unit;
+            const ndl::ArrayLayout whole = block_layout(n.type, n.shape, &unit);
+            uint64_t be = 1, bb;
+            gguf::type_size(n.type, &be, &bb);
+            std::vector<uint64_t> parts;
+            for (const NodeP &c : n.in) parts.push_back(n.axis == 0 ? c->shape[0] / be : c->shape[n.axis]);
+            const auto views = whole.split(n.axis, parts);
+            for (size_t k = 0; k < n.in.size(); k++) {
+                if (views[k].is_dense(unit)) {  // the part is one byte range of the result: produce it in place
+                    if ((rc = eval_into(*n.in[k], static_cast<char *>(d_dst) + views[k].offset, io)) != GGQ_OK) return rc;
+                    continue;
+                }
+                void *tmp;
+                if ((rc = with_child(*n.in[k], &tmp)) != GGQ_OK) return rc;
+                uint64_t u2;
+                rc = res->rearrange(d_dst, views[k].c(), tmp, block_layout(n.in[k]->type, n.in[k]->shape, &u2).c(), unit);
+                res->free(tmp);
+                if (rc != GGQ_OK) return rc;
+            }
+            return GGQ_OK;
+        }
+        case Node::SPLIT: {  // merge.rs:335-356
+            const Node &c = *n.in[0];
+            uint64_t unit, be = 1, bb;
+            gguf::type_size(n.type, &be, &bb);
+            ndl::ArrayLayout src = block_layout(c.type, c.shape, &unit);
+            const uint64_t start = n.axis == 0 ? n.start / be : n.start, len = n.axis == 0 ? n.shape[0] / be : n.shape[n.axis];
+            src.offset += (int64_t)start * src.strides[n.axis];
+            src.shape[n.axis] = len;
+            void *tmp;
+            if ((rc = with_child(c, &tmp)) != GGQ_OK) return rc;
+            rc = res->rearrange(d_dst, block_layout(n.type, n.shape, &unit).c(), tmp, src.c(), unit);
+            res->free(tmp);
+            return rc;
+        }
+        case Node::PERMUTE: {  // permute_qk.rs:46-60: rows (bytes) tiled [r/nh/2, 2, nh], the two inner tiles swapped
+            const uint64_t c = n.shape.size() == 1 ? nbytes_of(n.type, {1}) : nbytes_of(n.type, {n.shape[0]});
+            const uint64_t r = n.shape.size() == 1 ? n.shape[0] : n.shape[1];
+            const ndl::ArrayLayout src = ndl::ArrayLayout::new_contiguous({c, r}, 1).tile_le(1, {r / n.nh / 2, 2, n.nh}).transpose({2, 1});
+            const ndl::ArrayLayout dst = ndl::ArrayLayout::new_contiguous(src.shape, 1);
+            void *tmp;
+            if ((rc = with_child(*n.in[0], &tmp)) != GGQ_OK) return rc;
+            rc = res->rearrange(d_dst, dst.c(), tmp, src.c(), 1);
+            res->free(tmp);
+            return rc;
+        }
+    }
+    return GGQ_ERR_INVALID;
+}
+
+// write the node's bytes at out_off of the output file
+int emit(const Node &n, uint64_t out_off, IoCtx &io) {
+    const uint64_t nbytes = nbytes_of(n);
+    const int ofd = io.out_fd;
+    if (nbytes == 0) return GGQ_OK;
+    if (n.kind == Node::SOURCE) {  // untouched bytes: file to file
+        const int ifd = (*io.in_fds)[n.file];
+        constexpr size_t CH = size_t(8) << 20;
+        io.copy_buf->resize(std::min<uint64_t>(CH, nbytes));
+        for (uint64_t off = 0; off < nbytes; off += CH) {
+            const size_t len = (size_t)std::min<uint64_t>(CH, nbytes - off);
+            if (!pread_all(ifd, io.copy_buf->data(), len, n.file_off + off) || !pwrite_all(ofd, io.copy_buf->data(), len, out_off + off)) {
+                t_cerr = "I/O error while copying tensor bytes";
+                return GGQ_ERR_INVALID;
+            }
+        }
+        return GGQ_OK;
+    }
+    if (n.kind == Node::CAST && n.in[0]->kind == Node::SOURCE) {  // the streaming pipeline
+        const Node &src = *n.in[0];
+        const int ifd = (*io.in_fds)[src.file];
+        const uint64_t src_off = src.file_off;
+        ggq::ChainIO cio;
+        cio.read = [&](void *pinned, size_t off, size_t len) { return pread_all(ifd, pinned, len, src_off + off); };
+        cio.write = [&](const void *pinned, size_t off, size_t len) { return pwrite_all(ofd, pinned, len, out_off + off); };
+        const int rc = ggq::cast_chain_io(n.chain.data(), (int)n.chain.size(), count(n.shape), cio);
+        if (rc != GGQ_OK) t_cerr = ggq_last_error();
+        return rc;
+    }
+    if (n.kind == Node::CONCAT && axis_is_slowest(n.shape, n.axis)) {  // parts are consecutive byte ranges
+        uint64_t at = out_off;
+        for (const NodeP &c : n.in) {
+            const int rc = emit(*c, at, io);
+            if (rc != GGQ_OK) return rc;
+            at += nbytes_of(*c);
+        }
+        return GGQ_OK;
+    }
+    ggq::Resident *res = io.resident();
+    if (!res) return GGQ_ERR_CUDA;
+    void *d = nullptr;
+    int rc = res->alloc(nbytes, &d);
+    if (rc == GGQ_OK) rc = eval_into(n, d, io);
+    if (rc == GGQ_OK) rc = res->download(d, nbytes, [ofd, out_off](const void *pinned, size_t off, size_t len) { return pwrite_all(ofd, pinned, len, out_off + off); });
+    if (d) res->free(d);
+    if (rc != GGQ_OK && t_cerr.empty()) t_cerr = ggq_last_error();
+    return rc;
+}
+bool needs_gpu(const Node &n) {
+    if (n.kind == Node::SOURCE) return false;
+    if (n.kind == Node::CONCAT && axis_is_slowest(n.shape, n.axis)) {
+        for (const NodeP &c : n.in) if (needs_gpu(*c)) return true;
+        return false;
+    }
+    return true;
+}
 
 }  // namespace
 
@@ -174,7 +671,7 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
         const uint64_t max_bytes = o.max_bytes ? o.max_bytes : UINT64_MAX;
         if (!in_paths || n_in == 0 || !out_path) return failc(GGQ_ERR_INVALID, "no input or output path");
         // ---- parse `--steps "a -> b -> c"` (convert.rs:38-51) ----
-        std::vector<CastRule> rules;
+        std::vector<Step> ops;
         {
             std::string s(steps ? steps : "");
             size_t pos = 0;
@@ -184,11 +681,17 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
                 size_t a = step.find_first_not_of(" \t"), b = step.find_last_not_of(" \t");
                 step = a == step.npos ? "" : step.substr(a, b - a + 1);
                 if (!step.empty()) {
-                    if (step.rfind("cast:", 0) != 0) return failc(GGQ_ERR_UNSUPPORTED, "only `cast:` steps are implemented (got '" + step + "')");
-                    CastRule r;
-                    std::string err;
-                    if (!parse_cast_step(step.substr(5), &r, &err)) return failc(GGQ_ERR_UNSUPPORTED, err);
-                    rules.push_back(r);
+                    Step st{};
+                    if (step == "merge-linear") st.kind = Step::MERGE;
+                    else if (step == "split-linear" || step == "!merge-linear") st.kind = Step::SPLIT;
+                    else if (step == "permute-qk") st.kind = Step::PERMUTE;
+                    else if (step.rfind("cast:", 0) == 0) {
+                        st.kind = Step::CAST;
+                        std::string err;
+                        if (!parse_cast_step(step.substr(5), &st.rule, &err)) return failc(GGQ_ERR_UNSUPPORTED, err);
+                    } else
+                        return failc(GGQ_ERR_UNSUPPORTED, "only `cast:`, `merge-linear`, `split-linear` and `permute-qk` steps are implemented (got '" + step + "')");
+                    ops.push_back(st);
                 }
                 if (nx == s.npos) break;
                 pos = nx + 2;
@@ -220,34 +723,49 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
             }
             for (const auto &t : in->f.tensors) {
                 if (!name_seen.insert(t.name).second) return failc(GGQ_ERR_INVALID, "DuplicateTensorName(" + std::string(t.name) + ")");
-                tensors.push_back(Tensor{&t, (int)i, {}, 0});
+                auto node = std::make_shared<Node>();
+                node->type = t.type;
+                node->shape = t.shape;
+                node->file = (int)i;
+                node->file_off = in->data_off + t.offset;
+                Tensor vt;
+                vt.name = std::string(t.name);
+                vt.node = node;
+                tensors.push_back(std::move(vt));
             }
             files.push_back(std::move(in));
         }
         std::string arch;
         for (const auto &f : files) if (arch.empty()) arch = std::string(f->f.get_str("general.architecture"));
-        if (!rules.empty() && arch != "llama" && arch != "gpt2" && arch != "qwen2" && arch != "clip")
-            return failc(GGQ_ERR_UNSUPPORTED, "Unsupported architecture: " + arch);  // cast.rs:69
 
-        // ---- per-tensor type chains (cast.rs:73-90, applied once per step) and output sizes ----
-        const size_t nt = tensors.size();
-        for (auto &t : tensors) {
-            const auto &ti = *t.info;
-            t.chain.push_back(ti.type);
-            const int cls = classify(arch, ti.name, ti.shape.size());
-            for (const CastRule &r : rules)
-                if (r.has[cls] && r.ty[cls] != t.chain.back()) t.chain.push_back(r.ty[cls]);
-            t.out_nbytes = ti.nbytes;
-            if (t.chain.size() > 1) {
-                uint64_t be, bb;
-                if (!gguf::type_size(t.chain.back(), &be, &bb)) return failc(GGQ_ERR_UNSUPPORTED, "unsupported target type");
-                if (ti.shape.empty() || ti.shape[0] % be)  // cast.rs:142-143 `assert_eq!(row % N, 0)`
-                    return failc(GGQ_ERR_INDIVISIBLE, "row of " + std::string(ti.name) + " is not a multiple of the target block size");
-                t.out_nbytes = ti.n_elems() / be * bb;
-                for (uint32_t c : t.chain)
-                    if (ggq_type_nbytes(c, ti.n_elems()) == 0) return failc(GGQ_ERR_UNSUPPORTED, "cast chain of " + std::string(ti.name) + " has an unsupported type");
+        // ---- apply the operators in order (utils/mod.rs:48-53): they only rewrite the expressions ----
+        try {
+            for (const Step &op : ops) {
+                switch (op.kind) {
+                    case Step::CAST:
+                        if (arch != "llama" && arch != "gpt2" && arch != "qwen2" && arch != "clip")
+                            throw StepError{GGQ_ERR_UNSUPPORTED, "Unsupported architecture: " + arch};  // cast.rs:69
+                        for (Tensor &t : tensors) {  // cast.rs:73-90
+                            const int cls = classify(arch, t.name, t.node->shape.size());
+                            if (op.rule.has[cls]) t.node = make_cast(t.node, op.rule.ty[cls], t.name);
+                        }
+                        break;
+                    case Step::MERGE: apply_merge(tensors); break;
+                    case Step::SPLIT:
+                    case Step::PERMUTE: {
+                        uint64_t nh, nkvh;
+                        head_counts(kvs, arch, &nh, &nkvh);
+                        if (op.kind == Step::SPLIT) apply_split(tensors, nh, nkvh);
+                        else apply_permute(tensors, nh, nkvh);
+                        break;
+                    }
+                }
             }
+        } catch (const StepError &e) {
+            return failc(e.code, e.msg);
         }
+        const size_t nt = tensors.size();
+        for (Tensor &t : tensors) t.out_nbytes = nbytes_of(*t.node);
         // ---- plan the output shards (write.rs:23-51, with the simulator's byte accounting) ----
         uint64_t kv_bytes = 0;
         for (const auto *kv : kvs) kv_bytes += kv->raw_len;
@@ -257,16 +775,16 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
             for (size_t i = 0; i < nt; i++) {
                 if (shards.size() == 1 && o.no_tensor_first) {
                     sim = Simulator(alignment, 0);
-                    sim.write_tensor(*tensors[i].info, tensors[i].out_nbytes);
+                    sim.write_tensor(tensors[i]);
                     shards.push_back({i});
                     continue;
                 }
-                sim.write_tensor(*tensors[i].info, tensors[i].out_nbytes);
+                sim.write_tensor(tensors[i]);
                 if (shards.back().size() < max_tensors && sim.written_bytes() < max_bytes) {
                     shards.back().push_back(i);
                 } else {
                     sim = Simulator(alignment, 0);
-                    sim.write_tensor(*tensors[i].info, tensors[i].out_nbytes);
+                    sim.write_tensor(tensors[i]);
                     shards.push_back({i});
                 }
             }
@@ -282,7 +800,7 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
             if (shards.size() > 1) snprintf(suffix, sizeof suffix, "-%05zu-of-%05zu", si + 1, shards.size());
             const std::string path = base + suffix + ".gguf";
             std::vector<gguf::OutTensor> ot;
-            for (size_t i : shards[si]) ot.push_back({tensors[i].info->name, &tensors[i].info->shape, tensors[i].chain.back(), tensors[i].out_nbytes, 0});
+            for (size_t i : shards[si]) ot.push_back({tensors[i].name, &tensors[i].node->shape, tensors[i].node->type, tensors[i].out_nbytes, 0});
             const std::vector<const gguf::MetaKV *> none;
             const auto &shard_kvs = si == 0 ? kvs : none;           // write.rs:72, 77-81
             gguf::Sink sim;
@@ -314,16 +832,16 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
         if (const char *wenv = getenv("GGQ_CONVERT_WORKERS")) { const int v = atoi(wenv); if (v >= 1 && v <= 32) WORKERS_PER_DEVICE = v; }
         std::vector<size_t> order(nt);
         for (size_t i = 0; i < nt; i++) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tensors[a].info->nbytes > tensors[b].info->nbytes; });
+        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tensors[a].out_nbytes > tensors[b].out_nbytes; });
         std::atomic<size_t> next{0};
         std::atomic<int> rc_all{GGQ_OK};
-        std::atomic<uint64_t> cast_elems{0}, cast_tensors{0};
+        std::atomic<uint64_t> cast_elems{0}, cast_tensors{0}, rearranged{0};
         std::string first_err;
         std::mutex err_mu;
         const int ndev_avail = ggq_device_count();
         int ndev = o.n_devices <= 0 ? ndev_avail : std::min(o.n_devices, ndev_avail);
         bool need_gpu = false;
-        for (const auto &t : tensors) need_gpu |= t.chain.size() > 1;
+        for (const auto &t : tensors) need_gpu |= needs_gpu(*t.node);
         if (o.no_data) need_gpu = false;
         if (need_gpu && ndev < 1) return failc(GGQ_ERR_CUDA, "no CUDA device (libggq has no CPU fallback)");
         if (ndev < 1) ndev = 1;
@@ -332,35 +850,31 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
             int ok = GGQ_OK;
             if (rc_all.compare_exchange_strong(ok, rc)) first_err = m;
         };
+        std::vector<int> in_fds;
+        for (const auto &f : files) in_fds.push_back(f->fd);
         auto worker = [&](int dev) {
             if (need_gpu && ggq_set_device(dev) != GGQ_OK) { set_err(GGQ_ERR_CUDA, ggq_last_error()); return; }
             std::vector<uint8_t> copy_buf;
+            std::unique_ptr<ggq::Resident> res;
+            IoCtx io{&in_fds, -1, &copy_buf, nullptr, nullptr};
+            io.resident = [&]() -> ggq::Resident * {
+                if (!res) {
+                    res = std::make_unique<ggq::Resident>();
+                    if (res->status() != GGQ_OK) { t_cerr = ggq_last_error(); res.reset(); }
+                }
+                return res.get();
+            };
             for (;;) {
                 const size_t k = next.fetch_add(1);
                 if (k >= nt || rc_all.load() != GGQ_OK) return;
                 const Tensor &t = tensors[order[k]];
-                const auto &ti = *t.info;
-                const int ifd = files[t.file]->fd, ofd = outs[t.shard]->fd;
-                const uint64_t src_off = files[t.file]->data_off + ti.offset, dst_off = t.out_off;
-                if (t.chain.size() == 1) {  // untouched tensor: byte copy
-                    constexpr size_t CH = size_t(8) << 20;
-                    copy_buf.resize(std::min<uint64_t>(CH, ti.nbytes));
-                    for (uint64_t off = 0; off < ti.nbytes; off += CH) {
-                        const size_t n = (size_t)std::min<uint64_t>(CH, ti.nbytes - off);
-                        if (!pread_all(ifd, copy_buf.data(), n, src_off + off) || !pwrite_all(ofd, copy_buf.data(), n, dst_off + off)) {
-                            set_err(GGQ_ERR_INVALID, "I/O error copying " + std::string(ti.name));
-                            return;
-                        }
-                    }
-                    continue;
-                }
-                ggq::ChainIO io;
-                io.read = [&](void *pinned, size_t off, size_t n) { return pread_all(ifd, pinned, n, src_off + off); };
-                io.write = [&](const void *pinned, size_t off, size_t n) { return pwrite_all(ofd, pinned, n, dst_off + off); };
-                const int rc = ggq::cast_chain_io(t.chain.data(), (int)t.chain.size(), ti.n_elems(), io);
-                if (rc != GGQ_OK) { set_err(rc, std::string(ti.name) + ": " + ggq_last_error()); return; }
-                cast_elems += ti.n_elems();
-                cast_tensors += 1;
+                io.out_fd = outs[t.shard]->fd;
+                t_cerr.clear();
+                const int rc = emit(*t.node, t.out_off, io);
+                if (rc != GGQ_OK) { set_err(rc, t.name + ": " + t_cerr); return; }
+                const uint64_t ce = cast_elems_of(*t.node);
+                if (ce) { cast_elems += ce; cast_tensors += 1; }
+                if (has_kind(*t.node, Node::PERMUTE) || has_kind(*t.node, Node::CONCAT) || has_kind(*t.node, Node::SPLIT)) rearranged += 1;
             }
         };
         if (!o.no_data) {
@@ -383,6 +897,7 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
             stats->seconds_sync = 0.0;  // like the reference writer, no fsync: the page cache owns the rest
             stats->n_devices = ndev;
             stats->n_out_files = (int)outs.size();
+            stats->n_rearranged_tensors = rearranged.load();
         }
         return GGQ_OK;
     } catch (const std::exception &e) {

@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <functional>
 
+#include "../../include/ggq.h"
+
 namespace ggq {
 
 // Where a cast chain's bytes come from and go to.  Offsets are byte offsets inside the tensor.
@@ -17,5 +19,31 @@ struct ChainIO {
 // cast.rs:93-138 over a chain of types, streaming through the H2D -> kernels -> D2H pipeline of the
 // calling thread's device.  Returns a ggq_status; ggq_last_error() has the message.
 int cast_chain_io(const uint32_t *types, int n_types, size_t n_elems, const ChainIO &io);
+
+// Device-resident evaluation for tensors whose bytes are not a plain stream (rearranged rows): one
+// worker thread's context on its GPU — a stream, stream-ordered allocations, and the pinned bounce
+// buffers of a pooled pipeline for chunked upload / download.  Everything is enqueued on one stream
+// in call order; download() returns after the last byte has been handed to `write`.
+using ReadFn = std::function<bool(void *pinned, size_t byte_off, size_t nbytes)>;
+using WriteFn = std::function<bool(const void *pinned, size_t byte_off, size_t nbytes)>;
+class Resident {
+   public:
+    Resident();   // binds to the calling thread's device (ggq_set_device); check status()
+    ~Resident();  // synchronises the stream and frees what alloc() handed out
+    Resident(const Resident &) = delete;
+    Resident &operator=(const Resident &) = delete;
+    int status() const { return status_; }
+    int alloc(size_t nbytes, void **d);
+    void free(void *d);
+    int upload(void *d_dst, size_t nbytes, const ReadFn &read);
+    int download(const void *d_src, size_t nbytes, const WriteFn &write);
+    int cast(const uint32_t *types, int n_types, size_t n_elems, void *d_dst, const void *d_src);
+    int rearrange(void *d_dst, const ggq_layout &dl, const void *d_src, const ggq_layout &sl, size_t unit);
+
+   private:
+    struct Impl;
+    Impl *impl_ = nullptr;
+    int status_ = 0;
+};
 
 }  // namespace ggq

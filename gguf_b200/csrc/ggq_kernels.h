@@ -24,6 +24,16 @@ cudaError_t quant_blocks_k(uint32_t type, uint32_t fdt, const void *src, void *d
 // element casts between f32 / f16 / bf16 (the 1-element "blocks" of structs/half.rs).
 cudaError_t cast_elems(uint32_t src_dt, uint32_t dst_dt, const void *src, void *dst, size_t n, cudaStream_t stream, DevInfo dev);
 
+// Strided byte-run copy (rearrange.cu): byte strides / offset, at most 4 dims, same shape on both sides.
+struct StridedLayout {
+    int ndim;
+    uint64_t shape[4];
+    int64_t strides[4];
+    int64_t offset;
+};
+cudaError_t rearrange_strided(void *dst_base, const StridedLayout &dst, const void *src_base, const StridedLayout &src, size_t unit,
+                              cudaStream_t stream, uint64_t *launches);
+
 // occupancy cache helper: resident CTAs per SM for `kern`, after raising its dynamic smem limit.
 template <class K>
 static inline cudaError_t cached_occupancy(K kern, int threads, int smem, int device, std::atomic<int> *cache, int *out) {
@@ -44,9 +54,9 @@ static inline cudaError_t cached_occupancy(K kern, int threads, int smem, int de
 
 // Launch with the programmatic-stream-serialization attribute (PDL); kernels call pdl_wait() first.
 template <class... KArgs, class... Args>
-static inline cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args) {
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = grid;
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;

@@ -23,6 +23,7 @@
 #include <string>
 
 #include "../../include/ggq.h"
+#include "array_layout.hpp"
 
 namespace ggml_quants {
 
@@ -126,7 +127,14 @@ inline Result cast(std::initializer_list<uint32_t> types, void *dst, const void 
 // `GGmlType::size().elements_to_bytes` for a flat element count (ggus/src/tensor.rs:83-96)
 inline size_t type_nbytes(uint32_t type, size_t n_elems) { return ggq_type_nbytes(type, n_elems); }
 
-// `xtask convert FILE -x STEPS` for `cast:` steps (xtask/src/convert.rs:24-58); throws on failure.
+// `Rearranging::new(&dst, &src, unit)?.launch(dst_ptr, src_ptr)` (crate mem-rearrange; call sites
+// xtask/src/utils/operator/merge.rs:311-313, 344-350 and permute_qk.rs:61-66) on host memory, run on the GPU.
+inline Result rearrange(void *dst, const ndl::ArrayLayout &dst_layout, const void *src, const ndl::ArrayLayout &src_layout, size_t unit) {
+    const ggq_layout d = dst_layout.c(), s = src_layout.c();
+    return Result(ggq_rearrange(dst, &d, src, &s, unit));
+}
+
+// `xtask convert FILE -x STEPS` for `cast:`, `merge-linear`, `split-linear`, `permute-qk` steps (xtask/src/convert.rs:24-58); throws on failure.
 inline ggq_convert_stats convert(const std::string &file, const std::string &out, const std::string &steps, int n_devices = 0) {
     ggq_convert_stats st{};
     const int rc = ggq_convert_gguf(file.c_str(), out.c_str(), steps.c_str(), n_devices, &st);

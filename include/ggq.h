@@ -131,6 +131,38 @@ int ggq_cast(const uint32_t *types, int n_types, void *dst, const void *src, siz
  * 0 when the type is unknown or `n_elems` is not a whole number of blocks. */
 size_t ggq_type_nbytes(uint32_t type, size_t n_elems);
 
+/* ---- block-granular rearrangement (the tensor operators around the casts) ------------------------ */
+
+/* `ArrayLayout<4>` of the crate ndarray-layout 0.2.1 as the reference builds it
+ * (xtask/src/utils/operator/merge.rs:359-364 `layout(ty, shape)`: shape[0] counted in blocks, element
+ * = one block of `type_size` bytes; operator/permute_qk.rs:57-60: byte-granular rows tiled by head).
+ * Shape in elements of `unit` bytes, strides and offset in BYTES (may be negative). */
+#define GGQ_MAX_NDIM 4
+struct ggq_layout {
+    uint32_t ndim;                  /* <= GGQ_MAX_NDIM */
+    uint64_t shape[GGQ_MAX_NDIM];
+    int64_t strides[GGQ_MAX_NDIM];
+    int64_t offset;
+};
+
+/* `Rearranging::new(&dst_layout, &src_layout, unit)?.launch(dst, src)` of the crate mem-rearrange 0.1.0
+ * — the data movement of `concat` / `split` (merge.rs:288-357: merge-linear / split-linear of attn_qkv,
+ * ffn_gate_up, ffn_gate_up_exps) and of `permute_qk` (permute_qk.rs:46-69): for every index of the
+ * common shape, `unit` bytes go from src + src.offset + sum(i_k * src.strides[k]) to the same
+ * expression over dst.  Bytes of `dst` the layout does not address are left untouched.  Device
+ * pointers, enqueued on `stream` without synchronising.  The ranges addressed through `dst` and `src`
+ * must not overlap.  Returns GGQ_ERR_LENGTH_MISMATCH when ndim or shape differ (the crate's
+ * `SchemeError::ShapeMismatch`), GGQ_ERR_INVALID for ndim > GGQ_MAX_NDIM, unit == 0 or a zero dst
+ * stride on a dim of extent > 1. */
+int ggq_rearrange_device(void *dst, const struct ggq_layout *dst_layout, const void *src,
+                         const struct ggq_layout *src_layout, size_t unit, void *stream);
+
+/* The same on host memory, synchronous: the byte span `src_layout` addresses is copied to the GPU,
+ * rearranged there and the span `dst_layout` addresses is copied back (a span the layout covers
+ * only partly is uploaded first, so bytes between the addressed runs keep their values). */
+int ggq_rearrange(void *dst, const struct ggq_layout *dst_layout, const void *src,
+                  const struct ggq_layout *src_layout, size_t unit);
+
 /* ---- whole-file conversion --------------------------------------------------------------------- */
 
 struct ggq_convert_stats {
@@ -138,6 +170,7 @@ struct ggq_convert_stats {
     double seconds_plan, seconds_convert, seconds_sync;
     int n_devices;
     int n_out_files;
+    uint64_t n_rearranged_tensors; /* tensors produced by merge-linear / split-linear / permute-qk */
 };
 
 /* `OutputArgs` of xtask (xtask/src/utils/output.rs:8-53); zero means "unlimited" / "off". */
@@ -151,7 +184,9 @@ struct ggq_convert_options {
 
 /* `xtask convert FILE --steps "cast:linear:q8_0 embd:q8_0 -> cast:linear:f32 ..."` —
  * xtask/src/convert.rs:24-58 → utils/mod.rs:36-59 → operator/cast.rs:28-90 → utils/write.rs:6-100,
- * for `cast:` steps (the only operator that computes on tensor values) and a single output shard.
+ * for the steps that touch tensor bytes: `cast:<rules>` (operator/cast.rs), `merge-linear`,
+ * `split-linear` | `!merge-linear` (operator/merge.rs:22-83) and `permute-qk` (operator/permute_qk.rs:11-44);
+ * any other step returns GGQ_ERR_UNSUPPORTED.
  * Tensor-name → target-type rules are cast.rs:28-71 (architectures llama | gpt2 | qwen2 | clip); all
  * steps of a tensor run as one device-resident chain; tensors are spread over `n_devices` GPUs
  * (<= 0: all visible) with no inter-GPU traffic.  The output file is byte-identical to what the
