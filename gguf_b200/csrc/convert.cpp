@@ -315,11 +315,6 @@ NodeP make_permute(const NodeP &x, uint64_t nh) {
     return n;
 }
 
-bool has_kind(const Node &n, Node::Kind k) {
-    if (n.kind == k) return true;
-    for (const NodeP &c : n.in) if (has_kind(*c, k)) return true;
-    return false;
-}
 uint64_t cast_elems_of(const Node &n) {
     uint64_t e = n.kind == Node::CAST ? count(n.shape) : 0;
     for (const NodeP &c : n.in) e += cast_elems_of(*c);
@@ -522,6 +517,7 @@ struct IoCtx {
     std::vector<uint8_t> *copy_buf;
     ggq::Resident *res;  // created on first use by the worker
     std::function<ggq::Resident *()> resident;
+    bool used_resident = false;  // set by emit(): the tensor went through the device-resident path
 };
 
 // device-resident evaluation: the node's bytes end up, contiguous, at d_dst
@@ -637,6 +633,7 @@ int emit(const Node &n, uint64_t out_off, IoCtx &io) {
     }
     ggq::Resident *res = io.resident();
     if (!res) return GGQ_ERR_CUDA;
+    io.used_resident = true;
     void *d = nullptr;
     int rc = res->alloc(nbytes, &d);
     if (rc == GGQ_OK) rc = eval_into(n, d, io);
@@ -856,7 +853,7 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
             if (need_gpu && ggq_set_device(dev) != GGQ_OK) { set_err(GGQ_ERR_CUDA, ggq_last_error()); return; }
             std::vector<uint8_t> copy_buf;
             std::unique_ptr<ggq::Resident> res;
-            IoCtx io{&in_fds, -1, &copy_buf, nullptr, nullptr};
+            IoCtx io{&in_fds, -1, &copy_buf, nullptr, nullptr, false};
             io.resident = [&]() -> ggq::Resident * {
                 if (!res) {
                     res = std::make_unique<ggq::Resident>();
@@ -870,16 +867,17 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
                 const Tensor &t = tensors[order[k]];
                 io.out_fd = outs[t.shard]->fd;
                 t_cerr.clear();
+                io.used_resident = false;
                 const int rc = emit(*t.node, t.out_off, io);
                 if (rc != GGQ_OK) { set_err(rc, t.name + ": " + t_cerr); return; }
                 const uint64_t ce = cast_elems_of(*t.node);
                 if (ce) { cast_elems += ce; cast_tensors += 1; }
-                if (has_kind(*t.node, Node::PERMUTE) || has_kind(*t.node, Node::CONCAT) || has_kind(*t.node, Node::SPLIT)) rearranged += 1;
+                if (io.used_resident) rearranged += 1;
             }
         };
         if (!o.no_data) {
             std::vector<std::thread> th;
-            const int nworkers = ndev * (need_gpu ? WORKERS_PER_DEVICE : 1);
+            const int nworkers = ndev * WORKERS_PER_DEVICE;  // plain copies are file I/O: they want the threads too
             for (int w = 1; w < nworkers; w++) th.emplace_back(worker, w % ndev);
             worker(0);
             for (auto &x : th) x.join();

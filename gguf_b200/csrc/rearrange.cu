@@ -9,8 +9,8 @@
 // Design: HBM-bound byte work, no arithmetic.  The host normalises the two layouts (drops extent-1
 // dims, orders dims by destination stride, merges dims that are contiguous in BOTH layouts, folds
 // the unit-stride dim into a contiguous "run") and launches one grid of 16-byte vector copies:
-//   grid.y  enumerates the two outer dims,   grid.x × threads enumerate (innermost outer dim, vector)
-// so a thread pays one 32-bit division per 16 bytes and every warp writes consecutive vectors of a
+//   grid.x × threads enumerate (two innermost outer dims, vector),   grid.y / .z the next two dims
+// so a thread pays two 32-bit divisions per 16 bytes and every warp writes consecutive vectors of a
 // run.  Each thread keeps UNROLL independent loads in flight before its first store.  Vector width
 // falls back to 8/4/2/1 bytes when a pointer, stride or run length is not 16-byte aligned (block
 // rows are only 2-byte aligned in general: a Q4_0 row of 32·k elements is 18·k bytes).
@@ -24,10 +24,9 @@
 namespace ggq {
 
 struct RearrangeParams {
-    uint32_t n0;    // extent of the innermost outer dim (decomposed per thread)
-    uint32_t n1;    // blockIdx.y = i1 + n1 * i2
-    uint32_t vecs;  // W-byte vectors per run
-    int64_t ds0, ds1, ds2, ss0, ss1, ss2;  // byte strides of the three outer dims
+    uint32_t n0, n1;  // extents of the two innermost outer dims (decomposed per thread)
+    uint32_t vecs;    // W-byte vectors per run
+    int64_t ds[4], ss[4];  // byte strides of the four outer dims; dims 2 and 3 are blockIdx.y / .z
 };
 
 template <int W> struct RVec;
@@ -42,10 +41,9 @@ constexpr int RE_THREADS = 256;
 template <int W, int UNROLL>
 __global__ void __launch_bounds__(RE_THREADS) rearrange_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, RearrangeParams p) {
     using V = typename RVec<W>::type;
-    const uint32_t i2 = blockIdx.y / p.n1, i1 = blockIdx.y - i2 * p.n1;
-    dst += (int64_t)i1 * p.ds1 + (int64_t)i2 * p.ds2;
-    src += (int64_t)i1 * p.ss1 + (int64_t)i2 * p.ss2;
-    const uint64_t total = (uint64_t)p.n0 * p.vecs;  // < 2^32 (host splits larger extents)
+    dst += (int64_t)blockIdx.y * p.ds[2] + (int64_t)blockIdx.z * p.ds[3];
+    src += (int64_t)blockIdx.y * p.ss[2] + (int64_t)blockIdx.z * p.ss[3];
+    const uint64_t total = (uint64_t)p.n0 * p.n1 * p.vecs;  // < 2^32 (host splits larger extents)
     const uint64_t base = (uint64_t)blockIdx.x * (RE_THREADS * UNROLL) + threadIdx.x;
     pdl_launch_dependents();
     pdl_wait();
@@ -55,9 +53,10 @@ __global__ void __launch_bounds__(RE_THREADS) rearrange_kernel(uint8_t *__restri
     for (int u = 0; u < UNROLL; u++) {
         const uint64_t idx = base + (uint64_t)u * RE_THREADS;
         if (idx < total) {
-            const uint32_t i0 = (uint32_t)idx / p.vecs, k = (uint32_t)idx - i0 * p.vecs;
-            v[u] = __ldg(reinterpret_cast<const V *>(src + (int64_t)i0 * p.ss0 + (int64_t)k * W));
-            doff[u] = (int64_t)i0 * p.ds0 + (int64_t)k * W;
+            const uint32_t r = (uint32_t)idx / p.vecs, k = (uint32_t)idx - r * p.vecs;
+            const uint32_t i1 = r / p.n0, i0 = r - i1 * p.n0;
+            v[u] = __ldg(reinterpret_cast<const V *>(src + (int64_t)i0 * p.ss[0] + (int64_t)i1 * p.ss[1] + (int64_t)k * W));
+            doff[u] = (int64_t)i0 * p.ds[0] + (int64_t)i1 * p.ds[1] + (int64_t)k * W;
         }
     }
 #pragma unroll
@@ -70,70 +69,55 @@ namespace {
 struct Dim { uint64_t n; int64_t ds, ss; };
 
 template <int W>
-cudaError_t launch_w(uint8_t *dst, const uint8_t *src, const RearrangeParams &p, uint32_t n2, cudaStream_t stream) {
-    const uint64_t total = (uint64_t)p.n0 * p.vecs;
-    const unsigned gy = p.n1 * n2;
-    if (total >= (uint64_t)RE_THREADS * 4) {
-        dim3 grid((unsigned)((total + RE_THREADS * 4 - 1) / (RE_THREADS * 4)), gy);
+cudaError_t launch_w(uint8_t *dst, const uint8_t *src, const RearrangeParams &p, unsigned gy, unsigned gz, cudaStream_t stream) {
+    const uint64_t total = (uint64_t)p.n0 * p.n1 * p.vecs;
+    // four loads in flight per thread once that still leaves every SM several CTAs; small tensors keep
+    // one vector per thread so the grid stays wide (they are latency-, not bandwidth-bound)
+    const uint64_t ctas4 = (total + RE_THREADS * 4 - 1) / (RE_THREADS * 4) * gy * gz;
+    if (ctas4 >= 148 * 8) {
+        dim3 grid((unsigned)((total + RE_THREADS * 4 - 1) / (RE_THREADS * 4)), gy, gz);
         return launch_pdl(rearrange_kernel<W, 4>, grid, RE_THREADS, 0, stream, dst, src, p);
     }
-    dim3 grid((unsigned)((total + RE_THREADS - 1) / RE_THREADS), gy);
+    dim3 grid((unsigned)((total + RE_THREADS - 1) / RE_THREADS), gy, gz);
     return launch_pdl(rearrange_kernel<W, 1>, grid, RE_THREADS, 0, stream, dst, src, p);
 }
 
-// dims: innermost first, at most 3 after the recursion below has peeled the rest
+// dims: innermost first.  The grid enumerates four of them (two per thread index, two per blockIdx.y/z);
+// anything beyond that, or beyond the grid limits, is looped over on the host.
 cudaError_t launch_dims(uint8_t *dst, const uint8_t *src, std::vector<Dim> dims, uint64_t run, int w, cudaStream_t stream, uint64_t *launches) {
-    constexpr uint64_t MAX_Y = 65535, MAX_FLAT = 0xFFFFFFFFull;
+    constexpr uint64_t MAX_YZ = 65535, MAX_FLAT = 0xFFFFFFFFull;
     const uint64_t vecs = run / (uint64_t)w;
-    // peel dims the grid cannot enumerate: host loop over the outermost one
-    auto peel_last = [&]() -> cudaError_t {
-        const Dim d = dims.back();
-        dims.pop_back();
-        for (uint64_t i = 0; i < d.n; i++) {
-            cudaError_t e = launch_dims(dst + (int64_t)i * d.ds, src + (int64_t)i * d.ss, dims, run, w, stream, launches);
+    // loop over dim `d` on the host in chunks of `per`
+    auto host_loop = [&](size_t d, uint64_t per) -> cudaError_t {
+        for (uint64_t c = 0; c < dims[d].n; c += per) {
+            std::vector<Dim> d2 = dims;
+            d2[d].n = std::min(per, dims[d].n - c);
+            if (per == 1) d2.erase(d2.begin() + d);
+            cudaError_t e = launch_dims(dst + (int64_t)c * dims[d].ds, src + (int64_t)c * dims[d].ss, d2, run, w, stream, launches);
             if (e != cudaSuccess) return e;
         }
         return cudaSuccess;
     };
-    if (dims.size() > 3) return peel_last();
-    while (dims.size() < 3) dims.push_back({1, 0, 0});
-    if (dims[1].n * dims[2].n > MAX_Y) {
-        if (dims[2].n > 1) return peel_last();
-        // one huge middle dim: chunks of MAX_Y
-        for (uint64_t c = 0; c < dims[1].n; c += MAX_Y) {
-            std::vector<Dim> d2 = dims;
-            d2[1].n = std::min(MAX_Y, dims[1].n - c);
-            cudaError_t e = launch_dims(dst + (int64_t)c * dims[1].ds, src + (int64_t)c * dims[1].ss, d2, run, w, stream, launches);
-            if (e != cudaSuccess) return e;
-        }
-        return cudaSuccess;
-    }
-    if (dims[0].n * vecs > MAX_FLAT) {
-        const uint64_t per = std::max<uint64_t>(1, MAX_FLAT / vecs);  // vecs <= MAX_FLAT is ensured by the caller
-        for (uint64_t c = 0; c < dims[0].n; c += per) {
-            std::vector<Dim> d2 = dims;
-            d2[0].n = std::min(per, dims[0].n - c);
-            cudaError_t e = launch_dims(dst + (int64_t)c * dims[0].ds, src + (int64_t)c * dims[0].ss, d2, run, w, stream, launches);
-            if (e != cudaSuccess) return e;
-        }
-        return cudaSuccess;
-    }
+    if (dims.size() > 4) return host_loop(dims.size() - 1, 1);
+    while (dims.size() < 4) dims.push_back({1, 0, 0});
+    if (dims[3].n > MAX_YZ) return host_loop(3, MAX_YZ);
+    if (dims[2].n > MAX_YZ) return host_loop(2, MAX_YZ);
+    if (dims[0].n * vecs > MAX_FLAT) return host_loop(0, std::max<uint64_t>(1, MAX_FLAT / vecs));  // vecs <= 2^26 (caller)
+    if (dims[0].n * dims[1].n * vecs > MAX_FLAT) return host_loop(1, std::max<uint64_t>(1, MAX_FLAT / (dims[0].n * vecs)));
     RearrangeParams p;
     p.n0 = (uint32_t)dims[0].n;
     p.n1 = (uint32_t)dims[1].n;
     p.vecs = (uint32_t)vecs;
-    p.ds0 = dims[0].ds; p.ss0 = dims[0].ss;
-    p.ds1 = dims[1].ds; p.ss1 = dims[1].ss;
-    p.ds2 = dims[2].ds; p.ss2 = dims[2].ss;
-    const uint32_t n2 = (uint32_t)dims[2].n;
+    for (int i = 0; i < 4; i++) { p.ds[i] = dims[i].ds; p.ss[i] = dims[i].ss; }
+    const unsigned gy = (unsigned)dims[2].n, gz = (unsigned)dims[3].n;
     ++*launches;
     switch (w) {
-        case 16: return launch_w<16>(dst, src, p, n2, stream);
-        case 8: return launch_w<8>(dst, src, p, n2, stream);
-        case 4: return launch_w<4>(dst, src, p, n2, stream);
-        case 2: return launch_w<2>(dst, src, p, n2, stream);
+        case 16: return launch_w<16>(dst, src, p, gy, gz, stream);
+        case 8: return launch_w<8>(dst, src, p, gy, gz, stream);
+        case 4: return launch_w<4>(dst, src, p, gy, gz, stream);
+        case 2: return launch_w<2>(dst, src, p, gy, gz, stream);
     }
-    return launch_w<1>(dst, src, p, n2, stream);
+    return launch_w<1>(dst, src, p, gy, gz, stream);
 }
 
 }  // namespace

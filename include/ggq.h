@@ -170,7 +170,7 @@ struct ggq_convert_stats {
     double seconds_plan, seconds_convert, seconds_sync;
     int n_devices;
     int n_out_files;
-    uint64_t n_rearranged_tensors; /* tensors produced by merge-linear / split-linear / permute-qk */
+    uint64_t n_rearranged_tensors; /* tensors evaluated device-resident (rows moved by the rearrange kernel) */
 };
 
 /* `OutputArgs` of xtask (xtask/src/utils/output.rs:8-53); zero means "unlimited" / "off". */

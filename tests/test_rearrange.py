@@ -357,8 +357,8 @@ def test_convert_rearrange_steps_match_oracle(ggq, oracle, R, tmp_path, steps, o
     want = run_oracle_steps(R, oracle, ts, ops, 4, 2)
     check_file(dst, want)
     assert st["n_tensors"] == len(want)
-    if "permute-qk" in ops or experts and "merge-linear" in ops:
-        assert st["n_rearranged_tensors"] > 0
+    if "permute-qk" in ops or (experts and ops == ["merge-linear"]):
+        assert st["n_rearranged_tensors"] > 0  # rows really moved: device-resident evaluation
 
 
 @pytest.mark.gpu

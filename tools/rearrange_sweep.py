@@ -34,10 +34,34 @@ def nbytes(ty, shape):
     return n // be * bb
 
 
+def graph_time(jobs, nsets, reps):
+    """Device-side rate: the same launches captured once into a CUDA graph (no per-call host overhead)."""
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        global st
+        keep, st = st, s.cuda_stream
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            for i in range(reps):
+                jobs(i % nsets)
+        st = keep
+    gr.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gr.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
 def run(label, jobs, total_bytes):
     """jobs(i) enqueues the launches of one operator application on buffer set i."""
     nsets = max(2, int(300e6 // total_bytes) + 1)
     t = timeit(jobs, nsets, 40)
+    if t < 30e-6:  # launch-bound through ctypes: report the graph-replayed rate
+        t = graph_time(jobs, nsets, 40)
+        label += " [graph]"
     gbs = 2 * total_bytes / t / 1e9
     rows.append({"case": label, "us": t * 1e6, "GBps": gbs, "frac_measured_peak": gbs / PEAK, "tensor_MB": total_bytes / 1e6})
     print(f"{label:58s} {t*1e6:9.1f} us {gbs:8.1f} GB/s  {100*gbs/PEAK:5.1f}% of measured peak", flush=True)
