@@ -1,4 +1,4 @@
-"""`xtask convert` for `cast:` steps on the GPUs (host mirror of include/ggq.h: ggq_convert_gguf).
+"""`xtask convert` for `cast:` / `merge-linear` / `split-linear` / `permute-qk` steps on the GPUs (host mirror of include/ggq.h: ggq_convert_gguf).
 
     python -m gguf_b200.convert IN.gguf [IN2.gguf ...] -o OUT.gguf -x "cast:linear:q8_0 embd:q8_0 -> cast:linear:f32 embd:f32" [-t N] [-s 4G]
 
