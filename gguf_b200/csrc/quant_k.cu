@@ -53,9 +53,28 @@ __device__ __forceinline__ float byte_as_float(uint32_t word, int k) {
 }
 
 // ---- upstream make_qkx2_quants ------------------------------------------------------------------
+// Upstream keeps the codes L of the best candidate.  Every caller then REQUANTIZES the sub-block
+// with the 6-/4-bit rounded scale and min and uses the search's L only when that rounded scale is 0,
+// so the search here returns what produced its best codes — (iscale, min) of the accepted candidate —
+// and qkx2_codes() re-evaluates upstream's expression  nearest_int(iscale * (x[i] - min))  from those
+// in the rare case they are needed: same operands, same operation, same bits.  The candidate's codes
+// live in registers as floats for the error pass and are never packed.
+template <int N>
+__device__ __forceinline__ void qkx2_codes(const float (&x)[N], const float isc, const float mn, const int nmax, uint32_t (&L)[N / 4]) {
+    const float fmax_l = (float)nmax;
+#pragma unroll
+    for (int k = 0; k < N / 4; k++) L[k] = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        float rb;
+        round_clamped(isc * (x[i] - mn), 0.f, fmax_l, rb);
+        L[i >> 2] = put_byte(L[i >> 2], __float_as_uint(rb), i & 3);
+    }
+}
+
 template <int N, bool USE_MAD>
-__device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const float (&w)[N], const int nmax, uint32_t (&L)[N / 4],
-                                                  float &the_min, const float rmin, const float rdelta, const int nstep) {
+__device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const float (&w)[N], const int nmax, float &the_min, const float rmin,
+                                                  const float rdelta, const int nstep, float &isc_best, float &mn_best) {
     float mn = x[0], mx = x[0];
     float sum_w = w[0];
     float sum_x = sum_w * x[0];
@@ -66,22 +85,23 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
         sum_w += w[i];
         sum_x += w[i] * x[i];
     }
-#pragma unroll
-    for (int k = 0; k < N / 4; k++) L[k] = 0;
     if (mn > 0) mn = 0;
-    if (mx == mn) {
+    if (mx == mn) {  // L[i] = 0: iscale 0 reproduces that
         the_min = -mn;
+        isc_best = 0.f;
+        mn_best = mn;
         return 0.f;
     }
     const float fmax_l = (float)nmax;
     float iscale = fmax_l / (mx - mn);
     float scale = 1 / iscale;
     float best_mad = 0;
+    isc_best = iscale;
+    mn_best = mn;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         float rb;
         const float l = round_clamped(iscale * (x[i] - mn), 0.f, fmax_l, rb);
-        L[i >> 2] = put_byte(L[i >> 2], __float_as_uint(rb), i & 3);
         float diff = scale * l + mn - x[i];
         diff = USE_MAD ? fabsf(diff) : diff * diff;
         best_mad += w[i] * diff;
@@ -89,15 +109,14 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
     for (int is = 0; is <= nstep; ++is) {
         iscale = (rmin + rdelta * (float)is + fmax_l) / (mx - mn);
         float sum_l = 0, sum_l2 = 0, sum_xl = 0;
-        uint32_t Laux[N / 4];
+        float lf[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             float rb;
-            const float l = round_clamped(iscale * (x[i] - mn), 0.f, fmax_l, rb);
-            Laux[i >> 2] = (i & 3) == 0 ? __float_as_uint(rb) & 0xFFu : put_byte(Laux[i >> 2], __float_as_uint(rb), i & 3);
-            const float wl = w[i] * l;
+            lf[i] = round_clamped(iscale * (x[i] - mn), 0.f, fmax_l, rb);
+            const float wl = w[i] * lf[i];
             sum_l += wl;
-            sum_l2 += wl * l;
+            sum_l2 += wl * lf[i];
             sum_xl += wl * x[i];
         }
         const float D = sum_w * sum_l2 - sum_l * sum_l;
@@ -111,13 +130,13 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
             float mad = 0;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                float diff = this_scale * byte_as_float(Laux[i >> 2], i & 3) + this_min - x[i];
+                float diff = this_scale * lf[i] + this_min - x[i];
                 diff = USE_MAD ? fabsf(diff) : diff * diff;
                 mad += w[i] * diff;
             }
             if (mad < best_mad) {
-#pragma unroll
-                for (int k = 0; k < N / 4; k++) L[k] = Laux[k];
+                isc_best = iscale;  // the codes just evaluated came from (iscale, mn before the update)
+                mn_best = mn;
                 best_mad = mad;
                 scale = this_scale;
                 mn = this_min;
@@ -129,29 +148,34 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
 }
 
 // ---- upstream make_qx_quants(n=16, nmax, rmse_type=1, qw=NULL); codes stored as l + nmax -----------
-__device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const int nmax, uint32_t (&L)[4]) {
+// Same deferral: the search returns the iscale of its best candidate; qx_codes16() is upstream's
+// `L[i] = nmax + clamp(nearest_int(iscale * x[i]))`, evaluated only when the caller needs the codes.
+__device__ __forceinline__ void qx_codes16(const float (&x)[16], const float isc, const int nmax, uint32_t (&L)[4]) {
+    const float lo = (float)(-nmax), hi = (float)(nmax - 1), fn = (float)nmax;
+#pragma unroll
+    for (int k = 0; k < 4; k++) L[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float rb;
+        round_clamped(isc * x[i], lo, hi, rb);
+        L[i >> 2] = put_byte(L[i >> 2], __float_as_uint(rb + fn), i & 3);  // low byte of (l + nmax)
+    }
+}
+// returns the scale; `isc_best` = iscale of the kept codes; `all_zero`: upstream's early exit (L[i] = 0, raw)
+__device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const int nmax, float &isc_best, bool &all_zero) {
     float mx = 0, amax = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const float ax = fabsf(x[i]);
         if (ax > amax) { amax = ax; mx = x[i]; }
     }
-#pragma unroll
-    for (int k = 0; k < 4; k++) L[k] = 0;
-    if (amax < GROUP_MAX_EPS) return 0.f;
+    isc_best = 0.f;
+    all_zero = amax < GROUP_MAX_EPS;
+    if (all_zero) return 0.f;
     const float lo = (float)(-nmax), hi = (float)(nmax - 1), fn = (float)nmax;
     float w[16], wx[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { w[i] = x[i] * x[i]; wx[i] = w[i] * x[i]; }  // w*x*l is evaluated (w*x)*l
-    // codes for `iscale` (upstream recomputes them on acceptance with the same expression)
-    auto codes = [&](float isc) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float rb;
-            round_clamped(isc * x[i], lo, hi, rb);
-            L[i >> 2] = put_byte(L[i >> 2], __float_as_uint(rb + fn), i & 3);  // low byte of (l + nmax)
-        }
-    };
     float iscale = lo / mx;
     float sumlx = 0, suml2 = 0;
 #pragma unroll
@@ -161,7 +185,7 @@ __device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const in
         sumlx += wx[i] * l;
         suml2 += w[i] * l * l;
     }
-    codes(iscale);
+    isc_best = iscale;
     float scale = suml2 ? sumlx / suml2 : 0.0f;
     float best = scale * sumlx;
     for (int is = -9; is <= 9; ++is) {
@@ -176,7 +200,7 @@ __device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const in
             suml2 += w[i] * l * l;
         }
         if (suml2 > 0 && sumlx * sumlx > best * suml2) {
-            codes(iscale);
+            isc_best = iscale;
             scale = sumlx / suml2;
             best = scale * sumlx;
         }
@@ -283,8 +307,8 @@ template <int NMAX> __device__ __forceinline__ void k45_lane(const float (&x)[32
 #pragma unroll
     for (int l = 0; l < 32; ++l) w[l] = av_x + fabsf(x[l]);
     uint32_t L[8];
-    float the_min;
-    const float scale = make_qkx2_quants<32, false>(x, w, NMAX, L, the_min, rmin, 0.1f, nstep);
+    float the_min, isc_best, mn_best;
+    const float scale = make_qkx2_quants<32, false>(x, w, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best);
     const float max_scale = group_max_from_zero<8>(scale), max_min = group_max_from_zero<8>(the_min);
     const float inv_scale = max_scale > 0 ? 63.f / max_scale : 0.f;
     const float inv_min = max_min > 0 ? 63.f / max_min : 0.f;
@@ -304,6 +328,8 @@ template <int NMAX> __device__ __forceinline__ void k45_lane(const float (&x)[32
             l = max(0, min(NMAX, l));
             set_code(L, ii, l);
         }
+    } else {
+        qkx2_codes<32>(x, isc_best, mn_best, NMAX, L);  // upstream `if (!d) continue;`: the search's codes stay
     }
     put_codes<32>(s, j, L);
     s.a[j] = (uint8_t)ls;
@@ -349,26 +375,28 @@ template <> struct KQuant<T_Q5K> {
 template <> struct KQuant<T_Q6K> {
     static constexpr int SUB = 16;
     static __device__ __forceinline__ void lane(const float (&x)[16], int j, int lane_id, KScratch &s) {
-        uint32_t L[4];
-        const float scale = make_qx_quants16(x, 32, L);
+        uint32_t L[4] = {0, 0, 0, 0};
+        float isc_best;
+        bool sub_zero;
+        const float scale = make_qx_quants16(x, 32, isc_best, sub_zero);
         const float max_scale = group_max_by_abs<16>(scale, lane_id);
         const bool zero = fabsf(max_scale) < GROUP_MAX_EPS;
         int sc = 0;
         uint16_t d16 = 0;
-        if (!zero) {
+        if (!zero) {  // a zero super-block is written as zero bytes whatever L holds
             const float iscale = -128.f / max_scale;
             d16 = f2h(1 / iscale);
             sc = min(127, nearest_int(iscale * scale));
             const float d = h2f(d16) * (float)(int)(int8_t)sc;
             if (d != 0.f) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) L[k] = 0;
-#pragma unroll
                 for (int ii = 0; ii < 16; ++ii) {
                     int l = nearest_int(x[ii] / d);
                     l = max(-32, min(31, l));
                     set_code(L, ii, l + 32);
                 }
+            } else if (!sub_zero) {
+                qx_codes16(x, isc_best, 32, L);  // upstream `if (!d) continue;`: the search's codes stay
             }
         }
         put_codes<16>(s, j, L);
@@ -397,8 +425,8 @@ template <> struct KQuant<T_Q2K> {
 #pragma unroll
         for (int l = 0; l < 16; ++l) w[l] = fabsf(x[l]);
         uint32_t L[4];
-        float the_min;
-        const float scale = make_qkx2_quants<16, true>(x, w, 3, L, the_min, -0.5f, 0.1f, 15);
+        float the_min, isc_best, mn_best;
+        const float scale = make_qkx2_quants<16, true>(x, w, 3, the_min, -0.5f, 0.1f, 15, isc_best, mn_best);
         const float max_scale = group_max_from_zero<16>(scale), max_min = group_max_from_zero<16>(the_min);
         uint32_t b = 0;
         uint16_t d16 = 0, dmin16 = 0;
@@ -423,6 +451,8 @@ template <> struct KQuant<T_Q2K> {
                 l = max(0, min(3, l));
                 set_code(L, ii, l);
             }
+        } else {
+            qkx2_codes<16>(x, isc_best, mn_best, 3, L);  // upstream `if (!d) continue;`: the search's codes stay
         }
         put_codes<16>(s, j, L);
         s.a[j] = (uint8_t)b;

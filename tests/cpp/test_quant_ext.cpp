@@ -106,6 +106,33 @@ int main(int argc, char **argv) {
         CHECK(cast({GGQ_Q8_0, GGQ_F16}, h.data(), q.data(), 31).unwrap_err() == QuantizeError::Indivisible);
         CHECK(type_nbytes(GGQ_Q4K, 512) == 288 && type_nbytes(GGQ_Q4K, 100) == 0);
     }
+    {
+        // layout algebra of permute_qk.rs:57-60 (documented ndarray-layout examples) — no GPU needed
+        using ndl::ArrayLayout;
+        const ArrayLayout t = ArrayLayout::new_contiguous({6, 3, 2}, 1);      // strides 1, 6, 18
+        const ArrayLayout tl = t.tile_le(0, {2, 3});
+        CHECK((tl.shape == std::vector<uint64_t>{2, 3, 3, 2}) && (tl.strides == std::vector<int64_t>{1, 2, 6, 18}));
+        const ArrayLayout tr = t.transpose({1, 0});
+        CHECK((tr.shape == std::vector<uint64_t>{3, 6, 2}) && (tr.strides == std::vector<int64_t>{6, 1, 18}));
+        const auto parts = ArrayLayout::new_contiguous({4, 6}, 2).split(1, {1, 2, 3});
+        CHECK(parts.size() == 3 && parts[1].offset == 8 && parts[2].offset == 24 && parts[2].shape[1] == 3);
+        CHECK(parts[0].is_dense(2) && ArrayLayout::new_contiguous({4, 6, 2}, 2).split(1, {2, 4})[0].is_dense(2) == false);
+        // shape mismatch = SchemeError::ShapeMismatch, rejected before any CUDA call
+        uint8_t buf[64] = {0};
+        CHECK(rearrange(buf, ArrayLayout::new_contiguous({4, 4}, 2), buf, ArrayLayout::new_contiguous({4, 3}, 2), 2).unwrap_err() == QuantizeError::LengthMismatch);
+    }
+    if (!no_gpu) {
+        // permute_qk.rs:46-69 on 8 rows of 4 bytes, 2 heads: within a head, row 2*i+j <- row j*half+i
+        using ndl::ArrayLayout;
+        uint8_t src[32], dst[32];
+        for (int i = 0; i < 32; i++) src[i] = (uint8_t)i;
+        const ArrayLayout sl = ArrayLayout::new_contiguous({4, 8}, 1).tile_le(1, {2, 2, 2}).transpose({2, 1});
+        const ArrayLayout dl = ArrayLayout::new_contiguous(sl.shape, 1);
+        rearrange(dst, dl, src, sl, 1).unwrap();
+        const int want_row[8] = {0, 2, 1, 3, 4, 6, 5, 7};
+        for (int r = 0; r < 8; r++)
+            for (int b = 0; b < 4; b++) CHECK(dst[r * 4 + b] == want_row[r] * 4 + b);
+    }
     std::printf(failures ? "%d FAILURES\n" : "all ok%.0d\n", failures);
     return failures ? 1 : 0;
 }
