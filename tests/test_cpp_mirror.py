@@ -20,6 +20,16 @@ def test_cpp_mirror_error_order_no_gpu(ggq):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_tensor_ops_planner_no_gpu(ggq):
+    """tests/cpp/test_tensor_ops.cpp: merge-linear / split-linear / permute-qk / cast planning (host/tensor_ops.hpp)."""
+    exe = os.path.join(ROOT, "tests", "cpp", "test_tensor_ops")
+    so_dir = os.path.join(ROOT, "gguf_b200")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_tensor_ops.cpp"),
+                           "-L" + so_dir, "-l:libggq.so", "-Wl,-rpath," + so_dir])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_cpp_mirror_reference_unit_tests(ggq):
     build(ggq)
