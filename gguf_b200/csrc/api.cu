@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -254,6 +255,10 @@ class CopyPool {
     CopyPool() {
         unsigned hw = std::thread::hardware_concurrency();
         int n = hw ? (int)std::min(8u, std::max(2u, hw / 2)) : 4;
+        if (const char *env = getenv("GGQ_COPY_THREADS")) {  // tuning knob: helper threads for pageable bounce copies
+            const int v = atoi(env);
+            if (v >= 1 && v <= 64) n = v;
+        }
         for (int i = 0; i < n; i++)
             workers_.emplace_back([this] {
                 for (;;) {

@@ -55,9 +55,19 @@ def write_gguf(path, kvs, tensors, alignment=32, alignment_first=False, version=
         f.write(blob)
 
 
-def read_gguf(path):
+def index_gguf(path):
+    """Like read_gguf but without copying tensor data: (tensors: dict name -> (shape, type, absolute offset, nbytes),
+    alignment, uint8 memmap of the file)."""
+    import mmap
+    with open(path, "rb") as f:
+        mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+    _, tensors, alignment, _ = read_gguf(path, _buf=mm, _index_only=True)
+    return tensors, alignment, np.frombuffer(mm, np.uint8)
+
+
+def read_gguf(path, _buf=None, _index_only=False):
     """Returns (kvs: list of (key, type, raw value bytes), tensors: dict name -> (shape, type, bytes), alignment)."""
-    buf = open(path, "rb").read()
+    buf = open(path, "rb").read() if _buf is None else _buf
     assert buf[:4] == b"GGUF"
     ver, nt, nkv = struct.unpack_from("<IQQ", buf, 4)
     assert ver == 3
@@ -66,7 +76,7 @@ def read_gguf(path):
     def rs():
         nonlocal p
         (n,) = struct.unpack_from("<Q", buf, p)
-        s = buf[p + 8:p + 8 + n].decode()
+        s = bytes(buf[p + 8:p + 8 + n]).decode()
         p += 8 + n
         return s
 
@@ -108,6 +118,6 @@ def read_gguf(path):
     for name, shape, ty, off in infos:
         e, b = TYPE_SIZE[ty]
         n = int(np.prod(shape)) // e * b
-        tensors[name] = (shape, ty, buf[p + off:p + off + n])
+        tensors[name] = (shape, ty, p + off, n) if _index_only else (shape, ty, buf[p + off:p + off + n])
         assert off % alignment == 0
     return kvs, tensors, alignment, len(buf)

@@ -15,7 +15,7 @@ for ndev in sorted({1, ndev_all}):
     for ty in (g.Q8_0, g.Q4_0):
         e, b = g.block_info(ty)
         nbytes = n // e * b
-        for mem in ("pinned", "pageable"):
+        for mem in os.environ.get("E2E_MEM", "pinned,pageable").split(","):
             if mem == "pinned":
                 pf, pq = g.PinnedBuffer(n * 2), g.PinnedBuffer(nbytes)
                 fa, qa = pf.view(np.uint16), pq.array
