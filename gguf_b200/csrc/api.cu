@@ -562,6 +562,17 @@ void configure_mem_pool(int device) {  // keep freed stream-ordered allocations 
 
 namespace ggq {
 
+size_t device_free_bytes() {
+    DevInfo dev;
+    if (resolve_device(&dev) != GGQ_OK) return 0;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return free_b;
+}
+
 struct Resident::Impl {
     DevInfo dev;
     Pipeline *pl = nullptr;

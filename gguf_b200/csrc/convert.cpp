@@ -31,6 +31,7 @@
 #include <atomic>
 #include <cctype>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -114,6 +115,45 @@ struct Step {
 };
 
 // ---- producing a tensor's bytes ---------------------------------------------------------------------
+
+// Device memory the resident evaluation of `n` holds at its peak: the result plus the temporaries of
+// the deepest operand chain (each operator frees its operand as soon as it has consumed it).
+uint64_t resident_peak_bytes(const Node &n) {
+    if (n.kind == Node::SOURCE) return 0;  // uploaded straight into the caller's buffer
+    uint64_t worst = 0;
+    for (const NodeP &c : n.in) worst = std::max(worst, nbytes_of(*c) + resident_peak_bytes(*c));
+    if (n.kind == Node::CAST) {  // intermediates of a multi-hop chain: two live at a time, F32 is the widest
+        if (n.chain.size() > 2) worst += 2 * count(n.shape) * 4;
+    }
+    return worst;
+}
+
+// Worker threads evaluate different tensors at the same time; a per-device budget keeps the sum of their
+// peaks inside the GPU's free memory (a 256-expert merge is tens of GB).  A tensor that is larger than
+// the whole budget runs alone.
+class ResidentBudget {
+   public:
+    void acquire(int dev, uint64_t bytes) {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (limit_.count(dev) == 0) {
+            const size_t free_b = ggq::device_free_bytes();
+            limit_[dev] = free_b ? (uint64_t)(free_b * 0.8) : UINT64_MAX;
+            if (const char *env = getenv("GGQ_RESIDENT_BUDGET_MB")) limit_[dev] = (uint64_t)atoll(env) << 20;  // tests / tuning
+        }
+        cv_.wait(lk, [&] { return used_[dev] == 0 || used_[dev] + bytes <= limit_[dev]; });
+        used_[dev] += bytes;
+    }
+    void release(int dev, uint64_t bytes) {
+        { std::lock_guard<std::mutex> lk(mu_); used_[dev] -= bytes; }
+        cv_.notify_all();
+    }
+
+   private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::map<int, uint64_t> limit_, used_;
+};
+
 struct IoCtx {
     const std::vector<int> *in_fds;
     int out_fd;
@@ -121,6 +161,8 @@ struct IoCtx {
     ggq::Resident *res;  // created on first use by the worker
     std::function<ggq::Resident *()> resident;
     bool used_resident = false;  // set by emit(): the tensor went through the device-resident path
+    ResidentBudget *budget = nullptr;
+    int device = 0;
 };
 
 // device-resident evaluation: the node's bytes end up, contiguous, at d_dst
@@ -237,11 +279,14 @@ int emit(const Node &n, uint64_t out_off, IoCtx &io) {
     ggq::Resident *res = io.resident();
     if (!res) return GGQ_ERR_CUDA;
     io.used_resident = true;
+    const uint64_t peak = nbytes + resident_peak_bytes(n);
+    if (io.budget) io.budget->acquire(io.device, peak);
     void *d = nullptr;
     int rc = res->alloc(nbytes, &d);
     if (rc == GGQ_OK) rc = eval_into(n, d, io);
     if (rc == GGQ_OK) rc = res->download(d, nbytes, [ofd, out_off](const void *pinned, size_t off, size_t len) { return pwrite_all(ofd, pinned, len, out_off + off); });
     if (d) res->free(d);
+    if (io.budget) io.budget->release(io.device, peak);
     if (rc != GGQ_OK && t_cerr.empty()) t_cerr = ggq_last_error();
     return rc;
 }
@@ -459,11 +504,12 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
         };
         std::vector<int> in_fds;
         for (const auto &f : files) in_fds.push_back(f->fd);
+        ResidentBudget budget;
         auto worker = [&](int dev) {
             if (need_gpu && ggq_set_device(dev) != GGQ_OK) { set_err(GGQ_ERR_CUDA, ggq_last_error()); return; }
             std::vector<uint8_t> copy_buf;
             std::unique_ptr<ggq::Resident> res;
-            IoCtx io{&in_fds, -1, &copy_buf, nullptr, nullptr, false};
+            IoCtx io{&in_fds, -1, &copy_buf, nullptr, nullptr, false, &budget, dev};
             io.resident = [&]() -> ggq::Resident * {
                 if (!res) {
                     res = std::make_unique<ggq::Resident>();

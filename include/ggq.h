@@ -215,7 +215,7 @@ void *ggq_host_alloc(size_t bytes);
 void ggq_host_free(void *p);
 
 /* Releases the idle stream pipelines (device staging buffers, pinned bounce buffers, streams) the host
- * entry points keep pooled between calls.  Safe at any time; pipelines in use are not touched and the
+ * entry points keep pooled between calls, and the device memory cached by the stream-ordered allocator.  Safe at any time; pipelines in use are not touched and the
  * pool refills on demand. */
 void ggq_shutdown(void);
 

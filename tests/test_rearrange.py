@@ -385,3 +385,18 @@ def test_convert_split_of_premerged_file_and_quantized_permute(ggq, oracle, R, t
     assert set(seen) == set(want)
     for n, (ty, shape, data) in want.items():
         assert seen[n][2] == data.tobytes(), n
+
+
+@pytest.mark.gpu
+def test_convert_resident_budget_serialises_big_tensors(ggq, oracle, R, tmp_path, monkeypatch):
+    """With a 1 MB device-memory budget every device-resident tensor is larger than the budget and runs alone;
+    the output must not change."""
+    from gguf_b200.convert import convert
+    monkeypatch.setenv("GGQ_RESIDENT_BUDGET_MB", "1")
+    src, dst = tmp_path / "in.gguf", tmp_path / "out.gguf"
+    ts = qkv_model(R, hidden=512, ffn=768, experts=4, seed=80, layers=3)
+    write_gguf(src, model_kvs(), ts)
+    st = convert(src, dst, "permute-qk -> merge-linear -> cast:linear:q8_0")
+    want = run_oracle_steps(R, oracle, ts, ["permute-qk", "merge-linear", dict(linear=8)], 4, 2)
+    check_file(dst, want)
+    assert st["n_rearranged_tensors"] >= 6
