@@ -72,6 +72,27 @@ __device__ __forceinline__ void qkx2_codes(const float (&x)[N], const float isc,
     }
 }
 
+// Blackwell packed FP32 (FADD2 / FMUL2, `add/mul.rn.f32x2`): one issue slot performs the IEEE operation on
+// two independent floats — measured 73.6 T FP32 op/s against 36.1 T for scalar FADD / FMUL on B200
+// (tools/f32x2_probe.cu).  The search is issue-bound, so every per-element operation that is independent
+// between neighbouring elements is done on the pairs (x[2k], x[2k+1]); the running sums stay scalar and in
+// upstream's order (.x then .y), so every float is rounded exactly as before.
+__device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 clamp2(float2 v, float lo, float hi) { return make_float2(fminf(fmaxf(v.x, lo), hi), fminf(fmaxf(v.y, lo), hi)); }
+__device__ __forceinline__ float2 abs2(float2 v) { return make_float2(fabsf(v.x), fabsf(v.y)); }
+// (ns*l + nm) per lane with its two roundings.  Scalar on purpose: ptxas 12.9 contracts a mul.rn.f32x2 feeding an
+// add.rn.f32x2 into one single-rounding FFMA2 even with --fmad=false (the explicit .rn protects only scalar
+// code), which changes results.  No other packed multiply in this file feeds a packed add; the Makefile
+// checks that the object contains no FFMA2.
+__device__ __forceinline__ float2 affine2_two_roundings(float2 l, float ns, float nm) {
+    return make_float2(__fadd_rn(__fmul_rn(l.x, ns), nm), __fadd_rn(__fmul_rn(l.y, ns), nm));
+}
+// rint(clamp(v)) for both lanes, see round_clamped()
+__device__ __forceinline__ float2 round_clamped2(float2 v, float lo, float hi) {
+    const float2 rb = __fadd2_rn(clamp2(v, lo, hi), bcast2(RMAGIC));
+    return __fadd2_rn(rb, bcast2(-RMAGIC));
+}
+
 template <int N, bool USE_MAD>
 __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const float (&w)[N], const int nmax, float &the_min, const float rmin,
                                                   const float rdelta, const int nstep, float &isc_best, float &mn_best) {
@@ -92,32 +113,47 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
         mn_best = mn;
         return 0.f;
     }
+    float2 x2[N / 2], w2[N / 2];
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) { x2[k] = make_float2(x[2 * k], x[2 * k + 1]); w2[k] = make_float2(w[2 * k], w[2 * k + 1]); }
     const float fmax_l = (float)nmax;
     float iscale = fmax_l / (mx - mn);
     float scale = 1 / iscale;
     float best_mad = 0;
     isc_best = iscale;
     mn_best = mn;
+    // error of (scale, min) with codes l:  diff = scale*l + min - x  is evaluated as  x + ((-scale)*l + (-min)) = -diff
+    // (round-to-nearest is sign-symmetric, so this is the exact negation; only diff*diff or |diff| is used)
+    {
+        const float2 nmn = bcast2(-mn), isc2 = bcast2(iscale);
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        float rb;
-        const float l = round_clamped(iscale * (x[i] - mn), 0.f, fmax_l, rb);
-        float diff = scale * l + mn - x[i];
-        diff = USE_MAD ? fabsf(diff) : diff * diff;
-        best_mad += w[i] * diff;
+        for (int k = 0; k < N / 2; ++k) {
+            const float2 l = round_clamped2(__fmul2_rn(__fadd2_rn(x2[k], nmn), isc2), 0.f, fmax_l);
+            float2 d = __fadd2_rn(x2[k], affine2_two_roundings(l, -scale, -mn));
+            d = USE_MAD ? abs2(d) : __fmul2_rn(d, d);
+            const float2 e = __fmul2_rn(w2[k], d);
+            best_mad += e.x;
+            best_mad += e.y;
+        }
     }
     for (int is = 0; is <= nstep; ++is) {
         iscale = (rmin + rdelta * (float)is + fmax_l) / (mx - mn);
         float sum_l = 0, sum_l2 = 0, sum_xl = 0;
-        float lf[N];
+        float2 lf[N / 2];
+        {
+            const float2 nmn = bcast2(-mn), isc2 = bcast2(iscale);
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            float rb;
-            lf[i] = round_clamped(iscale * (x[i] - mn), 0.f, fmax_l, rb);
-            const float wl = w[i] * lf[i];
-            sum_l += wl;
-            sum_l2 += wl * lf[i];
-            sum_xl += wl * x[i];
+            for (int k = 0; k < N / 2; ++k) {
+                lf[k] = round_clamped2(__fmul2_rn(__fadd2_rn(x2[k], nmn), isc2), 0.f, fmax_l);
+                const float2 wl = __fmul2_rn(w2[k], lf[k]);
+                const float2 wl2 = __fmul2_rn(wl, lf[k]), wlx = __fmul2_rn(wl, x2[k]);
+                sum_l += wl.x;
+                sum_l2 += wl2.x;
+                sum_xl += wlx.x;
+                sum_l += wl.y;
+                sum_l2 += wl2.y;
+                sum_xl += wlx.y;
+            }
         }
         const float D = sum_w * sum_l2 - sum_l * sum_l;
         if (D > 0) {
@@ -129,10 +165,12 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
             }
             float mad = 0;
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                float diff = this_scale * lf[i] + this_min - x[i];
-                diff = USE_MAD ? fabsf(diff) : diff * diff;
-                mad += w[i] * diff;
+            for (int k = 0; k < N / 2; ++k) {
+                float2 d = __fadd2_rn(x2[k], affine2_two_roundings(lf[k], -this_scale, -this_min));
+                d = USE_MAD ? abs2(d) : __fmul2_rn(d, d);
+                const float2 e = __fmul2_rn(w2[k], d);
+                mad += e.x;
+                mad += e.y;
             }
             if (mad < best_mad) {
                 isc_best = iscale;  // the codes just evaluated came from (iscale, mn before the update)
@@ -173,32 +211,37 @@ __device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const in
     all_zero = amax < GROUP_MAX_EPS;
     if (all_zero) return 0.f;
     const float lo = (float)(-nmax), hi = (float)(nmax - 1), fn = (float)nmax;
-    float w[16], wx[16];
+    float2 x2[8], w2[8], wx2[8];  // packed pairs (see make_qkx2_quants); w*x*l is evaluated (w*x)*l, w*l*l as (w*l)*l
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { w[i] = x[i] * x[i]; wx[i] = w[i] * x[i]; }  // w*x*l is evaluated (w*x)*l
-    float iscale = lo / mx;
-    float sumlx = 0, suml2 = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        float rb;
-        const float l = round_clamped(iscale * x[i], lo, hi, rb);
-        sumlx += wx[i] * l;
-        suml2 += w[i] * l * l;
+    for (int k = 0; k < 8; ++k) {
+        x2[k] = make_float2(x[2 * k], x[2 * k + 1]);
+        w2[k] = __fmul2_rn(x2[k], x2[k]);
+        wx2[k] = __fmul2_rn(w2[k], x2[k]);
     }
+    // sumlx, suml2 for `isc`, accumulated in element order
+    auto sums = [&](float isc, float &sumlx, float &suml2) {
+        const float2 isc2 = bcast2(isc);
+        sumlx = suml2 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float2 l = round_clamped2(__fmul2_rn(isc2, x2[k]), lo, hi);
+            const float2 a = __fmul2_rn(wx2[k], l), b = __fmul2_rn(__fmul2_rn(w2[k], l), l);
+            sumlx += a.x;
+            suml2 += b.x;
+            sumlx += a.y;
+            suml2 += b.y;
+        }
+    };
+    float iscale = lo / mx;
+    float sumlx, suml2;
+    sums(iscale, sumlx, suml2);
     isc_best = iscale;
     float scale = suml2 ? sumlx / suml2 : 0.0f;
     float best = scale * sumlx;
     for (int is = -9; is <= 9; ++is) {
         if (is == 0) continue;
         iscale = -(fn + 0.1f * (float)is) / mx;
-        sumlx = suml2 = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float rb;
-            const float l = round_clamped(iscale * x[i], lo, hi, rb);
-            sumlx += wx[i] * l;
-            suml2 += w[i] * l * l;
-        }
+        sums(iscale, sumlx, suml2);
         if (suml2 > 0 && sumlx * sumlx > best * suml2) {
             isc_best = iscale;
             scale = sumlx / suml2;
