@@ -226,6 +226,22 @@ template <class FT> __device__ __forceinline__ float fix_zero_min(const Row<FT> 
 
 // floor(v) for 0 <= v < 2^23 left in the low mantissa bits (RZ add never rounds up across an integer)
 __device__ __forceinline__ uint32_t floor_bits(float v) { return __float_as_uint(__fadd_rz(v, 8388608.0f)); }
+// ---- packed FP32 (Blackwell FADD2 / FMUL2, `*.f32x2`): the kernel is issue-bound, and a packed instruction
+// does the IEEE operation on the pair (x[2k], x[2k+1]) in one issue slot.  One rule: a packed multiply must
+// never feed a packed add — ptxas 12.9 contracts that pair into a single-rounding FFMA2 even with
+// --fmad=false (see quant_k.cu; the Makefile rejects objects containing FFMA2) — so the `+ 8.5` / `+ 0.5`
+// after `x * recip` stays two scalar __fadd_rn.
+__device__ __forceinline__ float2 pair_of(const float *x, int k) { return make_float2(x[2 * k], x[2 * k + 1]); }
+__device__ __forceinline__ float2 mul2(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+__device__ __forceinline__ float2 add2(float2 a, float c) { return __fadd2_rn(a, make_float2(c, c)); }
+__device__ __forceinline__ float2 add_after_mul(float2 a, float c) { return make_float2(__fadd_rn(a.x, c), __fadd_rn(a.y, c)); }
+__device__ __forceinline__ float2 clamp2(float2 v, float lo, float hi) { return make_float2(fminf(fmaxf(v.x, lo), hi), fminf(fmaxf(v.y, lo), hi)); }
+// floor(v) of both lanes left in the low mantissa bits (see floor_bits)
+__device__ __forceinline__ void floor_bits2(float2 v, uint32_t &b0, uint32_t &b1) {
+    const float2 t = __fadd2_rz(v, make_float2(8388608.0f, 8388608.0f));
+    b0 = __float_as_uint(t.x);
+    b1 = __float_as_uint(t.y);
+}
 // Rust `v.round() as i8` as an int: half away from zero, NaN -> 0, +-inf saturate at int range
 __device__ __forceinline__ int round_half_away(float v) {
     const float h = __uint_as_float((__float_as_uint(v) & 0x80000000u) | 0x3F000000u);  // copysign(0.5, v)
@@ -280,10 +296,11 @@ template <> struct Encoder<T_Q4_0> {
             d16 = f2h(d);
             uint32_t c[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
+            for (int k = 0; k < 16; k++) {
                 // (x*recip + 8.5).min(15.) as u8 : NaN -> 15 (fminf drops it), negatives -> 0
-                const float v = fminf(__fadd_rn(__fmul_rn(r.x[i], rc), 8.5f), 15.0f);
-                c[i] = floor_bits(fmaxf(v, 0.0f));
+                float2 v = add_after_mul(mul2(pair_of(r.x, k), rc), 8.5f);
+                v = make_float2(fmaxf(fminf(v.x, 15.0f), 0.0f), fmaxf(fminf(v.y, 15.0f), 0.0f));
+                floor_bits2(v, c[2 * k], c[2 * k + 1]);
             }
             nibble_bytes(c, w);
         }
@@ -306,10 +323,10 @@ template <> struct Encoder<T_Q4_1> {
             d16 = f2h(d);
             uint32_t c[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
+            for (int k = 0; k < 16; k++) {
                 // (((x - min)*recip + 0.5) as u8).min(15) : NaN -> 0
-                const float v = __fadd_rn(__fmul_rn(__fsub_rn(r.x[i], mn), rc), 0.5f);
-                c[i] = floor_bits(fminf(fmaxf(v, 0.0f), 15.0f));
+                const float2 v = add_after_mul(mul2(add2(pair_of(r.x, k), -mn), rc), 0.5f);
+                floor_bits2(clamp2(v, 0.0f, 15.0f), c[2 * k], c[2 * k + 1]);
             }
             nibble_bytes(c, w);
         }
@@ -348,10 +365,10 @@ template <> struct Encoder<T_Q5_0> {
             d16 = f2h(d);
             uint32_t c[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
+            for (int k = 0; k < 16; k++) {
                 // ((x*recip + 16.5) as u8).min(31) : NaN -> 0
-                const float v = __fadd_rn(__fmul_rn(r.x[i], rc), 16.5f);
-                c[i] = floor_bits(fminf(fmaxf(v, 0.0f), 31.0f));
+                const float2 v = add_after_mul(mul2(pair_of(r.x, k), rc), 16.5f);
+                floor_bits2(clamp2(v, 0.0f, 31.0f), c[2 * k], c[2 * k + 1]);
             }
             pack5(c, qh, w);
         }
@@ -376,9 +393,9 @@ template <> struct Encoder<T_Q5_1> {
             d16 = f2h(d);
             uint32_t c[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                const float v = __fadd_rn(__fmul_rn(__fsub_rn(r.x[i], mn), rc), 0.5f);
-                c[i] = floor_bits(fminf(fmaxf(v, 0.0f), 31.0f));
+            for (int k = 0; k < 16; k++) {
+                const float2 v = add_after_mul(mul2(add2(pair_of(r.x, k), -mn), rc), 0.5f);
+                floor_bits2(clamp2(v, 0.0f, 31.0f), c[2 * k], c[2 * k + 1]);
             }
             pack5(c, qh, w);
         }
@@ -399,9 +416,10 @@ template <uint32_t T, bool WITH_SUM> struct Encoder8 {
             const float d = __fdiv_rn(amax, 127.0f), rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
 #pragma unroll
-            for (int k = 0; k < 8; k++)
-                w[k] = pack_sat_s8(round_half_away(__fmul_rn(r.x[4 * k], rc)), round_half_away(__fmul_rn(r.x[4 * k + 1], rc)),
-                                   round_half_away(__fmul_rn(r.x[4 * k + 2], rc)), round_half_away(__fmul_rn(r.x[4 * k + 3], rc)));
+            for (int k = 0; k < 8; k++) {
+                const float2 a = mul2(pair_of(r.x, 2 * k), rc), b = mul2(pair_of(r.x, 2 * k + 1), rc);
+                w[k] = pack_sat_s8(round_half_away(a.x), round_half_away(a.y), round_half_away(b.x), round_half_away(b.y));
+            }
             if constexpr (WITH_SUM) {
                 int s = 0;
 #pragma unroll
@@ -434,11 +452,14 @@ template <> struct Encoder<T_Q8K> {
             const float d = __fdiv_rn(mx, -127.0f), rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
             int q[32];
+            float2 prod[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) prod[k] = mul2(pair_of(r.x, k), rc);
 #pragma unroll
             for (int i = 0; i < 32; i++) {
                 // (x*recip).round().min(127.) as i8 : NaN.round() is NaN and NaN.min(127.) is 127.
                 // trunc(min(t, 127)) == min(trunc(t), 127) and fminf drops a NaN t, so no branch.
-                const float p = __fmul_rn(r.x[i], rc);
+                const float p = (i & 1) ? prod[i >> 1].y : prod[i >> 1].x;
                 const float h = __uint_as_float((__float_as_uint(p) & 0x80000000u) | 0x3F000000u);  // copysign(0.5, p)
                 q[i] = __float2int_rz(fminf(__fadd_rz(p, h), 127.0f));
             }
