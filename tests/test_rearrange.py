@@ -315,6 +315,50 @@ def test_rearrange_general_layouts_and_untouched_bytes(ggq, R):
 
 
 @pytest.mark.gpu
+def test_rearrange_fuzz_random_layouts(ggq, R):
+    """Random shapes (1-4 dims), units, padded / permuted destination layouts and arbitrary source layouts
+    (permuted, padded, reversed, broadcast) through the device API against the oracle's index arithmetic."""
+    import os
+    rng = np.random.default_rng(99)
+    n_cases = int(os.environ.get("GGQ_FUZZ_CASES", "300"))
+    for case in range(n_cases):
+        nd = int(rng.integers(1, 5))
+        shape = [int(rng.choice([1, 2, 3, 4, 5, 7, 8, 16, 33])) for _ in range(nd)]
+        unit = int(rng.choice([1, 2, 4, 6, 16, 18, 34]))
+
+        def layout(allow_special):
+            order = rng.permutation(nd)
+            strides, mul = [0] * nd, unit
+            for ax in order:
+                pad = int(rng.choice([0, 0, 0, 1, 3])) * unit
+                strides[ax] = mul
+                mul = mul * shape[ax] + pad
+            offset = int(rng.choice([0, 0, 1, 2, 5, 16]))
+            if allow_special:
+                for ax in range(nd):
+                    k = rng.random()
+                    if k < 0.15 and shape[ax] > 1:      # reversed axis
+                        offset += (shape[ax] - 1) * strides[ax]
+                        strides[ax] = -strides[ax]
+                    elif k < 0.25:                        # broadcast axis
+                        strides[ax] = 0
+            return (tuple(shape), tuple(strides), offset)
+        dl, sl = layout(False), layout(True)
+
+        def span(l):
+            hi = l[2] + sum((n - 1) * st for n, st in zip(l[0], l[1]) if st > 0) + unit
+            lo = l[2] + sum((n - 1) * st for n, st in zip(l[0], l[1]) if st < 0)
+            assert lo >= 0
+            return hi
+        src = rng.integers(0, 256, span(sl) + 3, dtype=np.uint8)
+        dst0 = rng.integers(0, 256, span(dl) + 3, dtype=np.uint8)
+        want = dst0.copy()
+        R.rearrange(want, dl, src, sl, unit)
+        got = dev_rearrange(ggq, as_product_layout(dl), as_product_layout(sl), unit, src, dst0)
+        assert np.array_equal(got, want), (case, dl, sl, unit)
+
+
+@pytest.mark.gpu
 def test_rearrange_launches_are_counted_and_async(ggq, R):
     import torch
     from gguf_b200._lib import lib
