@@ -23,25 +23,43 @@ namespace ggq {
 // thread CTAs: less per-tile overhead once ramp/tail no longer matter), smaller ones the SMALL config
 // (more, smaller tiles: better balance on 8-10 us launches).
 struct DqCfgDefault { static constexpr int TILE = 8192, STAGES = 3, THREADS = 256, MINB = 3; };
-template <uint32_t T> struct DqBig : DqCfgDefault {};
-template <uint32_t T> struct DqSmall : DqCfgDefault {};
 struct DqCfg32k2x512 { static constexpr int TILE = 32768, STAGES = 2, THREADS = 512, MINB = 1; };
 struct DqCfg16k3x512 { static constexpr int TILE = 16384, STAGES = 3, THREADS = 512, MINB = 1; };
 struct DqCfg16k2x512 { static constexpr int TILE = 16384, STAGES = 2, THREADS = 512, MINB = 1; };
 struct DqCfg16k3x256 { static constexpr int TILE = 16384, STAGES = 3, THREADS = 256, MINB = 3; };
 struct DqCfg8k2x256 { static constexpr int TILE = 8192, STAGES = 2, THREADS = 256, MINB = 3; };
-template <> struct DqBig<T_Q8_0> : DqCfg32k2x512 {};
-template <> struct DqBig<T_Q8_1> : DqCfg32k2x512 {};
-template <> struct DqBig<T_Q8K> : DqCfg32k2x512 {};
-template <> struct DqSmall<T_Q8_0> : DqCfg8k2x256 {};
-template <> struct DqSmall<T_Q8_1> : DqCfg8k2x256 {};
-template <> struct DqSmall<T_Q8K> : DqCfg8k2x256 {};
-template <> struct DqBig<T_Q4K> : DqCfg16k3x512 {};
-template <> struct DqBig<T_Q5K> : DqCfg32k2x512 {};
-template <> struct DqBig<T_Q3K> : DqCfg16k3x256 {};
-template <> struct DqBig<T_Q2K> : DqCfg16k2x512 {};
-template <> struct DqBig<T_Q6K> : DqCfg16k3x256 {};
-template <> struct DqSmall<T_Q6K> : DqCfg16k3x256 {};
+// 16-bit output (f16 / bf16) and the default for every float side
+template <uint32_t T, class FT> struct DqBig : DqCfgDefault {};
+template <uint32_t T, class FT> struct DqSmall : DqCfgDefault {};
+template <class FT> struct DqBig<T_Q8_0, FT> : DqCfg32k2x512 {};
+template <class FT> struct DqBig<T_Q8_1, FT> : DqCfg32k2x512 {};
+template <class FT> struct DqBig<T_Q8K, FT> : DqCfg32k2x512 {};
+template <class FT> struct DqSmall<T_Q8_0, FT> : DqCfg8k2x256 {};
+template <class FT> struct DqSmall<T_Q8_1, FT> : DqCfg8k2x256 {};
+template <class FT> struct DqSmall<T_Q8K, FT> : DqCfg8k2x256 {};
+template <class FT> struct DqBig<T_Q4K, FT> : DqCfg16k3x512 {};
+template <class FT> struct DqBig<T_Q5K, FT> : DqCfg32k2x512 {};
+template <class FT> struct DqBig<T_Q3K, FT> : DqCfg16k3x256 {};
+template <class FT> struct DqBig<T_Q2K, FT> : DqCfg16k2x512 {};
+template <class FT> struct DqBig<T_Q6K, FT> : DqCfg16k3x256 {};
+template <class FT> struct DqSmall<T_Q6K, FT> : DqCfg16k3x256 {};
+// f32 output writes twice the bytes per element: its own optimum (profiles/r01_dq_sweep_f32.txt, +2..15 %)
+template <> struct DqBig<T_Q4_0, F32> : DqCfg32k2x512 {};
+template <> struct DqBig<T_Q4_1, F32> : DqCfg32k2x512 {};
+template <> struct DqBig<T_Q5_0, F32> : DqCfg32k2x512 {};
+template <> struct DqBig<T_Q5_1, F32> : DqCfg32k2x512 {};
+template <> struct DqBig<T_Q2K, F32> : DqCfg32k2x512 {};
+template <> struct DqBig<T_Q3K, F32> : DqCfg32k2x512 {};
+template <> struct DqBig<T_Q4K, F32> : DqCfg32k2x512 {};
+template <> struct DqBig<T_Q5K, F32> : DqCfg16k2x512 {};
+template <> struct DqBig<T_Q6K, F32> : DqCfg16k2x512 {};
+template <> struct DqSmall<T_Q8_0, F32> : DqCfg32k2x512 {};
+template <> struct DqSmall<T_Q8_1, F32> : DqCfg32k2x512 {};
+template <> struct DqSmall<T_Q8K, F32> : DqCfg32k2x512 {};
+template <> struct DqSmall<T_Q3K, F32> : DqCfg16k3x512 {};
+template <> struct DqSmall<T_Q4K, F32> : DqCfg16k3x512 {};
+template <> struct DqSmall<T_Q5K, F32> : DqCfg16k3x512 {};
+template <> struct DqSmall<T_Q6K, F32> : DqCfg32k2x512 {};
 constexpr size_t DQ_BIG_ELEMS = size_t(32) << 20;
 constexpr int DQ_MODE = 0, DQ_SP = 0;
 
@@ -64,8 +82,8 @@ static cudaError_t launch_dequant_cfg(const void *src, void *dst, size_t nblocks
 
 template <uint32_t T, class FT>
 static cudaError_t launch_dequant(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
-    if (nblocks * (size_t)BlockTraits<T>::ELEMS >= DQ_BIG_ELEMS) return launch_dequant_cfg<T, FT, DqBig<T>>(src, dst, nblocks, stream, dev);
-    return launch_dequant_cfg<T, FT, DqSmall<T>>(src, dst, nblocks, stream, dev);
+    if (nblocks * (size_t)BlockTraits<T>::ELEMS >= DQ_BIG_ELEMS) return launch_dequant_cfg<T, FT, DqBig<T, FT>>(src, dst, nblocks, stream, dev);
+    return launch_dequant_cfg<T, FT, DqSmall<T, FT>>(src, dst, nblocks, stream, dev);
 }
 
 template <uint32_t T>

@@ -12,6 +12,10 @@
 
 using namespace ggq;
 
+#ifndef SWEEP_FT
+#define SWEEP_FT F16   // -DSWEEP_FT=F32 sweeps the f32-output instantiations
+#endif
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 static int g_sms = 148;
@@ -74,7 +78,7 @@ int main(int argc, char **argv) {
     CK(cudaSetDevice(dev));
     CK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t FFN = 4096ull * 14336, ATTN = 4096ull * 4096;
-    const size_t in_bytes = FFN * 290 / 256 + 4096, out_bytes = FFN * 2 + 4096;
+    const size_t in_bytes = FFN * 290 / 256 + 4096, out_bytes = FFN * SWEEP_FT::SIZE + 4096;
     uint8_t *in[NSETS];
     void *out[NSETS];
     for (int i = 0; i < NSETS; i++) {
@@ -104,7 +108,7 @@ int main(int argc, char **argv) {
         printf("expand (1 read : 4 write)             : %8.2f us  %7.1f GB/s\n", ms * 1e3 / iters, (double)ns * 16 * 5 * iters / (ms * 1e-3) / 1e9);
     }
 
-#define V(T, NAME, N, TILE, ST, THR, MINB, MODE, SP) run_variant<T, F16, TILE, ST, THR, MINB, MODE, SP>(NAME, N, in, out, iters)
+#define V(T, NAME, N, TILE, ST, THR, MINB, MODE, SP) run_variant<T, SWEEP_FT, TILE, ST, THR, MINB, MODE, SP>(NAME, N, in, out, iters)
 #define SWEEP(T, NAME, N)                      \
     V(T, NAME, N, 8192, 3, 256, 3, 0, 0);      \
     V(T, NAME, N, 8192, 2, 256, 3, 0, 0);      \
@@ -114,9 +118,11 @@ int main(int argc, char **argv) {
     V(T, NAME, N, 16384, 3, 512, 1, 0, 0);     \
     V(T, NAME, N, 8192, 2, 512, 1, 0, 0);      \
     V(T, NAME, N, 32768, 2, 512, 1, 0, 0);
-    for (int rep = 0; rep < 3; rep++)
+    for (int rep = 0; rep < 2; rep++)
         for (size_t n : {FFN, ATTN}) {
             SWEEP(T_Q8_0, "Q8_0", n)
+            SWEEP(T_Q4_0, "Q4_0", n)
+            SWEEP(T_Q6K, "Q6K", n)
             SWEEP(T_Q2K, "Q2K", n)
             SWEEP(T_Q3K, "Q3K", n)
             SWEEP(T_Q4K, "Q4K", n)
