@@ -638,6 +638,26 @@ template <> __device__ __forceinline__ uint16_t narrow_exact<BF16>(float f) { re
 // WIDER side exactly 16 bytes, so every warp access on either side is a contiguous run (no half-filled
 // sectors); U independent loads per thread are in flight before the first store.
 constexpr int CAST_THREADS = 256, CAST_TILE = 8192;
+// 16-bit <-> 16-bit casts, one word = two elements.  Without a NaN in the pair the crate's "widen, then narrow RNE"
+// is what the packed hardware conversions do; a pair holding a NaN takes the exact per-element route (payload
+// kept, quiet bit set).  `ok` is false when either half is a NaN.
+template <class ST, class DT> __device__ __forceinline__ uint32_t cast_pair16(uint32_t w, bool &ok);
+template <> __device__ __forceinline__ uint32_t cast_pair16<F16, BF16>(uint32_t w, bool &ok) {
+    const __half2 h = *reinterpret_cast<const __half2 *>(&w);
+    ok = __hbeq2(h, h);
+    const float2 f = __half22float2(h);
+    const __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
+    return *reinterpret_cast<const uint32_t *>(&b);
+}
+template <> __device__ __forceinline__ uint32_t cast_pair16<BF16, F16>(uint32_t w, bool &ok) {
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162 *>(&w);
+    ok = __hbeq2(b, b);
+    const __half2 h = __floats2half2_rn(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+template <class ST, class DT> struct IsPair16 { static constexpr bool value = false; };
+template <> struct IsPair16<F16, BF16> { static constexpr bool value = true; };
+template <> struct IsPair16<BF16, F16> { static constexpr bool value = true; };
 template <int BYTES> struct VecOf;
 template <> struct VecOf<16> { using type = uint4; };
 template <> struct VecOf<8> { using type = uint2; };
@@ -664,8 +684,22 @@ __global__ void __launch_bounds__(CAST_THREADS) cast_kernel(const typename ST::r
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 alignas(16) DR out[V];
+                if constexpr (IsPair16<ST, DT>::value) {
+                    bool all_ok = true;
 #pragma unroll
-                for (int k = 0; k < V; k++) out[k] = narrow_exact<DT>(widen_exact<ST>(in[u][k]));
+                    for (int k = 0; k < V / 2; k++) {
+                        bool ok;
+                        reinterpret_cast<uint32_t *>(out)[k] = cast_pair16<ST, DT>(reinterpret_cast<const uint32_t *>(in[u])[k], ok);
+                        all_ok &= ok;
+                    }
+                    if (!all_ok) {
+#pragma unroll
+                        for (int k = 0; k < V; k++) out[k] = narrow_exact<DT>(widen_exact<ST>(in[u][k]));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < V; k++) out[k] = narrow_exact<DT>(widen_exact<ST>(in[u][k]));
+                }
                 *reinterpret_cast<DV *>(dp + u * CAST_THREADS * V) = *reinterpret_cast<DV *>(out);
             }
         }
@@ -683,9 +717,12 @@ static cudaError_t launch_cast(const void *src, void *dst, size_t n, cudaStream_
     int ctas_per_sm = 0;
     cudaError_t e = cached_occupancy(kern, CAST_THREADS, 0, dev.device, occ_cache, &ctas_per_sm);
     if (e != cudaSuccess) return e;
+    // one tile per CTA (a persistent grid exposes the load latency of every tile; letting the hardware
+    // overlap many short CTAs is what the 1:1 copy of rearrange.cu does at 6.5-6.9 TB/s); the grid is
+    // capped only where it would overflow 2^31 - 1 blocks
     size_t want = (n + CAST_TILE - 1) / CAST_TILE;
-    size_t grid = (size_t)dev.sm_count * ctas_per_sm;
-    if (grid > want) grid = want ? want : 1;
+    size_t grid = want ? want : 1;
+    if (grid > 0x7FFFFFFFull) grid = (size_t)dev.sm_count * ctas_per_sm;
     return launch_pdl(kern, (unsigned)grid, CAST_THREADS, 0, stream, static_cast<const typename ST::raw *>(src), static_cast<typename DT::raw *>(dst), n);
 }
 template <class ST>
