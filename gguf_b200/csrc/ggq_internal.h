@@ -24,6 +24,9 @@ int cast_chain_io(const uint32_t *types, int n_types, size_t n_elems, const Chai
 // worker thread's context on its GPU — a stream, stream-ordered allocations, and the pinned bounce
 // buffers of a pooled pipeline for chunked upload / download.  Everything is enqueued on one stream
 // in call order; download() returns after the last byte has been handed to `write`.
+// memcpy with non-temporal stores (host_copy.cpp): for the bounce copies to / from pinned staging buffers.
+void stream_copy(void *dst, const void *src, size_t n);
+
 // Free device memory (bytes) on the calling thread's device, 0 when it cannot be queried.
 size_t device_free_bytes();
 
