@@ -16,6 +16,9 @@
 //     round-toward-zero add of 2^23 leaves floor(v) in the mantissa) instead of F2I on the XU pipe;
 //   * packed blocks are assembled in a shared-memory tile and leave the SM as ONE 1-D bulk async
 //     store per tile (`cp.async.bulk.global.shared::cta`, SASS UBLKCP), double buffered.
+#include <cstdlib>
+#include <type_traits>
+
 #include "ggq_common.cuh"
 #include "ggq_kernels.h"
 
@@ -576,11 +579,76 @@ quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, si
     if (tid == 0) bulk_wait_all<0>();
 }
 
+// One tile per CTA: stage ROWS rows, encode, write the packed blocks — no ring, no running pointers.  The
+// overlap of loads, math and stores comes from the hardware scheduling several resident CTAs per SM, the
+// structure that took the cast kernel from 85 % to 98 % of the copy peak; per row it also sheds the
+// bookkeeping of the persistent pipeline above.  launch_quant picks per (type, float side).
+template <uint32_t T, class FT, int ROWS>
+__global__ void __launch_bounds__(ROWS)
+quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t nblocks) {
+    using TR = BlockTraits<T>;
+    using E = Encoder<T>;
+    constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = ROWS / RPB;
+    constexpr int ROW_BYTES = 32 * FT::SIZE, ROW_STRIDE = ROW_BYTES + 16, CPR = ROW_BYTES / 16, ROWS_PER_PASS = ROWS / CPR;
+    constexpr int OUT_BYTES = TILE_BLOCKS * TR::BYTES;
+    static_assert(OUT_BYTES % 16 == 0, "tile must be a whole number of 16-byte chunks");
+    __shared__ __align__(128) uint8_t in_st[ROWS * ROW_STRIDE];
+    __shared__ __align__(16) uint8_t out_st[OUT_BYTES];
+    const int tid = threadIdx.x;
+    const size_t nrows = nblocks * RPB, ntiles = (nrows + ROWS - 1) / ROWS;
+    const bool vec_in = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    const uint32_t s_chunk0 = (uint32_t)(tid / CPR) * ROW_STRIDE + (uint32_t)(tid % CPR) * 16;
+    pdl_launch_dependents();
+    pdl_wait();
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {  // one iteration unless the grid was capped
+        const size_t rem = nrows - t * ROWS;
+        const int rows = (int)min((size_t)ROWS, rem);
+        const uint8_t *g = src + t * ((size_t)ROWS * ROW_BYTES);
+        if (vec_in) {
+#pragma unroll
+            for (int k = 0; k < CPR; k++)
+                if (rows == ROWS || tid / CPR + k * ROWS_PER_PASS < rows)
+                    cp_async16(in_st + s_chunk0 + k * ROWS_PER_PASS * ROW_STRIDE, g + (size_t)tid * 16 + (size_t)k * ROWS * 16);
+            cp_async_commit();
+            cp_async_wait<0>();
+        } else {  // source not 16-byte aligned: element-granular staging
+            using RAW = typename FT::raw;
+            const RAW *ge = reinterpret_cast<const RAW *>(g);
+            for (int e = tid; e < rows * 32; e += ROWS)
+                *reinterpret_cast<RAW *>(in_st + (e / 32) * ROW_STRIDE + (e % 32) * FT::SIZE) = ge[e];
+        }
+        __syncthreads();
+        if (RPB > 1 || tid < rows) {  // G > 1 encoders shuffle: every lane of the warp takes part
+            Row<FT> r;
+            if (tid < rows) r.load(in_st + tid * ROW_STRIDE);
+            else r.zero();
+            E::template run<FT>(r, tid % RPB, out_st + (uint32_t)(tid / RPB) * TR::BYTES);
+        }
+        __syncthreads();
+        cta_copy_s2g(dst + t * (size_t)OUT_BYTES, out_st, (uint32_t)(rows / RPB) * TR::BYTES, tid, ROWS);
+        __syncthreads();  // only matters when the loop runs again
+    }
+}
+
+template <uint32_t T, class FT, int ROWS>
+static cudaError_t launch_quant_oneshot(const void *src, void *dst, size_t nblocks, cudaStream_t stream) {
+    constexpr int RPB = BlockTraits<T>::ELEMS / 32, TILE_BLOCKS = ROWS / RPB;
+    size_t grid = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
+    if (grid > 0x7FFFFFFFull) grid = 0x7FFFFFFFull;
+    return launch_pdl(quant_rows_oneshot<T, FT, ROWS>, (unsigned)grid, ROWS, 0, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
+}
+
 template <uint32_t T, class FT>
 static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
     using TR = BlockTraits<T>;
     // measured (tools/codec_sweep.py): 2 input stages beat 3 (more CTAs per SM hide the per-tile barrier);
     // 128-row tiles are best for Q8_0 / Q8_1, 64-row tiles for the 4/5-bit types and Q8K
+    // measured (tools/codec_sweep.py, 58.7 M elements): with f32 input the one-tile-per-CTA kernel runs at 99-101 % of the
+    // copy peak (persistent ring: 89-92 %), and it wins for Q8_0 / Q8_1 from 16-bit input too (84-85 % vs 82 %); the
+    // 4/5-bit encoders from 16-bit input are bound by their instruction count either way (the ring is 1-3 points
+    // better there) and Q8K's eight-lane groups prefer the ring's 64-row tiles.
+    constexpr bool ONESHOT = (T != T_Q8K) && (std::is_same<FT, F32>::value || T == T_Q8_0 || T == T_Q8_1);
+    if constexpr (ONESHOT) return launch_quant_oneshot<T, FT, 128>(src, dst, nblocks, stream);
     constexpr int QS = 2;
     constexpr int QL_THREADS = (T == T_Q8_0 || T == T_Q8_1) ? 128 : 64;
     constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = QL_THREADS / RPB;
