@@ -232,8 +232,8 @@ __device__ __forceinline__ uint32_t floor_bits(float v) { return __float_as_uint
 // ---- packed FP32 (Blackwell FADD2 / FMUL2, `*.f32x2`): the kernel is issue-bound, and a packed instruction
 // does the IEEE operation on the pair (x[2k], x[2k+1]) in one issue slot.  One rule: a packed multiply must
 // never feed a packed add — ptxas 12.9 contracts that pair into a single-rounding FFMA2 even with
-// --fmad=false (see quant_k.cu; the Makefile rejects objects containing FFMA2) — so the `+ 8.5` / `+ 0.5`
-// after `x * recip` stays two scalar __fadd_rn.
+// --fmad=false (see quant_k.cu; the Makefile rejects objects containing FFMA2).  The encoders therefore clamp
+// between `x * recip` and the `+ 8.5` / `+ 0.5` (bounds shifted by the constant: identical results).
 __device__ __forceinline__ float2 pair_of(const float *x, int k) { return make_float2(x[2 * k], x[2 * k + 1]); }
 __device__ __forceinline__ float2 mul2(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
 __device__ __forceinline__ float2 add2(float2 a, float c) { return __fadd2_rn(a, make_float2(c, c)); }
@@ -301,9 +301,11 @@ template <> struct Encoder<T_Q4_0> {
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 // (x*recip + 8.5).min(15.) as u8 : NaN -> 15 (fminf drops it), negatives -> 0
-                float2 v = add_after_mul(mul2(pair_of(r.x, k), rc), 8.5f);
-                v = make_float2(fmaxf(fminf(v.x, 15.0f), 0.0f), fmaxf(fminf(v.y, 15.0f), 0.0f));
-                floor_bits2(v, c[2 * k], c[2 * k + 1]);
+                // the clamp moves in front of the add (bounds shifted by 8.5, same results incl. NaN -> 15), so the
+                // add no longer follows the packed multiply directly and can be packed as well
+                const float2 p = mul2(pair_of(r.x, k), rc);
+                const float2 q = make_float2(fmaxf(fminf(p.x, 6.5f), -8.5f), fmaxf(fminf(p.y, 6.5f), -8.5f));
+                floor_bits2(add2(q, 8.5f), c[2 * k], c[2 * k + 1]);
             }
             nibble_bytes(c, w);
         }
@@ -328,8 +330,8 @@ template <> struct Encoder<T_Q4_1> {
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 // (((x - min)*recip + 0.5) as u8).min(15) : NaN -> 0
-                const float2 v = add_after_mul(mul2(add2(pair_of(r.x, k), -mn), rc), 0.5f);
-                floor_bits2(clamp2(v, 0.0f, 15.0f), c[2 * k], c[2 * k + 1]);
+                const float2 p = mul2(add2(pair_of(r.x, k), -mn), rc);
+                floor_bits2(add2(clamp2(p, -0.5f, 14.5f), 0.5f), c[2 * k], c[2 * k + 1]);  // clamp before the add, see Q4_0
             }
             nibble_bytes(c, w);
         }
@@ -370,8 +372,8 @@ template <> struct Encoder<T_Q5_0> {
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 // ((x*recip + 16.5) as u8).min(31) : NaN -> 0
-                const float2 v = add_after_mul(mul2(pair_of(r.x, k), rc), 16.5f);
-                floor_bits2(clamp2(v, 0.0f, 31.0f), c[2 * k], c[2 * k + 1]);
+                const float2 p = mul2(pair_of(r.x, k), rc);
+                floor_bits2(add2(clamp2(p, -16.5f, 14.5f), 16.5f), c[2 * k], c[2 * k + 1]);  // clamp before the add, see Q4_0
             }
             pack5(c, qh, w);
         }
@@ -397,8 +399,8 @@ template <> struct Encoder<T_Q5_1> {
             uint32_t c[32];
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                const float2 v = add_after_mul(mul2(add2(pair_of(r.x, k), -mn), rc), 0.5f);
-                floor_bits2(clamp2(v, 0.0f, 31.0f), c[2 * k], c[2 * k + 1]);
+                const float2 p = mul2(add2(pair_of(r.x, k), -mn), rc);
+                floor_bits2(add2(clamp2(p, -0.5f, 30.5f), 0.5f), c[2 * k], c[2 * k + 1]);  // clamp before the add, see Q4_0
             }
             pack5(c, qh, w);
         }
