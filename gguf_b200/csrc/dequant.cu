@@ -5,10 +5,11 @@
 // dequant_kernel.cuh).
 //
 // Shape of the kernel (HBM-bound streaming codec, no tensor cores):
-//   * persistent CTAs, static round-robin over tiles of TILE_ELEMS elements (size-adaptive, see below);
+//   * tiles of TILE_ELEMS elements; big tensors run one tile per short-lived CTA, small ones persistent CTAs
+//     with a ring of stages (size-adaptive, see the configuration table below);
 //   * the packed bytes of a tile are one contiguous range -> one 1-D bulk async copy (TMA engine,
-//     `cp.async.bulk`, SASS UBLKCP) per tile into a STAGES-deep shared-memory ring guarded by
-//     mbarriers, issued STAGES tiles ahead by one thread — no LSU instructions or registers spent on loads;
+//     `cp.async.bulk`, SASS UBLKCP) per tile into shared memory, completion on an mbarrier, issued by one
+//     thread — no LSU instructions or registers spent on loads;
 //   * every thread decodes "units" out of shared memory and writes 16-byte vectors, so each warp
 //     store covers full 32-byte sectors of the output (which is 64-88 % of all traffic).
 // Every multiply in every decoder is exact in f32, so `fma(q, d, m)` equals the
@@ -18,63 +19,56 @@
 
 namespace ggq {
 
-// Shipped configurations, chosen with tools/dq_sweep.cu (profiles/r01_dq_sweep_pdl*.txt; repeatable to
-// +-0.3 %).  Tensors of >= DQ_BIG_ELEMS elements take the BIG config (bigger tiles, fewer stages, 512-
-// thread CTAs: less per-tile overhead once ramp/tail no longer matter), smaller ones the SMALL config
-// (more, smaller tiles: better balance on 8-10 us launches).
-struct DqCfgDefault { static constexpr int TILE = 8192, STAGES = 3, THREADS = 256, MINB = 3; };
-struct DqCfg32k2x512 { static constexpr int TILE = 32768, STAGES = 2, THREADS = 512, MINB = 1; };
-struct DqCfg16k3x512 { static constexpr int TILE = 16384, STAGES = 3, THREADS = 512, MINB = 1; };
-struct DqCfg16k2x512 { static constexpr int TILE = 16384, STAGES = 2, THREADS = 512, MINB = 1; };
-struct DqCfg16k3x256 { static constexpr int TILE = 16384, STAGES = 3, THREADS = 256, MINB = 3; };
-struct DqCfg8k2x256 { static constexpr int TILE = 8192, STAGES = 2, THREADS = 256, MINB = 3; };
-// 16-bit output (f16 / bf16) and the default for every float side
-template <uint32_t T, class FT> struct DqBig : DqCfgDefault {};
-template <uint32_t T, class FT> struct DqSmall : DqCfgDefault {};
-template <class FT> struct DqBig<T_Q8_0, FT> : DqCfg32k2x512 {};
-template <class FT> struct DqBig<T_Q8_1, FT> : DqCfg32k2x512 {};
-template <class FT> struct DqBig<T_Q8K, FT> : DqCfg32k2x512 {};
-template <class FT> struct DqSmall<T_Q8_0, FT> : DqCfg8k2x256 {};
-template <class FT> struct DqSmall<T_Q8_1, FT> : DqCfg8k2x256 {};
-template <class FT> struct DqSmall<T_Q8K, FT> : DqCfg8k2x256 {};
-template <class FT> struct DqBig<T_Q4K, FT> : DqCfg16k3x512 {};
-template <class FT> struct DqBig<T_Q5K, FT> : DqCfg32k2x512 {};
-template <class FT> struct DqBig<T_Q3K, FT> : DqCfg16k3x256 {};
-template <class FT> struct DqBig<T_Q2K, FT> : DqCfg16k2x512 {};
-template <class FT> struct DqBig<T_Q6K, FT> : DqCfg16k3x256 {};
-template <class FT> struct DqSmall<T_Q6K, FT> : DqCfg16k3x256 {};
-// f32 output writes twice the bytes per element: its own optimum (profiles/r01_dq_sweep_f32.txt, +2..15 %)
-template <> struct DqBig<T_Q4_0, F32> : DqCfg32k2x512 {};
-template <> struct DqBig<T_Q4_1, F32> : DqCfg32k2x512 {};
-template <> struct DqBig<T_Q5_0, F32> : DqCfg32k2x512 {};
-template <> struct DqBig<T_Q5_1, F32> : DqCfg32k2x512 {};
-template <> struct DqBig<T_Q2K, F32> : DqCfg32k2x512 {};
-template <> struct DqBig<T_Q3K, F32> : DqCfg32k2x512 {};
-template <> struct DqBig<T_Q4K, F32> : DqCfg32k2x512 {};
-template <> struct DqBig<T_Q5K, F32> : DqCfg16k2x512 {};
-template <> struct DqBig<T_Q6K, F32> : DqCfg16k2x512 {};
-template <> struct DqSmall<T_Q8_0, F32> : DqCfg32k2x512 {};
-template <> struct DqSmall<T_Q8_1, F32> : DqCfg32k2x512 {};
-template <> struct DqSmall<T_Q8K, F32> : DqCfg32k2x512 {};
-template <> struct DqSmall<T_Q3K, F32> : DqCfg16k3x512 {};
-template <> struct DqSmall<T_Q4K, F32> : DqCfg16k3x512 {};
-template <> struct DqSmall<T_Q5K, F32> : DqCfg16k3x512 {};
-template <> struct DqSmall<T_Q6K, F32> : DqCfg32k2x512 {};
-constexpr size_t DQ_BIG_ELEMS = size_t(32) << 20;
-constexpr int DQ_MODE = 0, DQ_SP = 0;
+// Shipped configurations, chosen with tools/dq_sweep.cu (profiles/r01_dq_sweep_modes*.txt; repeatable to
+// +-0.5 %).  Two kernel shapes (dequant_kernel.cuh):
+//   ONE  (MODE 1)  one tile per CTA, 128-thread CTAs, the register cap forced down (MINB) so that 8-12 CTAs are
+//                  resident per SM: while one CTA waits for its bulk copy its neighbours decode and store, and the
+//                  hardware block scheduler keeps the window of addresses in flight contiguous.  A persistent
+//                  grid-stride fill tops out at 5.3-5.6 TB/s on this GPU, the same fill as one 16 KB tile per CTA
+//                  reaches 6.3 TB/s; the decoders follow: 6.3-6.6 TB/s (96-101 % of the measured copy peak) on
+//                  58.7 M elements against 5.7-5.9 TB/s for the ring.  Needs a few waves of CTAs to overlap.
+//   RING (MODE 0)  persistent CTAs with a STAGES-deep bulk-copy ring: still the better shape for small tensors
+//                  (less than ~2 waves of tiles), where ONE's CTAs would all load and then all store in step.
+template <int TILE_, int STAGES_, int THREADS_, int MINB_, int MODE_> struct DqCfg {
+    static constexpr int TILE = TILE_, STAGES = STAGES_, THREADS = THREADS_, MINB = MINB_, MODE = MODE_;
+};
+using Ring8k3 = DqCfg<8192, 3, 256, 3, 0>;
+using Ring8k2 = DqCfg<8192, 2, 256, 3, 0>;
+using Ring16k3 = DqCfg<16384, 3, 256, 3, 0>;
+using One16k8 = DqCfg<16384, 1, 128, 8, 1>;
+using One16k9 = DqCfg<16384, 1, 128, 9, 1>;
+using One16k10 = DqCfg<16384, 1, 128, 10, 1>;
+using One16k12 = DqCfg<16384, 1, 128, 12, 1>;
+using One8k8 = DqCfg<8192, 1, 128, 8, 1>;
+using One4k10 = DqCfg<4096, 1, 128, 10, 1>;
+
+constexpr size_t Mi = size_t(1) << 20;
+template <uint32_t T> constexpr bool is_q8_family() { return T == T_Q8_0 || T == T_Q8_1 || T == T_Q8K; }
+template <uint32_t T> constexpr bool is_k2345() { return T == T_Q2K || T == T_Q3K || T == T_Q4K || T == T_Q5K; }
+
+// 16-bit output, big tensors
+template <uint32_t T> struct DqOneBig { using type = One16k8; };
+template <> struct DqOneBig<T_Q2K> { using type = One16k12; };
+template <> struct DqOneBig<T_Q3K> { using type = One16k9; };
+template <> struct DqOneBig<T_Q4K> { using type = One16k10; };
+template <> struct DqOneBig<T_Q5K> { using type = One16k9; };
+// small tensors that stay on the ring
+template <uint32_t T> struct DqRingSmall { using type = Ring8k3; };
+template <> struct DqRingSmall<T_Q6K> { using type = Ring16k3; };
 
 template <uint32_t T, class FT, class CFG>
 static cudaError_t launch_dequant_cfg(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
     using TR = BlockTraits<T>;
     constexpr int TILE_BLOCKS = CFG::TILE / TR::ELEMS;
-    constexpr int SMEM = dequant_smem_bytes<T, CFG::TILE, CFG::STAGES, DQ_MODE>();
-    auto kern = dequant_kernel<T, FT, CFG::TILE, CFG::STAGES, CFG::THREADS, CFG::MINB, DQ_MODE, DQ_SP>;
+    constexpr int SMEM = dequant_smem_bytes<T, CFG::TILE, CFG::STAGES, CFG::MODE>();
+    auto kern = dequant_kernel<T, FT, CFG::TILE, CFG::STAGES, CFG::THREADS, CFG::MINB, CFG::MODE, 0>;
     static std::atomic<int> occ_cache[MAX_DEVICES];  // per instantiation, per device
     int ctas_per_sm = 0;
     cudaError_t e = cached_occupancy(kern, CFG::THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
     if (e != cudaSuccess) return e;
     const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
-    size_t grid = (size_t)dev.sm_count * ctas_per_sm;
+    // RING: one persistent CTA per slot.  ONE: one CTA per tile (capped only where the grid would overflow)
+    size_t grid = CFG::MODE == 0 ? (size_t)dev.sm_count * ctas_per_sm : (size_t)0x7FFFFFFF;
     if (grid > ntiles) grid = ntiles;
     return launch_pdl(kern, (unsigned)grid, CFG::THREADS, SMEM, stream, static_cast<const uint8_t *>(src),
                       static_cast<typename FT::raw *>(dst), nblocks);
@@ -82,8 +76,20 @@ static cudaError_t launch_dequant_cfg(const void *src, void *dst, size_t nblocks
 
 template <uint32_t T, class FT>
 static cudaError_t launch_dequant(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
-    if (nblocks * (size_t)BlockTraits<T>::ELEMS >= DQ_BIG_ELEMS) return launch_dequant_cfg<T, FT, DqBig<T, FT>>(src, dst, nblocks, stream, dev);
-    return launch_dequant_cfg<T, FT, DqSmall<T, FT>>(src, dst, nblocks, stream, dev);
+    const size_t n = nblocks * (size_t)BlockTraits<T>::ELEMS;
+    if constexpr (FT::SIZE == 4) {  // f32 output: twice the bytes per element, ONE wins from ~6 Mi elements up
+        if (n >= 12 * Mi) return launch_dequant_cfg<T, FT, One8k8>(src, dst, nblocks, stream, dev);
+        if (n >= 6 * Mi || is_q8_family<T>()) return launch_dequant_cfg<T, FT, One4k10>(src, dst, nblocks, stream, dev);
+        return launch_dequant_cfg<T, FT, Ring8k3>(src, dst, nblocks, stream, dev);
+    } else {
+        if (n >= (is_k2345<T>() ? 32 : 24) * Mi) return launch_dequant_cfg<T, FT, typename DqOneBig<T>::type>(src, dst, nblocks, stream, dev);
+        if constexpr (is_q8_family<T>()) {
+            if (n >= 6 * Mi) return launch_dequant_cfg<T, FT, One8k8>(src, dst, nblocks, stream, dev);
+            return launch_dequant_cfg<T, FT, One4k10>(src, dst, nblocks, stream, dev);
+        } else {
+            return launch_dequant_cfg<T, FT, typename DqRingSmall<T>::type>(src, dst, nblocks, stream, dev);
+        }
+    }
 }
 
 template <uint32_t T>

@@ -333,7 +333,9 @@ template <> struct Decoder<T_Q3K> {
 };
 
 // MODE 0: persistent CTAs, static round-robin over tiles, STAGES-deep bulk-copy (TMA) ring.
-// MODE 1: one tile per CTA (grid = ntiles): the hardware block scheduler balances the tail.
+// MODE 1: one tile per CTA (grid = ntiles), the tile arrives by one bulk copy: the hardware block scheduler
+//         overlaps the load of one CTA with the stores of its neighbours and balances the tail.
+// MODE 2: one tile per CTA, staged by cooperative 16-byte loads (no mbarrier, no async proxy).
 template <uint32_t T, class FT, int TILE_ELEMS, int STAGES, int THREADS, int MINB, int MODE, int SP>
 __global__ void __launch_bounds__(THREADS, MINB)
 dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ dst, size_t nblocks) {
@@ -355,18 +357,20 @@ dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ d
     const bool src_fast = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
     const bool vec = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
 
-    if (tid == 0) {
+    if constexpr (MODE != 2) {
+        if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
-        fence_barrier_init();
+            for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
+            fence_barrier_init();
+        }
     }
     pdl_launch_dependents();  // the next kernel may begin scheduling as our CTAs retire
-    __syncthreads();
+    if constexpr (MODE != 2) __syncthreads();
     pdl_wait();               // the previous kernel in the stream is complete before any global access
 
     auto issue = [&](size_t i) {  // thread 0 only
         const size_t t = blockIdx.x + i * (size_t)gridDim.x;
-        if (t < full_tiles && src_fast) {
+        if (MODE != 2 && t < full_tiles && src_fast) {
             const int s = (int)(i % NST);
             mbar_expect_tx(&bars[s], TILE_BYTES);
             bulk_g2s(stages + (size_t)s * TILE_BYTES, src + t * (size_t)TILE_BYTES, TILE_BYTES, &bars[s]);
@@ -381,7 +385,7 @@ dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ d
     for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
         const int s = (int)(i % NST);
         uint8_t *stage = stages + (size_t)s * TILE_BYTES;
-        const bool bulk = (t < full_tiles) && src_fast;
+        const bool bulk = MODE != 2 && (t < full_tiles) && src_fast;
         const int nb = (t < full_tiles) ? TILE_BLOCKS : rem_blocks;
         if (bulk) {
             mbar_wait(&bars[s], (uint32_t)((i / NST) & 1));
@@ -401,6 +405,11 @@ dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ d
         if constexpr (MODE == 0) {
             __syncthreads();  // stage s fully consumed
             if (tid == 0) issue(i + NST);
+        } else {
+            if (t + gridDim.x < ntiles) {  // only when the grid was capped below ntiles
+                __syncthreads();
+                if (MODE == 1 && tid == 0) issue(i + 1);
+            }
         }
     }
 }

@@ -321,6 +321,46 @@ def test_every_kernel_ragged_with_guard_zones(ggq, oracle, ty, fdt):
         assert (gd[:G + off] == 0x5A).all() and (gd[G + off + x.nbytes:] == 0x5A).all(), "dequantize wrote outside dst"
 
 
+
+def _big_dequant_sizes(ty, fdt):
+    """Element counts that select each one-tile-per-CTA decoder shape of dequant.cu (+ a ragged tail)."""
+    mi = 1 << 20
+    if fdt == F32:
+        return [12 * mi, 6 * mi]                    # One8k8, One4k10
+    sizes = [(32 if ty in (10, 11, 12, 13) else 24) * mi]   # DqOneBig<T>
+    if ty in (8, 9, 15):
+        sizes.append(6 * mi)                        # One8k8 for the Q8 family
+    return sizes
+
+
+@pytest.mark.parametrize("fdt", FDTS)
+@pytest.mark.parametrize("ty", ALLQ)
+def test_big_tensor_decoder_shapes_bit_exact(ggq, oracle, ty, fdt):
+    """Tensors above the size thresholds take the one-tile-per-CTA kernels (dequant.cu); every type and float
+    side is checked against the oracle at those sizes, ragged (the last tile is partial, the block count is
+    not a multiple of 8), at aligned and at 2-byte-offset device pointers, with guard zones."""
+    import torch
+    n, b = oracle.block_info(ty)
+    st = torch.cuda.current_stream().cuda_stream
+    G = 64
+    esz = 4 if fdt == F32 else 2
+    for k, n_elems in enumerate(_big_dequant_sizes(ty, fdt)):
+        nb = n_elems // n + (5 if n == 32 else 3)
+        blocks = random_packed(ty, nb, b, 900 + ty + 31 * k)
+        want = oracle.dequantize(ty, fdt, blocks, threads=16)
+        for off in ((0, 2) if k == 0 else (0,)):
+            src = torch.zeros(blocks.nbytes + 2 * G, dtype=torch.uint8, device="cuda")
+            src[G + off:G + off + blocks.nbytes] = torch.from_numpy(blocks).cuda()
+            d = torch.full((nb * n * esz + 2 * G,), 0x5A, dtype=torch.uint8, device="cuda")
+            doff = off * (2 if fdt == F32 else 1)  # keep the float side element-aligned
+            ggq.dequantize_slice_device(ty, fdt, d.data_ptr() + G + doff, nb * n, src.data_ptr() + G + off, nb, st)
+            torch.cuda.synchronize()
+            gd = d.cpu().numpy()
+            assert same_floats(gd[G + doff:G + doff + nb * n * esz].view(want.dtype), want)
+            assert (gd[:G + doff] == 0x5A).all() and (gd[G + doff + nb * n * esz:] == 0x5A).all(), "dequantize wrote outside dst"
+            del src, d
+
+
 def test_host_api_rejects_device_pointers(ggq):
     import ctypes, torch
     from gguf_b200._lib import lib

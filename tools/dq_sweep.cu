@@ -40,6 +40,29 @@ template <int RATIO> __global__ void expand_kernel(uint4 *dst, const uint4 *src,
     }
 }
 
+// one-tile-per-CTA forms of the calibration kernels (grid = n16 / (256 * U)): what the hardware block scheduler
+// reaches when every CTA is short-lived
+template <int U> __global__ void fill1_kernel(uint4 *dst) {
+    uint4 *p = dst + (size_t)blockIdx.x * 256 * U + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < U; u++) p[u * 256] = make_uint4(1, 2, 3, 4);
+}
+template <int U> __global__ void copy1_kernel(uint4 *dst, const uint4 *src) {
+    const size_t o = (size_t)blockIdx.x * 256 * U + threadIdx.x;
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) v[u] = __ldg(src + o + u * 256);
+#pragma unroll
+    for (int u = 0; u < U; u++) dst[o + u * 256] = v[u];
+}
+// 1 read : 4 write, one CTA = 256 source vectors -> 1024 destination vectors
+__global__ void expand1_kernel(uint4 *dst, const uint4 *src) {
+    const uint4 v = __ldg(src + (size_t)blockIdx.x * 256 + threadIdx.x);
+    uint4 *p = dst + (size_t)blockIdx.x * 1024 + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < 4; r++) p[r * 256] = v;
+}
+
 struct Timer {
     cudaEvent_t a, b;
     Timer() { cudaEventCreate(&a); cudaEventCreate(&b); }
@@ -87,6 +110,9 @@ int main(int argc, char **argv) {
         CK(cudaMemset(in[i], 0x11 * (i + 1), in_bytes));  // finite f16 scales (0x1111..), arbitrary codes
     }
     const int iters = argc > 1 ? atoi(argv[1]) : 60;
+    std::vector<size_t> sizes;  // element counts (<= FFN) from the command line, default FFN and ATTN
+    for (int a = 2; a < argc; a++) sizes.push_back((size_t)atoll(argv[a]));
+    if (sizes.empty()) sizes = {FFN, ATTN};
     Timer t;
 
     // ---- calibration: what can pure streams reach ----
@@ -106,9 +132,22 @@ int main(int argc, char **argv) {
         for (int i = 0; i < iters; i++) expand_kernel<4><<<grid, 256>>>((uint4 *)out[i % NSETS], (const uint4 *)in[i % NSETS], ns);
         ms = t.stop();
         printf("expand (1 read : 4 write)             : %8.2f us  %7.1f GB/s\n", ms * 1e3 / iters, (double)ns * 16 * 5 * iters / (ms * 1e-3) / 1e9);
+        t.start();
+        for (int i = 0; i < iters; i++) fill1_kernel<4><<<(unsigned)(n16 / 1024), 256>>>((uint4 *)out[i % NSETS]);
+        ms = t.stop();
+        printf("fill1  (one 16 KB tile per CTA)       : %8.2f us  %7.1f GB/s\n", ms * 1e3 / iters, (double)n16 * 16 * iters / (ms * 1e-3) / 1e9);
+        t.start();
+        for (int i = 0; i < iters; i++) copy1_kernel<4><<<(unsigned)(n16 / 1024), 256>>>((uint4 *)out[i % NSETS], (const uint4 *)out[(i + 3) % NSETS]);
+        ms = t.stop();
+        printf("copy1  (one 16 KB tile per CTA)       : %8.2f us  %7.1f GB/s\n", ms * 1e3 / iters, (double)n16 * 32 * iters / (ms * 1e-3) / 1e9);
+        t.start();
+        for (int i = 0; i < iters; i++) expand1_kernel<<<(unsigned)(ns / 256), 256>>>((uint4 *)out[i % NSETS], (const uint4 *)in[i % NSETS]);
+        ms = t.stop();
+        printf("expand1 (1:4, 4 KB in per CTA)        : %8.2f us  %7.1f GB/s\n", ms * 1e3 / iters, (double)ns * 16 * 5 * iters / (ms * 1e-3) / 1e9);
     }
 
 #define V(T, NAME, N, TILE, ST, THR, MINB, MODE, SP) run_variant<T, SWEEP_FT, TILE, ST, THR, MINB, MODE, SP>(NAME, N, in, out, iters)
+#if !defined(SWEEP_SET) || SWEEP_SET == 1
 #define SWEEP(T, NAME, N)                      \
     V(T, NAME, N, 8192, 3, 256, 3, 0, 0);      \
     V(T, NAME, N, 8192, 2, 256, 3, 0, 0);      \
@@ -116,10 +155,69 @@ int main(int argc, char **argv) {
     V(T, NAME, N, 16384, 2, 256, 3, 0, 0);     \
     V(T, NAME, N, 16384, 2, 512, 1, 0, 0);     \
     V(T, NAME, N, 16384, 3, 512, 1, 0, 0);     \
-    V(T, NAME, N, 8192, 2, 512, 1, 0, 0);      \
-    V(T, NAME, N, 32768, 2, 512, 1, 0, 0);
+    V(T, NAME, N, 32768, 2, 512, 1, 0, 0);     \
+    V(T, NAME, N, 4096, 1, 256, 3, 1, 0);      \
+    V(T, NAME, N, 8192, 1, 256, 3, 1, 0);      \
+    V(T, NAME, N, 16384, 1, 256, 3, 1, 0);     \
+    V(T, NAME, N, 8192, 1, 512, 1, 1, 0);      \
+    V(T, NAME, N, 16384, 1, 512, 1, 1, 0);     \
+    V(T, NAME, N, 4096, 1, 128, 6, 1, 0);      \
+    V(T, NAME, N, 4096, 1, 256, 3, 2, 0);      \
+    V(T, NAME, N, 8192, 1, 256, 3, 2, 0);      \
+    V(T, NAME, N, 16384, 1, 256, 3, 2, 0);     \
+    V(T, NAME, N, 8192, 1, 512, 1, 2, 0);      \
+    V(T, NAME, N, 16384, 1, 512, 1, 2, 0);     \
+    V(T, NAME, N, 4096, 1, 128, 6, 2, 0);
+#else
+// one tile per CTA (MODE 1) needs many resident CTAs: force the register cap down with MINB
+#if SWEEP_SET == 2 || SWEEP_SET == 4
+#define SWEEP_A(T, NAME, N)                    \
+    V(T, NAME, N, 16384, 1, 256, 4, 1, 0);     \
+    V(T, NAME, N, 16384, 1, 256, 5, 1, 0);     \
+    V(T, NAME, N, 16384, 1, 256, 6, 1, 0);     \
+    V(T, NAME, N, 8192, 1, 128, 8, 1, 0);      \
+    V(T, NAME, N, 8192, 1, 128, 10, 1, 0);     \
+    V(T, NAME, N, 8192, 1, 128, 12, 1, 0);     \
+    V(T, NAME, N, 4096, 1, 128, 10, 1, 0);     \
+    V(T, NAME, N, 16384, 1, 128, 8, 1, 0);     \
+    V(T, NAME, N, 16384, 1, 128, 10, 1, 0);    \
+    V(T, NAME, N, 32768, 1, 256, 4, 1, 0);     \
+    V(T, NAME, N, 32768, 1, 256, 6, 1, 0);
+#else
+#define SWEEP_A(T, NAME, N)
+#endif
+#if SWEEP_SET == 5
+#define SWEEP_B(T, NAME, N)                    \
+    V(T, NAME, N, 8192, 3, 256, 3, 0, 0);      \
+    V(T, NAME, N, 8192, 2, 256, 3, 0, 0);      \
+    V(T, NAME, N, 16384, 3, 256, 3, 0, 0);     \
+    V(T, NAME, N, 16384, 3, 512, 1, 0, 0);     \
+    V(T, NAME, N, 32768, 2, 512, 1, 0, 0);     \
+    V(T, NAME, N, 8192, 1, 128, 8, 1, 0);      \
+    V(T, NAME, N, 16384, 1, 128, 8, 1, 0);     \
+    V(T, NAME, N, 4096, 1, 128, 10, 1, 0);     \
+    V(T, NAME, N, 8192, 1, 64, 16, 1, 0);
+#elif SWEEP_SET == 3 || SWEEP_SET == 4
+#define SWEEP_B(T, NAME, N)                    \
+    V(T, NAME, N, 32768, 1, 128, 8, 1, 0);     \
+    V(T, NAME, N, 32768, 1, 128, 10, 1, 0);    \
+    V(T, NAME, N, 16384, 1, 128, 12, 1, 0);    \
+    V(T, NAME, N, 16384, 1, 128, 9, 1, 0);     \
+    V(T, NAME, N, 16384, 1, 64, 16, 1, 0);     \
+    V(T, NAME, N, 16384, 1, 64, 20, 1, 0);     \
+    V(T, NAME, N, 8192, 1, 64, 16, 1, 0);      \
+    V(T, NAME, N, 8192, 1, 64, 20, 1, 0);      \
+    V(T, NAME, N, 8192, 1, 64, 24, 1, 0);      \
+    V(T, NAME, N, 8192, 1, 128, 8, 1, 0);      \
+    V(T, NAME, N, 16384, 1, 128, 8, 1, 0);     \
+    V(T, NAME, N, 16384, 1, 128, 10, 1, 0);
+#else
+#define SWEEP_B(T, NAME, N)
+#endif
+#define SWEEP(T, NAME, N) SWEEP_A(T, NAME, N) SWEEP_B(T, NAME, N)
+#endif
     for (int rep = 0; rep < 2; rep++)
-        for (size_t n : {FFN, ATTN}) {
+        for (size_t n : sizes) {
             SWEEP(T_Q8_0, "Q8_0", n)
             SWEEP(T_Q4_0, "Q4_0", n)
             SWEEP(T_Q6K, "Q6K", n)
@@ -127,6 +225,13 @@ int main(int argc, char **argv) {
             SWEEP(T_Q3K, "Q3K", n)
             SWEEP(T_Q4K, "Q4K", n)
             SWEEP(T_Q5K, "Q5K", n)
+#if defined(SWEEP_SET) && SWEEP_SET >= 2
+            SWEEP(T_Q4_1, "Q4_1", n)
+            SWEEP(T_Q5_0, "Q5_0", n)
+            SWEEP(T_Q5_1, "Q5_1", n)
+            SWEEP(T_Q8_1, "Q8_1", n)
+            SWEEP(T_Q8K, "Q8K", n)
+#endif
         }
     return 0;
 }
