@@ -87,10 +87,13 @@ __device__ __forceinline__ float2 abs2(float2 v) { return make_float2(fabsf(v.x)
 __device__ __forceinline__ float2 affine2_two_roundings(float2 l, float ns, float nm) {
     return make_float2(__fadd_rn(__fmul_rn(l.x, ns), nm), __fadd_rn(__fmul_rn(l.y, ns), nm));
 }
-// rint(clamp(v)) for both lanes, see round_clamped()
+// rint(clamp(v)) for both lanes.  cvt.rni.f32.f32 (FRND, XU pipe) gives the same round-to-nearest-even integer
+// as round_clamped()'s magic-number add but leaves the FP32 pipe, which bounds the search, two operations per
+// element lighter (-3..-4.5 % kernel time).  rint(-0.x) is -0 where the add gives +0: a zero code contributes
+// +-0 to every sum and product either way, so no compared value changes.
 __device__ __forceinline__ float2 round_clamped2(float2 v, float lo, float hi) {
-    const float2 rb = __fadd2_rn(clamp2(v, lo, hi), bcast2(RMAGIC));
-    return __fadd2_rn(rb, bcast2(-RMAGIC));
+    const float2 c = clamp2(v, lo, hi);
+    return make_float2(rintf(c.x), rintf(c.y));
 }
 
 template <int N, bool USE_MAD>
