@@ -336,6 +336,8 @@ template <> struct Decoder<T_Q3K> {
 // MODE 1: one tile per CTA (grid = ntiles), the tile arrives by one bulk copy: the hardware block scheduler
 //         overlaps the load of one CTA with the stores of its neighbours and balances the tail.
 // MODE 2: one tile per CTA, staged by cooperative 16-byte loads (no mbarrier, no async proxy).
+// MODE 3: STAGES consecutive tiles per short-lived CTA (grid = ceil(ntiles / STAGES)); all their bulk copies are
+//         issued up front, so the CTA decodes tile k while tiles k+1.. are still in flight.
 template <uint32_t T, class FT, int TILE_ELEMS, int STAGES, int THREADS, int MINB, int MODE, int SP>
 __global__ void __launch_bounds__(THREADS, MINB)
 dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ dst, size_t nblocks) {
@@ -343,7 +345,7 @@ dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ d
     constexpr int TILE_BLOCKS = TILE_ELEMS / TR::ELEMS;
     constexpr int TILE_BYTES = TILE_BLOCKS * TR::BYTES;
     constexpr int UNITS = Decoder<T>::template units<FT::V>();
-    constexpr int NST = MODE == 0 ? STAGES : 1;
+    constexpr int NST = (MODE == 0 || MODE == 3) ? STAGES : 1;
     static_assert(TILE_BYTES % 16 == 0, "tile must be a whole number of 16-byte chunks");
 
     extern __shared__ __align__(128) uint8_t smem[];
@@ -368,8 +370,11 @@ dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ d
     if constexpr (MODE != 2) __syncthreads();
     pdl_wait();               // the previous kernel in the stream is complete before any global access
 
+    auto tile_of = [&](size_t i) -> size_t {  // the i-th tile of this CTA
+        return MODE == 3 ? (size_t)blockIdx.x * STAGES + i : blockIdx.x + i * (size_t)gridDim.x;
+    };
     auto issue = [&](size_t i) {  // thread 0 only
-        const size_t t = blockIdx.x + i * (size_t)gridDim.x;
+        const size_t t = tile_of(i);
         if (MODE != 2 && t < full_tiles && src_fast) {
             const int s = (int)(i % NST);
             mbar_expect_tx(&bars[s], TILE_BYTES);
@@ -381,8 +386,9 @@ dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ d
         for (int i = 0; i < NST; i++) issue(i);
     }
 
-    size_t i = 0;
-    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+    for (size_t i = 0; MODE != 3 || i < (size_t)STAGES; ++i) {
+        const size_t t = tile_of(i);
+        if (t >= ntiles) break;
         const int s = (int)(i % NST);
         uint8_t *stage = stages + (size_t)s * TILE_BYTES;
         const bool bulk = MODE != 2 && (t < full_tiles) && src_fast;
@@ -405,7 +411,7 @@ dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ d
         if constexpr (MODE == 0) {
             __syncthreads();  // stage s fully consumed
             if (tid == 0) issue(i + NST);
-        } else {
+        } else if constexpr (MODE != 3) {
             if (t + gridDim.x < ntiles) {  // only when the grid was capped below ntiles
                 __syncthreads();
                 if (MODE == 1 && tid == 0) issue(i + 1);
@@ -415,7 +421,7 @@ dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ d
 }
 
 template <uint32_t T, int TILE_ELEMS, int STAGES, int MODE> constexpr int dequant_smem_bytes() {
-    return 128 + (MODE == 0 ? STAGES : 1) * (TILE_ELEMS / BlockTraits<T>::ELEMS) * BlockTraits<T>::BYTES + 16;
+    return 128 + ((MODE == 0 || MODE == 3) ? STAGES : 1) * (TILE_ELEMS / BlockTraits<T>::ELEMS) * BlockTraits<T>::BYTES + 16;
 }
 
 }  // namespace ggq

@@ -81,7 +81,7 @@ void run_variant(const char *tname, size_t n_elems, uint8_t *const *in, void *co
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, SMEM));
     const size_t nblocks = n_elems / TR::ELEMS;
     const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
-    size_t grid = MODE == 0 ? (size_t)g_sms * occ : ntiles;
+    size_t grid = MODE == 0 ? (size_t)g_sms * occ : MODE == 3 ? (ntiles + STAGES - 1) / STAGES : ntiles;
     if (grid > ntiles) grid = ntiles;
     for (int i = 0; i < 3; i++) CK(launch_pdl(kern, (unsigned)grid, THREADS, SMEM, (cudaStream_t)0, (const uint8_t *)in[i % NSETS], (typename FT::raw *)out[i % NSETS], nblocks));
     CK(cudaDeviceSynchronize());
@@ -186,7 +186,22 @@ int main(int argc, char **argv) {
 #else
 #define SWEEP_A(T, NAME, N)
 #endif
-#if SWEEP_SET == 5
+#if SWEEP_SET == 6
+// MODE 3: 2-4 consecutive tiles per short-lived CTA, all bulk copies issued up front
+#define SWEEP_B(T, NAME, N)                    \
+    V(T, NAME, N, 8192, 3, 256, 3, 0, 0);      \
+    V(T, NAME, N, 16384, 1, 128, 8, 1, 0);     \
+    V(T, NAME, N, 8192, 1, 128, 8, 1, 0);      \
+    V(T, NAME, N, 4096, 2, 128, 8, 3, 0);      \
+    V(T, NAME, N, 4096, 4, 128, 8, 3, 0);      \
+    V(T, NAME, N, 8192, 2, 128, 8, 3, 0);      \
+    V(T, NAME, N, 8192, 2, 128, 10, 3, 0);     \
+    V(T, NAME, N, 2048, 4, 128, 10, 3, 0);     \
+    V(T, NAME, N, 2048, 4, 64, 16, 3, 0);      \
+    V(T, NAME, N, 4096, 2, 64, 16, 3, 0);      \
+    V(T, NAME, N, 8192, 2, 256, 4, 3, 0);      \
+    V(T, NAME, N, 4096, 4, 256, 4, 3, 0);
+#elif SWEEP_SET == 5
 #define SWEEP_B(T, NAME, N)                    \
     V(T, NAME, N, 8192, 3, 256, 3, 0, 0);      \
     V(T, NAME, N, 8192, 2, 256, 3, 0, 0);      \
