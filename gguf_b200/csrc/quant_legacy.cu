@@ -5,17 +5,20 @@
 // Replaces the per-block `Quantize::quantize` bodies behind `QuantExt::quantize_slice`
 // (/root/reference/ggml-quants/src/lib.rs:121-133; per-type bodies cited at each encoder).
 //
-// Shape of the kernel (input-dominated stream; the first version with 4 lanes per block spent ~21
+// Shape of the kernels (input-dominated stream; the first version with 4 lanes per block spent ~21
 // instructions per element on shuffles / redundant divides and was issue-bound at 38 % of HBM peak):
 //   * ONE THREAD PER 32-ELEMENT ROW (a legacy block, or 1/8 of a Q8K super-block): the folds of
 //     structs.rs:91-107 are register-local, delta/recip cost two divides per 32 elements;
 //   * rows are staged global -> shared with 16-byte cp.async (coalesced, no registers), into rows
-//     padded by 16 bytes so that every thread's LDS.128 of its own row is bank-conflict free,
-//     QS stages deep;
+//     padded by 16 bytes so that every thread's LDS.128 of its own row is bank-conflict free;
 //   * f16 input folds with packed HMNMX2; codes are produced with full-rate float ops (clamp, then a
 //     round-toward-zero add of 2^23 leaves floor(v) in the mantissa) instead of F2I on the XU pipe;
-//   * packed blocks are assembled in a shared-memory tile and leave the SM as ONE 1-D bulk async
-//     store per tile (`cp.async.bulk.global.shared::cta`, SASS UBLKCP), double buffered.
+//   * launch shape (launch_quant): short-lived CTAs that request their tile(s) up front — one 128-row tile
+//     from f32 input, two 64-row tiles from 16-bit input (rows are half as long there, and the bytes in
+//     flight per SM, not the instruction count, bounded the encoders) — encode and write the packed blocks
+//     with cooperative 16-byte stores (quant_rows_oneshot); Q8K keeps the persistent ring
+//     (quant_rows_kernel: 2 cp.async stages, packed tile leaves as ONE 1-D bulk async store,
+//     `cp.async.bulk.global.shared::cta`, SASS UBLKCP, double buffered).
 #include <cstdlib>
 #include <type_traits>
 
@@ -187,9 +190,7 @@ template <> __device__ __forceinline__ void row_min_max<BF16>(const Row<BF16> &r
 // max_by_abs (structs.rs:96-100) over G lanes x 32 elements: the FIRST x with strictly greatest |x|.
 // With P = max(0, x...) and N = min(0, x...) the winner is P if P > -N, N if -N > P; only when both
 // +a and -a occur (P == -N != 0) does the order matter, and then the first of them wins.
-template <int G, class FT> __device__ __forceinline__ float block_max_by_abs(const Row<FT> &r, int j) {
-    float P, N;
-    row_pos_neg<FT>(r, P, N);
+template <int G, class FT> __device__ __forceinline__ float max_by_abs_from(const Row<FT> &r, int j, float P, float N) {
 #pragma unroll
     for (int m = 1; m < G; m <<= 1) {
         P = fmaxf(P, __shfl_xor_sync(FULL, P, m));
@@ -215,6 +216,45 @@ template <int G, class FT> __device__ __forceinline__ float block_max_by_abs(con
         if (tie) res = val;
     }
     return res;
+}
+
+template <int G, class FT> __device__ __forceinline__ float block_max_by_abs(const Row<FT> &r, int j) {
+    float P, N;
+    row_pos_neg<FT>(r, P, N);
+    return max_by_abs_from<G, FT>(r, j, P, N);
+}
+// row_pos_neg that also reports whether the row holds a NaN, at no extra cost for 16-bit rows: the max fold
+// propagates NaN (`max.NaN.f16x2`), so P comes out NaN exactly when some element is (and is then unusable: the
+// caller recomputes with row_pos_neg).  f32 rows have no such fold and always report "unknown" (true).
+template <class FT> __device__ __forceinline__ bool row_pos_neg_nan(const Row<FT> &r, float &P, float &N) {
+    row_pos_neg<FT>(r, P, N);
+    return true;
+}
+template <> __device__ __forceinline__ bool row_pos_neg_nan<F16>(const Row<F16> &r, float &P, float &N) {
+    __half2 p = __floats2half2_rn(0.0f, 0.0f), n = p;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const __half2 v = *reinterpret_cast<const __half2 *>(&r.raw[k]);
+        p = __hmax2_nan(p, v);
+        n = __hmin2(n, v);
+    }
+    const float pl = __low2float(p), ph = __high2float(p);
+    P = fmaxf(pl, ph);
+    N = fminf(__low2float(n), __high2float(n));
+    return (pl != pl) || (ph != ph);
+}
+template <> __device__ __forceinline__ bool row_pos_neg_nan<BF16>(const Row<BF16> &r, float &P, float &N) {
+    __nv_bfloat162 p = bf_pair(0u), n = p;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const __nv_bfloat162 v = bf_pair(r.raw[k]);
+        p = __hmax2_nan(p, v);
+        n = __hmin2(n, v);
+    }
+    const float pl = bf_lo(p), ph = bf_hi(p);
+    P = fmaxf(pl, ph);
+    N = fminf(bf_lo(n), bf_hi(n));
+    return (pl != pl) || (ph != ph);
 }
 
 // min of the row as the reference's strict-compare fold reports it: when the minimum is a zero, the
@@ -286,6 +326,19 @@ __device__ __forceinline__ void nibble_bytes(const uint32_t *c, uint32_t *w) {
 // ---- encoders: one thread, one 32-element row -------------------------------------------------------
 template <uint32_t T> struct Encoder;
 
+// The 4- and 5-bit encoders are issue-bound from 16-bit input, and two of their ~8.5 instructions per element are
+// the clamp around `v = x * recip` (or `(x - min) * recip`).  When delta is an ordinary number — 2^-100 <= |d| <=
+// 2^100, so that neither d, 1/d nor any product under- or overflows — one side of that clamp can never act:
+//   symmetric types   |x| <= |max|  =>  |v| <= N (1 + 3*2^-24), N = 8 / 16: v + N.5 stays above 0.49, only the top
+//                     (x = -max: v + N.5 = 2N.5) needs the clamp;
+//   affine types      0 <= x - min <= max - min  =>  0 <= v <= L (1 + 3*2^-24), L = 15 / 31: v + 0.5 < L + 1, only
+//                     the bottom clamp is kept, and only because it is what maps a NaN element to code 0.
+// Every other row (denormal / huge / infinite delta) takes the two-sided clamp below, as before.
+__device__ __forceinline__ bool ordinary_scale(float d) {
+    const float a = fabsf(d);
+    return a >= 7.888609052210118e-31f && a <= 1.2676506002282294e30f;  // 2^-100 .. 2^100 (false for NaN)
+}
+
 // q4_0.rs:23-44
 template <> struct Encoder<T_Q4_0> {
     static constexpr int G = 1;
@@ -298,14 +351,22 @@ template <> struct Encoder<T_Q4_0> {
             const float rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
             uint32_t c[32];
+            if (ordinary_scale(d)) {  // v >= -8.000002: the lower clamp cannot act (see ordinary_scale)
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                // (x*recip + 8.5).min(15.) as u8 : NaN -> 15 (fminf drops it), negatives -> 0
-                // the clamp moves in front of the add (bounds shifted by 8.5, same results incl. NaN -> 15), so the
-                // add no longer follows the packed multiply directly and can be packed as well
-                const float2 p = mul2(pair_of(r.x, k), rc);
-                const float2 q = make_float2(fmaxf(fminf(p.x, 6.5f), -8.5f), fmaxf(fminf(p.y, 6.5f), -8.5f));
-                floor_bits2(add2(q, 8.5f), c[2 * k], c[2 * k + 1]);
+                for (int k = 0; k < 16; k++) {
+                    const float2 p = mul2(pair_of(r.x, k), rc);
+                    floor_bits2(add2(make_float2(fminf(p.x, 6.5f), fminf(p.y, 6.5f)), 8.5f), c[2 * k], c[2 * k + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    // (x*recip + 8.5).min(15.) as u8 : NaN -> 15 (fminf drops it), negatives -> 0
+                    // the clamp moves in front of the add (bounds shifted by 8.5, same results incl. NaN -> 15), so the
+                    // add no longer follows the packed multiply directly and can be packed as well
+                    const float2 p = mul2(pair_of(r.x, k), rc);
+                    const float2 q = make_float2(fmaxf(fminf(p.x, 6.5f), -8.5f), fmaxf(fminf(p.y, 6.5f), -8.5f));
+                    floor_bits2(add2(q, 8.5f), c[2 * k], c[2 * k + 1]);
+                }
             }
             nibble_bytes(c, w);
         }
@@ -327,11 +388,19 @@ template <> struct Encoder<T_Q4_1> {
             const float d = __fdiv_rn(__fsub_rn(mx, mn), 15.0f), rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
             uint32_t c[32];
+            if (ordinary_scale(d)) {  // v <= 15.000003: the upper clamp cannot act; the lower one maps NaN -> 0
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                // (((x - min)*recip + 0.5) as u8).min(15) : NaN -> 0
-                const float2 p = mul2(add2(pair_of(r.x, k), -mn), rc);
-                floor_bits2(add2(clamp2(p, -0.5f, 14.5f), 0.5f), c[2 * k], c[2 * k + 1]);  // clamp before the add, see Q4_0
+                for (int k = 0; k < 16; k++) {
+                    const float2 p = mul2(add2(pair_of(r.x, k), -mn), rc);
+                    floor_bits2(add2(make_float2(fmaxf(p.x, -0.5f), fmaxf(p.y, -0.5f)), 0.5f), c[2 * k], c[2 * k + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    // (((x - min)*recip + 0.5) as u8).min(15) : NaN -> 0
+                    const float2 p = mul2(add2(pair_of(r.x, k), -mn), rc);
+                    floor_bits2(add2(clamp2(p, -0.5f, 14.5f), 0.5f), c[2 * k], c[2 * k + 1]);  // clamp before the add, see Q4_0
+                }
             }
             nibble_bytes(c, w);
         }
@@ -361,7 +430,10 @@ __device__ __forceinline__ void pack5(const uint32_t *c, uint32_t &qh, uint32_t 
 template <> struct Encoder<T_Q5_0> {
     static constexpr int G = 1;
     template <class FT> static __device__ __forceinline__ void run(const Row<FT> &r, int, uint8_t *blk) {
-        const float mx = block_max_by_abs<1, FT>(r, 0);
+        float P, N;
+        const bool maybe_nan = row_pos_neg_nan<FT>(r, P, N);
+        if (FT::SIZE == 2 && maybe_nan) row_pos_neg<FT>(r, P, N);  // a NaN in the row spoiled P: fold again without it
+        const float mx = max_by_abs_from<1, FT>(r, 0, P, N);
         uint32_t w[4] = {0, 0, 0, 0};
         uint32_t d16 = 0, qh = 0;
         if (mx != 0.0f) {
@@ -369,11 +441,20 @@ template <> struct Encoder<T_Q5_0> {
             const float rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
             uint32_t c[32];
+            if (!maybe_nan && ordinary_scale(d)) {
+                // v >= -16.000004: the lower clamp could only act on a NaN element (NaN -> code 0), and there is none
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                // ((x*recip + 16.5) as u8).min(31) : NaN -> 0
-                const float2 p = mul2(pair_of(r.x, k), rc);
-                floor_bits2(add2(clamp2(p, -16.5f, 14.5f), 16.5f), c[2 * k], c[2 * k + 1]);  // clamp before the add, see Q4_0
+                for (int k = 0; k < 16; k++) {
+                    const float2 p = mul2(pair_of(r.x, k), rc);
+                    floor_bits2(add2(make_float2(fminf(p.x, 14.5f), fminf(p.y, 14.5f)), 16.5f), c[2 * k], c[2 * k + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    // ((x*recip + 16.5) as u8).min(31) : NaN -> 0
+                    const float2 p = mul2(pair_of(r.x, k), rc);
+                    floor_bits2(add2(clamp2(p, -16.5f, 14.5f), 16.5f), c[2 * k], c[2 * k + 1]);  // clamp before the add, see Q4_0
+                }
             }
             pack5(c, qh, w);
         }
@@ -397,10 +478,18 @@ template <> struct Encoder<T_Q5_1> {
             const float d = __fdiv_rn(__fsub_rn(mx, mn), 31.0f), rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
             uint32_t c[32];
+            if (ordinary_scale(d)) {  // v <= 31.000006: the upper clamp cannot act; the lower one maps NaN -> 0
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const float2 p = mul2(add2(pair_of(r.x, k), -mn), rc);
-                floor_bits2(add2(clamp2(p, -0.5f, 30.5f), 0.5f), c[2 * k], c[2 * k + 1]);  // clamp before the add, see Q4_0
+                for (int k = 0; k < 16; k++) {
+                    const float2 p = mul2(add2(pair_of(r.x, k), -mn), rc);
+                    floor_bits2(add2(make_float2(fmaxf(p.x, -0.5f), fmaxf(p.y, -0.5f)), 0.5f), c[2 * k], c[2 * k + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const float2 p = mul2(add2(pair_of(r.x, k), -mn), rc);
+                    floor_bits2(add2(clamp2(p, -0.5f, 30.5f), 0.5f), c[2 * k], c[2 * k + 1]);  // clamp before the add, see Q4_0
+                }
             }
             pack5(c, qh, w);
         }
@@ -581,89 +670,126 @@ quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, si
     if (tid == 0) bulk_wait_all<0>();
 }
 
-// One tile per CTA: stage ROWS rows, encode, write the packed blocks — no ring, no running pointers.  The
-// overlap of loads, math and stores comes from the hardware scheduling several resident CTAs per SM, the
-// structure that took the cast kernel from 85 % to 98 % of the copy peak; per row it also sheds the
-// bookkeeping of the persistent pipeline above.  launch_quant picks per (type, float side).
-template <uint32_t T, class FT, int ROWS>
+// Short-lived CTAs: stage K tiles of ROWS rows up front, encode them one after the other, write the packed
+// blocks — no ring, no running pointers.  The overlap of loads, math and stores comes from the hardware
+// scheduling several resident CTAs per SM, the structure that took the cast kernel from 85 % to 98 % of the copy
+// peak; per row it also sheds the bookkeeping of the persistent pipeline above.  K > 1 exists for 16-bit input:
+// a thread's row is then only 64 bytes, and one row per resident thread (registers allow ~1 150 threads per SM)
+// is ~70 KB in flight per SM in the best case — too little to cover HBM latency at full bandwidth, which is why
+// every 16-bit-input encoder stopped at ~31 us per 58.7 M elements whatever its instruction count.  With K
+// tiles requested before the first is encoded the bytes in flight per thread multiply and tile k+1 keeps
+// arriving while tile k is encoded.  launch_quant picks (ROWS, K) per (type, float side).
+template <int N> __device__ __forceinline__ void cp_async_wait_upto(int pending) {  // wait until <= pending groups are outstanding
+    if constexpr (N == 0) {
+        cp_async_wait<0>();
+    } else {
+        if (pending >= N) cp_async_wait<N>();
+        else cp_async_wait_upto<N - 1>(pending);
+    }
+}
+template <uint32_t T, class FT, int ROWS, int K>
 __global__ void __launch_bounds__(ROWS)
 quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t nblocks) {
     using TR = BlockTraits<T>;
     using E = Encoder<T>;
     constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = ROWS / RPB;
     constexpr int ROW_BYTES = 32 * FT::SIZE, ROW_STRIDE = ROW_BYTES + 16, CPR = ROW_BYTES / 16, ROWS_PER_PASS = ROWS / CPR;
-    constexpr int OUT_BYTES = TILE_BLOCKS * TR::BYTES;
+    constexpr int IN_STAGE = ROWS * ROW_STRIDE, OUT_BYTES = TILE_BLOCKS * TR::BYTES;
     static_assert(OUT_BYTES % 16 == 0, "tile must be a whole number of 16-byte chunks");
-    __shared__ __align__(128) uint8_t in_st[ROWS * ROW_STRIDE];
-    __shared__ __align__(16) uint8_t out_st[OUT_BYTES];
+    __shared__ __align__(128) uint8_t in_st[K * IN_STAGE];
+    __shared__ __align__(16) uint8_t out_st[K * OUT_BYTES];
     const int tid = threadIdx.x;
     const size_t nrows = nblocks * RPB, ntiles = (nrows + ROWS - 1) / ROWS;
     const bool vec_in = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
     const uint32_t s_chunk0 = (uint32_t)(tid / CPR) * ROW_STRIDE + (uint32_t)(tid % CPR) * 16;
     pdl_launch_dependents();
     pdl_wait();
-    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {  // one iteration unless the grid was capped
-        const size_t rem = nrows - t * ROWS;
-        const int rows = (int)min((size_t)ROWS, rem);
-        const uint8_t *g = src + t * ((size_t)ROWS * ROW_BYTES);
-        if (vec_in) {
+    for (size_t t0 = (size_t)blockIdx.x * K; t0 < ntiles; t0 += (size_t)gridDim.x * K) {  // one iteration unless the grid was capped
+        // ---- request all K tiles ----
 #pragma unroll
-            for (int k = 0; k < CPR; k++)
-                if (rows == ROWS || tid / CPR + k * ROWS_PER_PASS < rows)
-                    cp_async16(in_st + s_chunk0 + k * ROWS_PER_PASS * ROW_STRIDE, g + (size_t)tid * 16 + (size_t)k * ROWS * 16);
-            cp_async_commit();
-            cp_async_wait<0>();
-        } else {  // source not 16-byte aligned: element-granular staging
-            using RAW = typename FT::raw;
-            const RAW *ge = reinterpret_cast<const RAW *>(g);
-            for (int e = tid; e < rows * 32; e += ROWS)
-                *reinterpret_cast<RAW *>(in_st + (e / 32) * ROW_STRIDE + (e % 32) * FT::SIZE) = ge[e];
+        for (int k = 0; k < K; k++) {
+            const size_t t = t0 + k;
+            if (t < ntiles) {
+                const size_t rem = nrows - t * ROWS;
+                const int rows = (int)min((size_t)ROWS, rem);
+                const uint8_t *g = src + t * ((size_t)ROWS * ROW_BYTES);
+                uint8_t *st = in_st + k * IN_STAGE;
+                if (vec_in) {
+#pragma unroll
+                    for (int c = 0; c < CPR; c++)
+                        if (rows == ROWS || tid / CPR + c * ROWS_PER_PASS < rows)
+                            cp_async16(st + s_chunk0 + c * ROWS_PER_PASS * ROW_STRIDE, g + (size_t)tid * 16 + (size_t)c * ROWS * 16);
+                } else {  // source not 16-byte aligned: element-granular staging
+                    using RAW = typename FT::raw;
+                    const RAW *ge = reinterpret_cast<const RAW *>(g);
+                    for (int e = tid; e < rows * 32; e += ROWS)
+                        *reinterpret_cast<RAW *>(st + (e / 32) * ROW_STRIDE + (e % 32) * FT::SIZE) = ge[e];
+                }
+            }
+            cp_async_commit();  // one group per tile, empty or not
+        }
+        // ---- encode tile k while tiles k+1.. are still arriving ----
+        size_t rows_total = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const size_t t = t0 + k;
+            if (t < ntiles) {  // CTA-uniform
+                const int rows = (int)min((size_t)ROWS, nrows - t * ROWS);
+                cp_async_wait_upto<K - 1>(K - 1 - k);
+                __syncthreads();
+                if (RPB > 1 || tid < rows) {  // G > 1 encoders shuffle: every lane of the warp takes part
+                    Row<FT> r;
+                    if (tid < rows) r.load(in_st + k * IN_STAGE + tid * ROW_STRIDE);
+                    else r.zero();
+                    E::template run<FT>(r, tid % RPB, out_st + k * OUT_BYTES + (uint32_t)(tid / RPB) * TR::BYTES);
+                }
+                rows_total += rows;
+            }
         }
         __syncthreads();
-        if (RPB > 1 || tid < rows) {  // G > 1 encoders shuffle: every lane of the warp takes part
-            Row<FT> r;
-            if (tid < rows) r.load(in_st + tid * ROW_STRIDE);
-            else r.zero();
-            E::template run<FT>(r, tid % RPB, out_st + (uint32_t)(tid / RPB) * TR::BYTES);
-        }
-        __syncthreads();
-        cta_copy_s2g(dst + t * (size_t)OUT_BYTES, out_st, (uint32_t)(rows / RPB) * TR::BYTES, tid, ROWS);
+        // the K tiles are consecutive in dst: one cooperative copy
+        cta_copy_s2g(dst + t0 * (size_t)OUT_BYTES, out_st, (uint32_t)(rows_total / RPB) * TR::BYTES, tid, ROWS);
         __syncthreads();  // only matters when the loop runs again
     }
 }
 
-template <uint32_t T, class FT, int ROWS>
+template <uint32_t T, class FT, int ROWS, int K>
 static cudaError_t launch_quant_oneshot(const void *src, void *dst, size_t nblocks, cudaStream_t stream) {
     constexpr int RPB = BlockTraits<T>::ELEMS / 32, TILE_BLOCKS = ROWS / RPB;
-    size_t grid = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
+    size_t grid = (nblocks + (size_t)TILE_BLOCKS * K - 1) / ((size_t)TILE_BLOCKS * K);
     if (grid > 0x7FFFFFFFull) grid = 0x7FFFFFFFull;
-    return launch_pdl(quant_rows_oneshot<T, FT, ROWS>, (unsigned)grid, ROWS, 0, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
+    return launch_pdl(quant_rows_oneshot<T, FT, ROWS, K>, (unsigned)grid, ROWS, 0, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
 }
 
 template <uint32_t T, class FT>
 static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
     using TR = BlockTraits<T>;
-    // measured (tools/codec_sweep.py): 2 input stages beat 3 (more CTAs per SM hide the per-tile barrier);
-    // 128-row tiles are best for Q8_0 / Q8_1, 64-row tiles for the 4/5-bit types and Q8K
-    // measured (tools/codec_sweep.py, 58.7 M elements): with f32 input the one-tile-per-CTA kernel runs at 99-101 % of the
-    // copy peak (persistent ring: 89-92 %), and it wins for Q8_0 / Q8_1 from 16-bit input too (84-85 % vs 82 %); the
-    // 4/5-bit encoders from 16-bit input are bound by their instruction count either way (the ring is 1-3 points
-    // better there) and Q8K's eight-lane groups prefer the ring's 64-row tiles.
-    constexpr bool ONESHOT = (T != T_Q8K) && (std::is_same<FT, F32>::value || T == T_Q8_0 || T == T_Q8_1);
-    if constexpr (ONESHOT) return launch_quant_oneshot<T, FT, 128>(src, dst, nblocks, stream);
-    constexpr int QS = 2;
-    constexpr int QL_THREADS = (T == T_Q8_0 || T == T_Q8_1) ? 128 : 64;
-    constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = QL_THREADS / RPB;
-    constexpr int SMEM = QS * QL_THREADS * (32 * FT::SIZE + 16) + 2 * ((TILE_BLOCKS * TR::BYTES + 15) & ~15);
-    auto kern = quant_rows_kernel<T, FT, QS, QL_THREADS>;
-    static std::atomic<int> occ_cache[MAX_DEVICES];
-    int ctas_per_sm = 0;
-    cudaError_t e = cached_occupancy(kern, QL_THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
-    if (e != cudaSuccess) return e;
-    const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
-    size_t grid = (size_t)dev.sm_count * ctas_per_sm;
-    if (grid > ntiles) grid = ntiles;
-    return launch_pdl(kern, (unsigned)grid, QL_THREADS, SMEM, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
+    // measured (tools/codec_sweep.py, 58.7 M elements, profiles/r01_quant_oneshot_sweep.txt):
+    //   f32 input: one 128-row tile per CTA runs at 99-101 % of the copy peak (persistent ring: 89-92 %);
+    //   16-bit input: two 64-row tiles per CTA, both requested up front: 83-89 % (ring and one tile per CTA: 73-75 %
+    //   for the 4/5-bit types, 84-87 % for Q8_0 / Q8_1 — bytes in flight, not instructions, were the limit; K = 3,
+    //   96- and 128-row tiles are 1-3 points behind, 32-row tiles 10);
+    //   Q8K's eight-lane groups are slower in every one-shot form (59-64 % vs 74 %) and keep the ring's 64-row tiles.
+    constexpr bool ONESHOT_F32 = (T != T_Q8K) && std::is_same<FT, F32>::value;
+    constexpr bool ONESHOT_16 = (T != T_Q8K) && !std::is_same<FT, F32>::value;
+    if constexpr (ONESHOT_F32) {
+        return launch_quant_oneshot<T, FT, 128, 1>(src, dst, nblocks, stream);
+    } else if constexpr (ONESHOT_16) {
+        return launch_quant_oneshot<T, FT, 64, 2>(src, dst, nblocks, stream);
+    } else {  // Q8K: persistent ring, 2 input stages, 64-row tiles
+        constexpr int QS = 2, QL_THREADS = 64;
+        constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = QL_THREADS / RPB;
+        constexpr int SMEM = QS * QL_THREADS * (32 * FT::SIZE + 16) + 2 * ((TILE_BLOCKS * TR::BYTES + 15) & ~15);
+        auto kern = quant_rows_kernel<T, FT, QS, QL_THREADS>;
+        static std::atomic<int> occ_cache[MAX_DEVICES];
+        int ctas_per_sm = 0;
+        cudaError_t e = cached_occupancy(kern, QL_THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
+        if (e != cudaSuccess) return e;
+        const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
+        size_t grid = (size_t)dev.sm_count * ctas_per_sm;
+        if (grid > ntiles) grid = ntiles;
+        return launch_pdl(kern, (unsigned)grid, QL_THREADS, SMEM, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
+    }
 }
 
 template <uint32_t T>
