@@ -194,6 +194,9 @@ def ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa(local_rank) if world > 1 else "single rank"
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     L = lib()
     stream = torch.cuda.current_stream().cuda_stream
