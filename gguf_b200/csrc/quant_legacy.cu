@@ -790,6 +790,22 @@ static cudaError_t launch_quant_oneshot(const void *src, void *dst, size_t nbloc
     return launch_pdl(quant_rows_oneshot<T, FT, ROWS, K>, (unsigned)grid, ROWS, 0, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
 }
 
+template <uint32_t T, class FT, int QS, int QL_THREADS>
+static cudaError_t launch_quant_ring(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
+    using TR = BlockTraits<T>;
+    constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = QL_THREADS / RPB;
+    constexpr int SMEM = QS * QL_THREADS * (32 * FT::SIZE + 16) + 2 * ((TILE_BLOCKS * TR::BYTES + 15) & ~15);
+    auto kern = quant_rows_kernel<T, FT, QS, QL_THREADS>;
+    static std::atomic<int> occ_cache[MAX_DEVICES];
+    int ctas_per_sm = 0;
+    cudaError_t e = cached_occupancy(kern, QL_THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
+    if (e != cudaSuccess) return e;
+    const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
+    size_t grid = (size_t)dev.sm_count * ctas_per_sm;
+    if (grid > ntiles) grid = ntiles;
+    return launch_pdl(kern, (unsigned)grid, QL_THREADS, SMEM, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
+}
+
 template <uint32_t T, class FT>
 static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
     using TR = BlockTraits<T>;
@@ -805,19 +821,10 @@ static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cuda
         return launch_quant_oneshot<T, FT, 128, 1>(src, dst, nblocks, stream);
     } else if constexpr (ONESHOT_16) {
         return launch_quant_oneshot<T, FT, 64, 2>(src, dst, nblocks, stream);
-    } else {  // Q8K: persistent ring, 2 input stages, 64-row tiles
-        constexpr int QS = 2, QL_THREADS = 64;
-        constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = QL_THREADS / RPB;
-        constexpr int SMEM = QS * QL_THREADS * (32 * FT::SIZE + 16) + 2 * ((TILE_BLOCKS * TR::BYTES + 15) & ~15);
-        auto kern = quant_rows_kernel<T, FT, QS, QL_THREADS>;
-        static std::atomic<int> occ_cache[MAX_DEVICES];
-        int ctas_per_sm = 0;
-        cudaError_t e = cached_occupancy(kern, QL_THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
-        if (e != cudaSuccess) return e;
-        const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
-        size_t grid = (size_t)dev.sm_count * ctas_per_sm;
-        if (grid > ntiles) grid = ntiles;
-        return launch_pdl(kern, (unsigned)grid, QL_THREADS, SMEM, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
+    } else {  // Q8K: persistent ring, 64-row tiles
+        // 2 input stages and 64-row tiles: 3-4 stages or 128-row tiles are 2-8 points slower (the encoder's
+        // eight-lane shuffles, not bytes in flight, bound this one)
+        return launch_quant_ring<T, FT, 2, 64>(src, dst, nblocks, stream, dev);
     }
 }
 
