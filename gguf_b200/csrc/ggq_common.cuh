@@ -202,6 +202,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
+// 16-byte asynchronous global -> shared copies (SASS LDGSTS), per-thread group completion
+__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Programmatic dependent launch (PDL): `pdl_launch_dependents` lets the next kernel in the stream start
 // scheduling its CTAs as ours retire; `pdl_wait` blocks until the previous kernel in the stream has
 // completed and flushed.  Every kernel calls pdl_wait before its first global access, so stream-order

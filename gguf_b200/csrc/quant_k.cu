@@ -15,6 +15,8 @@
 //   * codes go through a per-warp shared-memory scratch and are assembled bytewise into the packed
 //     layout, then copied to global memory.
 // This path is COMPUTE-bound (~400 dependent flops per element for Q4K), not HBM-bound; see DESIGN.md.
+#include <type_traits>
+
 #include "ggq_common.cuh"
 #include "ggq_kernels.h"
 
@@ -574,7 +576,13 @@ quant_k_kernel(const typename FT::raw *__restrict__ src, uint8_t *__restrict__ d
     constexpr int BYTES = BlockTraits<T>::BYTES;
     constexpr int OUT_BYTES = (SBW * BYTES + 15) & ~15;
 
-    __shared__ float xs[KQ_WARPS][32][SUB + 1];
+    // Input staging: the SBW super-blocks of a warp pass are SBW*256 consecutive elements = 32 sub-block rows.
+    // They are copied raw (16-byte cp.async, coalesced, no registers) into rows padded by 16 bytes, so that every
+    // lane's LDS.128 of its own row is bank-conflict free, two stages deep: the rows of the NEXT pass are in flight
+    // while this pass runs its search (the synchronous load-convert-scatter this replaces was 1.5 % of the executed
+    // instructions but 7 % of the stall samples: every warp sat out a full HBM round trip per pass).
+    constexpr int ROW_BYTES = SUB * FT::SIZE, RSTRIDE = ROW_BYTES + 16, CPR = ROW_BYTES / 16;
+    __shared__ __align__(16) uint8_t xraw[KQ_WARPS][2][32 * RSTRIDE];
     __shared__ KScratch scratch[KQ_WARPS][SBW];
     __shared__ __align__(16) uint8_t outb[KQ_WARPS][OUT_BYTES];
 
@@ -582,30 +590,72 @@ quant_k_kernel(const typename FT::raw *__restrict__ src, uint8_t *__restrict__ d
     const int sbi = lane / NSUB, j = lane % NSUB;
     const size_t ngroups = (nblocks + SBW - 1) / SBW;
     const bool vec_in = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    const size_t gstep = (size_t)gridDim.x * KQ_WARPS;
 
-    for (size_t g = (size_t)blockIdx.x * KQ_WARPS + warp; g < ngroups; g += (size_t)gridDim.x * KQ_WARPS) {
+    auto issue = [&](size_t g, int stage) {  // request the rows of warp pass g (a no-op group past the end)
+        if (g < ngroups) {
+            const size_t sb0 = g * SBW;
+            const int nsb = (int)min((size_t)SBW, nblocks - sb0);
+            const uint8_t *in = reinterpret_cast<const uint8_t *>(src + sb0 * 256);
+            uint8_t *st = xraw[warp][stage];
+            const int live = nsb * (256 / SUB) * CPR;  // chunks that exist; the rest of the pass is zero rows
+#pragma unroll
+            for (int c = 0; c < CPR; c++) {
+                const int ch = lane + 32 * c, row = ch / CPR, cc = ch % CPR;
+                uint8_t *sdst = st + row * RSTRIDE + cc * 16;
+                if (ch < live) {
+                    if (vec_in) {
+                        cp_async16(sdst, in + (size_t)ch * 16);
+                    } else {  // source only element-aligned: synchronous element copies
+                        using RAW = typename FT::raw;
+                        const RAW *ge = reinterpret_cast<const RAW *>(in + (size_t)ch * 16);
+#pragma unroll
+                        for (int e = 0; e < 16 / FT::SIZE; e++) reinterpret_cast<RAW *>(sdst)[e] = ge[e];
+                    }
+                } else {
+                    *reinterpret_cast<uint4 *>(sdst) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    size_t g = (size_t)blockIdx.x * KQ_WARPS + warp;
+    int stage = 0;
+    issue(g, 0);
+    for (; g < ngroups; g += gstep, stage ^= 1) {
         const size_t sb0 = g * SBW;
         const int nsb = (int)min((size_t)SBW, nblocks - sb0);
-        const typename FT::raw *in = src + sb0 * 256;
-        // cooperative coalesced load of SBW*256 elements -> xs[row = sub-block][col]
+        issue(g + gstep, stage ^ 1);  // the other stage was consumed before the __syncwarp that ended the previous pass
+        cp_async_wait<1>();           // this lane's chunks of pass g have landed ...
+        __syncwarp();                 // ... and so have everybody else's
+        float x[SUB];
+        {
+            const uint8_t *row = xraw[warp][stage] + lane * RSTRIDE;
+            if constexpr (FT::SIZE == 4) {
 #pragma unroll
-        for (int it = 0; it < SBW * 256 / (32 * 8); it++) {
-            const int e0 = (it * 32 + lane) * 8;
-            float v[8];
-            if (e0 / 256 < nsb) {
-                load8<FT>(in + e0, v, vec_in);
+                for (int i = 0; i < SUB / 4; i++) {
+                    const float4 v = *reinterpret_cast<const float4 *>(row + 16 * i);
+                    x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+                }
             } else {
 #pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = 0.f;
+                for (int i = 0; i < SUB / 8; i++) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(row + 16 * i);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if constexpr (std::is_same<FT, F16>::value) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[q]));
+                            x[8 * i + 2 * q] = f.x; x[8 * i + 2 * q + 1] = f.y;
+                        } else {
+                            x[8 * i + 2 * q] = __uint_as_float(w[q] << 16);
+                            x[8 * i + 2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
+                        }
+                    }
+                }
             }
-            const int row = e0 / SUB, col = e0 % SUB;
-#pragma unroll
-            for (int k = 0; k < 8; k++) xs[warp][row][col + k] = v[k];
         }
-        __syncwarp();
-        float x[SUB];
-#pragma unroll
-        for (int i = 0; i < SUB; i++) x[i] = xs[warp][lane][i];
         KQ::lane(x, j, lane, scratch[warp][sbi]);
         __syncwarp();
         for (int o = lane; o < nsb * BYTES; o += 32) outb[warp][o] = (uint8_t)KQ::byte(scratch[warp][o / BYTES], o % BYTES);
@@ -613,6 +663,7 @@ quant_k_kernel(const typename FT::raw *__restrict__ src, uint8_t *__restrict__ d
         cta_copy_s2g(dst + sb0 * BYTES, outb[warp], (uint32_t)(nsb * BYTES), lane, 32);
         __syncwarp();
     }
+    cp_async_wait<0>();
 }
 
 template <uint32_t T, class FT>

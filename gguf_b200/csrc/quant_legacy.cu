@@ -30,11 +30,6 @@ namespace ggq {
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr float F32_MAX = 3.40282347e+38f;
 
-__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- a row of 32 elements, widened to f32 (lib.rs:66-69, 82-84); `raw` keeps the f16 pairs --------
 template <class FT> struct Row;
