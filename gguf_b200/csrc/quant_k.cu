@@ -12,8 +12,9 @@
 //     the oracle's exact order — no redundant work, no cross-lane float reduction;
 //   * the 8/16 per-sub-block results of a super-block are combined by xor-shuffles (max is
 //     order-independent; "first with greatest |.|" uses a lowest-lane-wins arg-max);
-//   * codes go through a per-warp shared-memory scratch and are assembled bytewise into the packed
-//     layout, then copied to global memory.
+//   * codes go through a per-warp shared-memory scratch and are assembled into the packed layout one 32-bit
+//     (Q2K / Q4K / Q5K) or 16-bit (Q3K / Q6K) unit per lane and iteration, then copied to global memory;
+//   * the rows of the next warp pass arrive by cp.async while this pass searches.
 // This path is COMPUTE-bound (~400 dependent flops per element for Q4K), not HBM-bound; see DESIGN.md.
 #include <type_traits>
 
@@ -384,44 +385,72 @@ template <int NMAX> __device__ __forceinline__ void k45_lane(const float (&x)[32
     s.b[j] = (uint8_t)lm;
     if (j == 0) { s.d16 = d16; s.dmin16 = dmin16; s.zero = 0; }
 }
-// header bytes 0..15 of Q4K / Q5K: delta, min, 12 bytes of 6-bit scales/mins
-__device__ __forceinline__ uint32_t k45_header_byte(const KScratch &s, int o) {
-    if (o < 2) return (s.d16 >> (8 * o)) & 0xFF;
-    if (o < 4) return (s.dmin16 >> (8 * (o - 2))) & 0xFF;
-    const int k = o - 4;
-    if (k < 4) return s.a[k] | ((s.a[k + 4] >> 4) << 6);
-    if (k < 8) return s.b[k - 4] | ((s.b[k] >> 4) << 6);
-    return (s.a[k - 4] & 0xF) | ((s.b[k - 4] & 0xF) << 4);
-}
+// header bytes 0..15 of Q4K / Q5K: delta, min, 12 bytes of 6-bit scales/mins — byte k of the 12: k < 4: a[k] | (a[k+4] >> 4) << 6;
+// k < 8: b[k-4] | (b[k] >> 4) << 6; else (a[k-4] & 15) | (b[k-4] & 15) << 4 —
 
+// the same 16 header bytes as four little-endian words (a[] and b[] hold 6-bit codes)
+__device__ __forceinline__ uint32_t k45_header_word(const KScratch &s, int w) {
+    if (w == 0) return (uint32_t)s.d16 | ((uint32_t)s.dmin16 << 16);
+    const uint32_t a0 = *reinterpret_cast<const uint32_t *>(&s.a[0]), a1 = *reinterpret_cast<const uint32_t *>(&s.a[4]);
+    const uint32_t b0 = *reinterpret_cast<const uint32_t *>(&s.b[0]), b1 = *reinterpret_cast<const uint32_t *>(&s.b[4]);
+    if (w == 1) return a0 | ((a1 & 0x30303030u) << 2);
+    if (w == 2) return b0 | ((b1 & 0x30303030u) << 2);
+    return (a1 & 0x0F0F0F0Fu) | ((b1 & 0x0F0F0F0Fu) << 4);
+}
+__device__ __forceinline__ uint32_t code_word(const KScratch &s, int w) { return reinterpret_cast<const uint32_t *>(s.L)[w]; }
+
+// Types whose block is a whole number of 32-bit words also provide word(s, w), the w-th little-endian word of the
+// packed block: the assembler then runs one iteration per four output bytes (the bytewise assembler this replaced
+// cost ~25 instructions and 2-4 dependent one-byte shared loads per output byte; that phase was 5 % of the executed
+// instructions but 10 % of the stall samples of the Q4K kernel).  Q3K / Q6K blocks (110 / 210 bytes) are assembled in
+// 16-bit units with half(s, h) instead.
 template <> struct KQuant<T_Q4K> {
     static constexpr int SUB = 32;
-    static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s) { k45_lane<15>(x, j, s, -1.f, 20); }
-    static __device__ __forceinline__ uint32_t byte(const KScratch &s, int o) {
-        if (o < 16) return k45_header_byte(s, o);
-        const int t = o - 16, p = t >> 5, l = t & 31;
-        return s.L[64 * p + l] | (s.L[64 * p + 32 + l] << 4);
+    static constexpr int WORDS = 36;
+    static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
+        if (w < 4) return k45_header_word(s, w);
+        const int t = w - 4, p = t >> 3, jj = t & 7;
+        return code_word(s, 16 * p + jj) | (code_word(s, 16 * p + 8 + jj) << 4);
     }
+    static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s) { k45_lane<15>(x, j, s, -1.f, 20); }
 };
 template <> struct KQuant<T_Q5K> {
     static constexpr int SUB = 32;
-    static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s) { k45_lane<31>(x, j, s, -0.5f, 15); }
-    static __device__ __forceinline__ uint32_t byte(const KScratch &s, int o) {
-        if (o < 16) return k45_header_byte(s, o);
-        if (o < 48) {
-            const int l = o - 16;
+    static constexpr int WORDS = 44;
+    static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
+        if (w < 4) return k45_header_word(s, w);
+        if (w < 12) {  // qh: bit 2p / 2p+1 of byte l = fifth bit of elements 64p+l / 64p+32+l
+            const int jj = w - 4;
             uint32_t h = 0;
 #pragma unroll
-            for (int p = 0; p < 4; p++) h |= ((s.L[64 * p + l] >> 4) << (2 * p)) | ((s.L[64 * p + 32 + l] >> 4) << (2 * p + 1));
+            for (int p = 0; p < 4; p++)
+                h |= (((code_word(s, 16 * p + jj) >> 4) & 0x01010101u) << (2 * p)) | (((code_word(s, 16 * p + 8 + jj) >> 4) & 0x01010101u) << (2 * p + 1));
             return h;
         }
-        const int t = o - 48, p = t >> 5, l = t & 31;
-        return (s.L[64 * p + l] & 15) | ((s.L[64 * p + 32 + l] & 15) << 4);
+        const int t = w - 12, p = t >> 3, jj = t & 7;
+        return (code_word(s, 16 * p + jj) & 0x0F0F0F0Fu) | ((code_word(s, 16 * p + 8 + jj) & 0x0F0F0F0Fu) << 4);
     }
+    static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s) { k45_lane<31>(x, j, s, -0.5f, 15); }
 };
 
 template <> struct KQuant<T_Q6K> {
     static constexpr int SUB = 16;
+    static constexpr int WORDS = 0, HALVES = 105;  // 210 bytes: not a whole number of words -> 16-bit units
+    static __device__ __forceinline__ uint32_t half(const KScratch &s, int h) {
+        if (s.zero) return 0;
+        const uint16_t *Lh = reinterpret_cast<const uint16_t *>(s.L);
+        if (h < 64) {  // ql
+            const int o = 2 * h, n = o >> 6, r = o & 63, e = 128 * n + (r & 31) + (r >= 32 ? 32 : 0);
+            return (Lh[e >> 1] & 0x0F0Fu) | ((Lh[(e + 64) >> 1] & 0x0F0Fu) << 4);
+        }
+        if (h < 96) {  // qh
+            const int t = 2 * (h - 64), n = t >> 5, e = 128 * n + (t & 31);
+            return ((Lh[e >> 1] >> 4) & 0x0303u) | (((Lh[(e + 32) >> 1] >> 4) & 0x0303u) << 2) | (((Lh[(e + 64) >> 1] >> 4) & 0x0303u) << 4) |
+                   (((Lh[(e + 96) >> 1] >> 4) & 0x0303u) << 6);
+        }
+        if (h < 104) return reinterpret_cast<const uint16_t *>(s.a)[h - 96];
+        return s.d16;
+    }
     static __device__ __forceinline__ void lane(const float (&x)[16], int j, int lane_id, KScratch &s) {
         uint32_t L[4] = {0, 0, 0, 0};
         float isc_best;
@@ -451,23 +480,19 @@ template <> struct KQuant<T_Q6K> {
         s.a[j] = (uint8_t)(int8_t)sc;
         if (j == 0) { s.d16 = d16; s.dmin16 = 0; s.zero = zero ? 1u : 0u; }
     }
-    static __device__ __forceinline__ uint32_t byte(const KScratch &s, int o) {
-        if (s.zero) return 0;
-        if (o < 128) {  // ql
-            const int n = o >> 6, r = o & 63, l = r & 31, e = 128 * n + l + (r >= 32 ? 32 : 0);
-            return (s.L[e] & 15) | ((s.L[e + 64] & 15) << 4);
-        }
-        if (o < 192) {  // qh
-            const int t = o - 128, n = t >> 5, l = t & 31, e = 128 * n + l;
-            return (s.L[e] >> 4) | ((s.L[e + 32] >> 4) << 2) | ((s.L[e + 64] >> 4) << 4) | ((s.L[e + 96] >> 4) << 6);
-        }
-        if (o < 208) return s.a[o - 192];
-        return (s.d16 >> (8 * (o - 208))) & 0xFF;
-    }
 };
 
 template <> struct KQuant<T_Q2K> {
     static constexpr int SUB = 16;
+    static constexpr int WORDS = 21;
+    static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
+        if (w < 4) return *reinterpret_cast<const uint32_t *>(&s.a[4 * w]);
+        if (w < 20) {
+            const int t = w - 4, n = t >> 3, jj = t & 7, base = 32 * n + jj;
+            return code_word(s, base) | (code_word(s, base + 8) << 2) | (code_word(s, base + 16) << 4) | (code_word(s, base + 24) << 6);
+        }
+        return (uint32_t)s.d16 | ((uint32_t)s.dmin16 << 16);
+    }
     static __device__ __forceinline__ void lane(const float (&x)[16], int j, int, KScratch &s) {
         float w[16];
 #pragma unroll
@@ -506,19 +531,32 @@ template <> struct KQuant<T_Q2K> {
         s.a[j] = (uint8_t)b;
         if (j == 0) { s.d16 = d16; s.dmin16 = dmin16; s.zero = 0; }
     }
-    static __device__ __forceinline__ uint32_t byte(const KScratch &s, int o) {
-        if (o < 16) return s.a[o];
-        if (o < 80) {
-            const int t = o - 16, n = t >> 5, l = t & 31, e = 128 * n + l;
-            return s.L[e] | (s.L[e + 32] << 2) | (s.L[e + 64] << 4) | (s.L[e + 96] << 6);
-        }
-        if (o < 82) return (s.d16 >> (8 * (o - 80))) & 0xFF;
-        return (s.dmin16 >> (8 * (o - 82))) & 0xFF;
-    }
 };
 
 template <> struct KQuant<T_Q3K> {
     static constexpr int SUB = 16;
+    static constexpr int WORDS = 0, HALVES = 55;  // 110 bytes -> 16-bit units
+    static __device__ __forceinline__ uint32_t half(const KScratch &s, int h) {
+        const uint16_t *Lh = reinterpret_cast<const uint16_t *>(s.L), *Ah = reinterpret_cast<const uint16_t *>(s.a);
+        if (h < 16) {  // hmask: bit bq of byte o = (code[32 bq + o] > 3) = bit 2 of a 3-bit code
+            uint32_t m = 0;
+#pragma unroll
+            for (int bq = 0; bq < 8; bq++) m |= ((Lh[16 * bq + h] >> 2) & 0x0101u) << bq;
+            return m;
+        }
+        if (h < 48) {
+            const int t = 2 * (h - 16), n = t >> 5, e = 128 * n + (t & 31);
+            return (Lh[e >> 1] & 0x0303u) | ((Lh[(e + 32) >> 1] & 0x0303u) << 2) | ((Lh[(e + 64) >> 1] & 0x0303u) << 4) | ((Lh[(e + 96) >> 1] & 0x0303u) << 6);
+        }
+        if (h < 54) {
+            const int k = 2 * (h - 48);
+            if (k < 8) return (Ah[k >> 1] & 0x0F0Fu) | ((Ah[(k + 8) >> 1] & 0x0F0Fu) << 4);
+            const int r = k - 8;
+            return ((Ah[r >> 1] >> 4) & 0x0303u) | (((Ah[(r + 4) >> 1] >> 4) & 0x0303u) << 2) | (((Ah[(r + 8) >> 1] >> 4) & 0x0303u) << 4) |
+                   (((Ah[(r + 12) >> 1] >> 4) & 0x0303u) << 6);
+        }
+        return s.d16;
+    }
     static __device__ __forceinline__ void lane(const float (&x)[16], int j, int lane_id, KScratch &s) {
         uint32_t L[4];
         const float scale = make_q3_quants16(x, 4, L);
@@ -545,25 +583,6 @@ template <> struct KQuant<T_Q3K> {
         put_codes<16>(s, j, L);
         s.a[j] = (uint8_t)c;
         if (j == 0) { s.d16 = d16; s.dmin16 = 0; s.zero = 0; }
-    }
-    static __device__ __forceinline__ uint32_t byte(const KScratch &s, int o) {
-        if (o < 32) {  // hmask
-            uint32_t h = 0;
-#pragma unroll
-            for (int bq = 0; bq < 8; bq++) h |= (uint32_t)(s.L[32 * bq + o] > 3) << bq;
-            return h;
-        }
-        if (o < 96) {
-            const int t = o - 32, n = t >> 5, l = t & 31, e = 128 * n + l;
-            return (s.L[e] & 3) | ((s.L[e + 32] & 3) << 2) | ((s.L[e + 64] & 3) << 4) | ((s.L[e + 96] & 3) << 6);
-        }
-        if (o < 108) {
-            const int k = o - 96;
-            if (k < 8) return (s.a[k] & 0xF) | ((s.a[k + 8] & 0xF) << 4);
-            const int r = k - 8;
-            return (s.a[r] >> 4) | ((s.a[r + 4] >> 4) << 2) | ((s.a[r + 8] >> 4) << 4) | ((s.a[r + 12] >> 4) << 6);
-        }
-        return (s.d16 >> (8 * (o - 108))) & 0xFF;
     }
 };
 
@@ -658,7 +677,15 @@ quant_k_kernel(const typename FT::raw *__restrict__ src, uint8_t *__restrict__ d
         }
         KQ::lane(x, j, lane, scratch[warp][sbi]);
         __syncwarp();
-        for (int o = lane; o < nsb * BYTES; o += 32) outb[warp][o] = (uint8_t)KQ::byte(scratch[warp][o / BYTES], o % BYTES);
+        if constexpr (KQ::WORDS > 0) {
+            static_assert(KQ::WORDS == 0 || KQ::WORDS * 4 == BYTES, "word() covers the whole block");
+            uint32_t *outw = reinterpret_cast<uint32_t *>(outb[warp]);
+            for (int w = lane; w < nsb * KQ::WORDS; w += 32) outw[w] = KQ::word(scratch[warp][w / KQ::WORDS], w % KQ::WORDS);
+        } else {
+            static_assert(KQ::HALVES * 2 == BYTES, "half() covers the whole block");
+            uint16_t *outh = reinterpret_cast<uint16_t *>(outb[warp]);
+            for (int h = lane; h < nsb * KQ::HALVES; h += 32) outh[h] = (uint16_t)KQ::half(scratch[warp][h / KQ::HALVES], h % KQ::HALVES);
+        }
         __syncwarp();
         cta_copy_s2g(dst + sb0 * BYTES, outb[warp], (uint32_t)(nsb * BYTES), lane, 32);
         __syncwarp();
