@@ -329,6 +329,35 @@ template <int G> __device__ __forceinline__ float group_max_by_abs(float v, int 
     return acc;
 }
 
+// ---- n / d for the 16 or 32 numerators of a sub-block that share one divisor ------------------------------------
+// Upstream requantizes with `nearest_int((x + dm) / d)`: an IEEE division per element, ~18 instructions each the way
+// the compiler expands it (reciprocal, two refinements, residual, range check).  With one divisor per sub-block the
+// reciprocal is computed once, correctly rounded (`rcp.rn`), and Markstein's sequence gives the correctly rounded
+// quotient in three operations:  q0 = RN(n r);  e = n - d q0 (exact, one FMA);  q = RN(q0 + e r)  —  the same value
+// `div.rn` returns, PROVIDED nothing under- or overflows on the way: d is taken in 2^-40 .. 2^40 and |n| <= 2^60; if
+// the exact residual is too small to be represented then |q0| < 2^-63 and the caller's nearest_int() is 0 for any
+// last-bit error.  Everything else takes `div.rn`.
+struct SharedDivisor {
+    float d, r;
+    bool ok;
+};
+__device__ __forceinline__ SharedDivisor shared_divisor(float d) {
+    SharedDivisor sd;
+    const float a = fabsf(d);
+    sd.d = d;
+    sd.ok = a >= 9.094947017729282e-13f && a <= 1.099511627776e12f;  // 2^-40 .. 2^40 (false for NaN)
+    sd.r = __frcp_rn(d);
+    return sd;
+}
+__device__ __forceinline__ float div_shared(float n, const SharedDivisor &sd) {
+    if (sd.ok && fabsf(n) <= 1.152921504606846976e18f) {  // 2^60
+        const float q0 = __fmul_rn(n, sd.r);
+        const float e = __fmaf_rn(-sd.d, q0, n);
+        return __fmaf_rn(e, sd.r, q0);
+    }
+    return __fdiv_rn(n, sd.d);
+}
+
 // ---- per-type quantizers ---------------------------------------------------------------------------
 // Scratch written by the lanes of one super-block, read by the bytewise assembler.
 struct KScratch {
@@ -371,9 +400,10 @@ template <int NMAX> __device__ __forceinline__ void k45_lane(const float (&x)[32
         const float dm = h2f(dmin16) * (float)lm;
 #pragma unroll
         for (int k = 0; k < 8; k++) L[k] = 0;
+        const SharedDivisor sd = shared_divisor(d);
 #pragma unroll
         for (int ii = 0; ii < 32; ++ii) {
-            int l = nearest_int((x[ii] + dm) / d);
+            int l = nearest_int(div_shared(x[ii] + dm, sd));
             l = max(0, min(NMAX, l));
             set_code(L, ii, l);
         }
@@ -466,9 +496,10 @@ template <> struct KQuant<T_Q6K> {
             sc = min(127, nearest_int(iscale * scale));
             const float d = h2f(d16) * (float)(int)(int8_t)sc;
             if (d != 0.f) {
+                const SharedDivisor sd = shared_divisor(d);
 #pragma unroll
                 for (int ii = 0; ii < 16; ++ii) {
-                    int l = nearest_int(x[ii] / d);
+                    int l = nearest_int(div_shared(x[ii], sd));
                     l = max(-32, min(31, l));
                     set_code(L, ii, l + 32);
                 }
@@ -518,9 +549,10 @@ template <> struct KQuant<T_Q2K> {
             const float dm = h2f(dmin16) * (float)(b >> 4);
 #pragma unroll
             for (int k = 0; k < 4; k++) L[k] = 0;
+            const SharedDivisor sd = shared_divisor(d);
 #pragma unroll
             for (int ii = 0; ii < 16; ++ii) {
-                int l = nearest_int((x[ii] + dm) / d);
+                int l = nearest_int(div_shared(x[ii] + dm, sd));
                 l = max(0, min(3, l));
                 set_code(L, ii, l);
             }
@@ -573,9 +605,10 @@ template <> struct KQuant<T_Q3K> {
         if (d != 0.f) {
 #pragma unroll
             for (int k = 0; k < 4; k++) L[k] = 0;
+            const SharedDivisor sd = shared_divisor(d);
 #pragma unroll
             for (int ii = 0; ii < 16; ++ii) {
-                int l = nearest_int(x[ii] / d);
+                int l = nearest_int(div_shared(x[ii], sd));
                 l = max(-4, min(3, l));
                 set_code(L, ii, l + 4);
             }

@@ -30,6 +30,14 @@ def test_tensor_ops_planner_no_gpu(ggq):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_shared_divisor_division_is_correctly_rounded():
+    """tests/cpp/test_shared_divisor.c: the three-operation division of quant_k.cu (div_shared) returns the bits of n / d."""
+    exe = os.path.join(ROOT, "tests", "cpp", "test_shared_divisor")
+    subprocess.check_call(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_shared_divisor.c"), "-lm"])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_cpp_mirror_reference_unit_tests(ggq):
     build(ggq)
