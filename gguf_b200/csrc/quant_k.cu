@@ -432,11 +432,11 @@ __device__ __forceinline__ uint32_t code_word(const KScratch &s, int w) { return
 // Types whose block is a whole number of 32-bit words also provide word(s, w), the w-th little-endian word of the
 // packed block: the assembler then runs one iteration per four output bytes (the bytewise assembler this replaced
 // cost ~25 instructions and 2-4 dependent one-byte shared loads per output byte; that phase was 5 % of the executed
-// instructions but 10 % of the stall samples of the Q4K kernel).  Q3K / Q6K blocks (110 / 210 bytes) are assembled in
-// 16-bit units with half(s, h) instead.
+// instructions but 10 % of the stall samples of the Q4K kernel).  Q3K / Q6K blocks (110 / 210 bytes) end in a 16-bit delta,
+// returned by tail(s).
 template <> struct KQuant<T_Q4K> {
     static constexpr int SUB = 32;
-    static constexpr int WORDS = 36;
+    static constexpr int WORDS = 36, TAIL = 0;
     static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
         if (w < 4) return k45_header_word(s, w);
         const int t = w - 4, p = t >> 3, jj = t & 7;
@@ -446,7 +446,7 @@ template <> struct KQuant<T_Q4K> {
 };
 template <> struct KQuant<T_Q5K> {
     static constexpr int SUB = 32;
-    static constexpr int WORDS = 44;
+    static constexpr int WORDS = 44, TAIL = 0;
     static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
         if (w < 4) return k45_header_word(s, w);
         if (w < 12) {  // qh: bit 2p / 2p+1 of byte l = fifth bit of elements 64p+l / 64p+32+l
@@ -465,22 +465,21 @@ template <> struct KQuant<T_Q5K> {
 
 template <> struct KQuant<T_Q6K> {
     static constexpr int SUB = 16;
-    static constexpr int WORDS = 0, HALVES = 105;  // 210 bytes: not a whole number of words -> 16-bit units
-    static __device__ __forceinline__ uint32_t half(const KScratch &s, int h) {
+    static constexpr int WORDS = 52, TAIL = 1;  // 210 bytes = 52 words (ql 32, qh 16, scales 4) + the 16-bit delta
+    static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
         if (s.zero) return 0;
-        const uint16_t *Lh = reinterpret_cast<const uint16_t *>(s.L);
-        if (h < 64) {  // ql
-            const int o = 2 * h, n = o >> 6, r = o & 63, e = 128 * n + (r & 31) + (r >= 32 ? 32 : 0);
-            return (Lh[e >> 1] & 0x0F0Fu) | ((Lh[(e + 64) >> 1] & 0x0F0Fu) << 4);
+        if (w < 32) {  // ql
+            const int i = 32 * (w >> 4) + (w & 15);
+            return (code_word(s, i) & 0x0F0F0F0Fu) | ((code_word(s, i + 16) & 0x0F0F0F0Fu) << 4);
         }
-        if (h < 96) {  // qh
-            const int t = 2 * (h - 64), n = t >> 5, e = 128 * n + (t & 31);
-            return ((Lh[e >> 1] >> 4) & 0x0303u) | (((Lh[(e + 32) >> 1] >> 4) & 0x0303u) << 2) | (((Lh[(e + 64) >> 1] >> 4) & 0x0303u) << 4) |
-                   (((Lh[(e + 96) >> 1] >> 4) & 0x0303u) << 6);
+        if (w < 48) {  // qh
+            const int jj = w - 32, i = 32 * (jj >> 3) + (jj & 7);
+            return ((code_word(s, i) >> 4) & 0x03030303u) | (((code_word(s, i + 8) >> 4) & 0x03030303u) << 2) |
+                   (((code_word(s, i + 16) >> 4) & 0x03030303u) << 4) | (((code_word(s, i + 24) >> 4) & 0x03030303u) << 6);
         }
-        if (h < 104) return reinterpret_cast<const uint16_t *>(s.a)[h - 96];
-        return s.d16;
+        return *reinterpret_cast<const uint32_t *>(&s.a[4 * (w - 48)]);
     }
+    static __device__ __forceinline__ uint32_t tail(const KScratch &s) { return s.zero ? 0u : (uint32_t)s.d16; }
     static __device__ __forceinline__ void lane(const float (&x)[16], int j, int lane_id, KScratch &s) {
         uint32_t L[4] = {0, 0, 0, 0};
         float isc_best;
@@ -515,7 +514,7 @@ template <> struct KQuant<T_Q6K> {
 
 template <> struct KQuant<T_Q2K> {
     static constexpr int SUB = 16;
-    static constexpr int WORDS = 21;
+    static constexpr int WORDS = 21, TAIL = 0;
     static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
         if (w < 4) return *reinterpret_cast<const uint32_t *>(&s.a[4 * w]);
         if (w < 20) {
@@ -567,28 +566,24 @@ template <> struct KQuant<T_Q2K> {
 
 template <> struct KQuant<T_Q3K> {
     static constexpr int SUB = 16;
-    static constexpr int WORDS = 0, HALVES = 55;  // 110 bytes -> 16-bit units
-    static __device__ __forceinline__ uint32_t half(const KScratch &s, int h) {
-        const uint16_t *Lh = reinterpret_cast<const uint16_t *>(s.L), *Ah = reinterpret_cast<const uint16_t *>(s.a);
-        if (h < 16) {  // hmask: bit bq of byte o = (code[32 bq + o] > 3) = bit 2 of a 3-bit code
+    static constexpr int WORDS = 27, TAIL = 1;  // 110 bytes = 27 words (hmask 8, qs 16, scales 3) + the 16-bit delta
+    static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
+        if (w < 8) {  // hmask: bit bq of byte o = (code[32 bq + o] > 3) = bit 2 of a 3-bit code
             uint32_t m = 0;
 #pragma unroll
-            for (int bq = 0; bq < 8; bq++) m |= ((Lh[16 * bq + h] >> 2) & 0x0101u) << bq;
+            for (int bq = 0; bq < 8; bq++) m |= ((code_word(s, 8 * bq + w) >> 2) & 0x01010101u) << bq;
             return m;
         }
-        if (h < 48) {
-            const int t = 2 * (h - 16), n = t >> 5, e = 128 * n + (t & 31);
-            return (Lh[e >> 1] & 0x0303u) | ((Lh[(e + 32) >> 1] & 0x0303u) << 2) | ((Lh[(e + 64) >> 1] & 0x0303u) << 4) | ((Lh[(e + 96) >> 1] & 0x0303u) << 6);
+        if (w < 24) {
+            const int jj = w - 8, i = 32 * (jj >> 3) + (jj & 7);
+            return (code_word(s, i) & 0x03030303u) | ((code_word(s, i + 8) & 0x03030303u) << 2) | ((code_word(s, i + 16) & 0x03030303u) << 4) |
+                   ((code_word(s, i + 24) & 0x03030303u) << 6);
         }
-        if (h < 54) {
-            const int k = 2 * (h - 48);
-            if (k < 8) return (Ah[k >> 1] & 0x0F0Fu) | ((Ah[(k + 8) >> 1] & 0x0F0Fu) << 4);
-            const int r = k - 8;
-            return ((Ah[r >> 1] >> 4) & 0x0303u) | (((Ah[(r + 4) >> 1] >> 4) & 0x0303u) << 2) | (((Ah[(r + 8) >> 1] >> 4) & 0x0303u) << 4) |
-                   (((Ah[(r + 12) >> 1] >> 4) & 0x0303u) << 6);
-        }
-        return s.d16;
+        const uint32_t *A = reinterpret_cast<const uint32_t *>(s.a);  // 16 six-bit scale codes
+        if (w < 26) return (A[w - 24] & 0x0F0F0F0Fu) | ((A[w - 22] & 0x0F0F0F0Fu) << 4);
+        return ((A[0] >> 4) & 0x03030303u) | (((A[1] >> 4) & 0x03030303u) << 2) | (((A[2] >> 4) & 0x03030303u) << 4) | (((A[3] >> 4) & 0x03030303u) << 6);
     }
+    static __device__ __forceinline__ uint32_t tail(const KScratch &s) { return s.d16; }
     static __device__ __forceinline__ void lane(const float (&x)[16], int j, int lane_id, KScratch &s) {
         uint32_t L[4];
         const float scale = make_q3_quants16(x, 4, L);
@@ -710,14 +705,25 @@ quant_k_kernel(const typename FT::raw *__restrict__ src, uint8_t *__restrict__ d
         }
         KQ::lane(x, j, lane, scratch[warp][sbi]);
         __syncwarp();
-        if constexpr (KQ::WORDS > 0) {
-            static_assert(KQ::WORDS == 0 || KQ::WORDS * 4 == BYTES, "word() covers the whole block");
-            uint32_t *outw = reinterpret_cast<uint32_t *>(outb[warp]);
-            for (int w = lane; w < nsb * KQ::WORDS; w += 32) outw[w] = KQ::word(scratch[warp][w / KQ::WORDS], w % KQ::WORDS);
-        } else {
-            static_assert(KQ::HALVES * 2 == BYTES, "half() covers the whole block");
-            uint16_t *outh = reinterpret_cast<uint16_t *>(outb[warp]);
-            for (int h = lane; h < nsb * KQ::HALVES; h += 32) outh[h] = (uint16_t)KQ::half(scratch[warp][h / KQ::HALVES], h % KQ::HALVES);
+        {   // assemble the packed blocks: one 32-bit word (plus, for the 110- / 210-byte blocks, one trailing 16-bit
+            // delta) per lane and iteration; odd Q3K / Q6K blocks start 2 bytes off a word boundary
+            constexpr int U = KQ::WORDS + KQ::TAIL;
+            static_assert(KQ::WORDS * 4 + KQ::TAIL * 2 == BYTES, "word() / tail() cover the whole block");
+            for (int u = lane; u < nsb * U; u += 32) {
+                const int sb = u / U, k = u % U;
+                uint8_t *o = outb[warp] + sb * BYTES + 4 * k;
+                if (KQ::TAIL && k == KQ::WORDS) {
+                    if constexpr (KQ::TAIL != 0) *reinterpret_cast<uint16_t *>(o) = (uint16_t)KQ::tail(scratch[warp][sb]);
+                } else {
+                    const uint32_t v = KQ::word(scratch[warp][sb], k);
+                    if (KQ::TAIL && (sb & 1)) {
+                        *reinterpret_cast<uint16_t *>(o) = (uint16_t)v;
+                        *reinterpret_cast<uint16_t *>(o + 2) = (uint16_t)(v >> 16);
+                    } else {
+                        *reinterpret_cast<uint32_t *>(o) = v;
+                    }
+                }
+            }
         }
         __syncwarp();
         cta_copy_s2g(dst + sb0 * BYTES, outb[warp], (uint32_t)(nsb * BYTES), lane, 32);
