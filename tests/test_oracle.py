@@ -120,3 +120,28 @@ def test_f16c_mediation_equals_software(oracle):
     blocks = np.random.default_rng(3).integers(0, 256, 34 * 4096, dtype=np.uint8)
     y32 = oracle.dequantize(8, 0, blocks)
     assert np.array_equal(oracle.dequantize(8, 1, blocks), oracle.quantize(1, 0, y32).view(np.uint16))  # hw narrow == software narrow
+
+
+@pytest.mark.parametrize("ty", [10, 11, 12, 13, 14])
+def test_kquant_quantize_matches_independent_numpy_restatement(oracle, ty):
+    """K-quant quantize has no reference arithmetic to pin it (todo!() in structs/q{2..6}_k.rs): the C oracle must at
+    least agree, byte for byte, with a second restatement of upstream's published algorithm written independently in
+    numpy (tests/kquant_numpy.py) — Gaussian, heavy-tailed, mixed-magnitude, constant, all-zero and tiny super-blocks."""
+    from kquant_numpy import QUANTIZERS
+    rng = np.random.default_rng(1234 + ty)
+    parts = [
+        (rng.standard_normal(256 * 96) * 0.02).astype(np.float32),
+        (rng.standard_t(3, 256 * 48) * 0.02).astype(np.float32),
+        (rng.standard_normal(256 * 24) * np.repeat(10.0 ** rng.integers(-6, 3, 24 * 16), 16)).astype(np.float32),
+        rng.random(256 * 8, dtype=np.float32),                       # all positive: min clamps to 0
+        np.full(256 * 2, 0.37, np.float32),                          # max == min
+        np.zeros(256 * 2, np.float32),
+        (rng.standard_normal(256 * 4) * 1e-12).astype(np.float32),
+        (rng.standard_normal(256 * 8) * 0.02).astype(np.float16).astype(np.float32),   # f16-representable inputs
+    ]
+    x = np.concatenate(parts)
+    got = oracle.quantize(ty, oracle.F32, x)
+    want = QUANTIZERS[ty](x)
+    _, b = oracle.block_info(ty)
+    bad = np.flatnonzero((got.reshape(-1, b) != want.reshape(-1, b)).any(axis=1))
+    assert bad.size == 0, f"{bad.size} of {x.size // 256} super-blocks differ, first at {bad[:5]}"
