@@ -28,13 +28,17 @@ namespace ggq {
 //                  reaches 6.3 TB/s; the decoders follow: 6.3-6.6 TB/s (96-101 % of the measured copy peak) on
 //                  58.7 M elements against 5.7-5.9 TB/s for the ring.  Needs a few waves of CTAs to overlap.
 //   RING (MODE 0)  persistent CTAs with a STAGES-deep bulk-copy ring: still the better shape for small tensors
-//                  (less than ~2 waves of tiles), where ONE's CTAs would all load and then all store in step.
+//                  (less than ~2 waves of tiles), where ONE's CTAs would all load and then all store in step.  Small
+//                  tiles (4096 elements) and small CTAs (128 threads, 8 per SM) balance these 3-9 us launches best.
 template <int TILE_, int STAGES_, int THREADS_, int MINB_, int MODE_> struct DqCfg {
     static constexpr int TILE = TILE_, STAGES = STAGES_, THREADS = THREADS_, MINB = MINB_, MODE = MODE_;
 };
 using Ring8k3 = DqCfg<8192, 3, 256, 3, 0>;
 using Ring8k2 = DqCfg<8192, 2, 256, 3, 0>;
 using Ring16k3 = DqCfg<16384, 3, 256, 3, 0>;
+using Ring4k3x128 = DqCfg<4096, 3, 128, 8, 0>;   // small CTAs, 8 per SM: +3..5 % on 8-24 Mi-element tensors (r01_dq_sweep_ring_small.txt)
+using Ring4k3x256 = DqCfg<4096, 3, 256, 4, 0>;   // best below ~6 Mi elements
+using Ring8k3x128 = DqCfg<8192, 3, 128, 6, 0>;
 using One16k8 = DqCfg<16384, 1, 128, 8, 1>;
 using One16k9 = DqCfg<16384, 1, 128, 9, 1>;
 using One16k10 = DqCfg<16384, 1, 128, 10, 1>;
@@ -52,9 +56,12 @@ template <> struct DqOneBig<T_Q2K> { using type = One16k12; };
 template <> struct DqOneBig<T_Q3K> { using type = One16k9; };
 template <> struct DqOneBig<T_Q4K> { using type = One16k10; };
 template <> struct DqOneBig<T_Q5K> { using type = One16k9; };
-// small tensors that stay on the ring
-template <uint32_t T> struct DqRingSmall { using type = Ring8k3; };
+// small tensors that stay on the ring (16-bit output, 6 Mi elements and up)
+template <uint32_t T> struct DqRingSmall { using type = Ring4k3x128; };
 template <> struct DqRingSmall<T_Q6K> { using type = Ring16k3; };
+template <> struct DqRingSmall<T_Q8_0> { using type = Ring8k3x128; };
+template <> struct DqRingSmall<T_Q8_1> { using type = Ring8k3x128; };
+template <> struct DqRingSmall<T_Q8K> { using type = Ring8k3x128; };
 
 template <uint32_t T, class FT, class CFG>
 static cudaError_t launch_dequant_cfg(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
@@ -83,12 +90,9 @@ static cudaError_t launch_dequant(const void *src, void *dst, size_t nblocks, cu
         return launch_dequant_cfg<T, FT, Ring8k3>(src, dst, nblocks, stream, dev);
     } else {
         if (n >= (is_k2345<T>() ? 32 : 24) * Mi) return launch_dequant_cfg<T, FT, typename DqOneBig<T>::type>(src, dst, nblocks, stream, dev);
-        if constexpr (is_q8_family<T>()) {
-            if (n >= 6 * Mi) return launch_dequant_cfg<T, FT, One8k8>(src, dst, nblocks, stream, dev);
-            return launch_dequant_cfg<T, FT, One4k10>(src, dst, nblocks, stream, dev);
-        } else {
-            return launch_dequant_cfg<T, FT, typename DqRingSmall<T>::type>(src, dst, nblocks, stream, dev);
-        }
+        if (n >= 6 * Mi) return launch_dequant_cfg<T, FT, typename DqRingSmall<T>::type>(src, dst, nblocks, stream, dev);
+        if constexpr (T == T_Q6K) return launch_dequant_cfg<T, FT, Ring4k3x128>(src, dst, nblocks, stream, dev);
+        else return launch_dequant_cfg<T, FT, Ring4k3x256>(src, dst, nblocks, stream, dev);
     }
 }
 

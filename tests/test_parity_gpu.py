@@ -329,7 +329,7 @@ def _big_dequant_sizes(ty, fdt):
         return [12 * mi, 6 * mi]                    # One8k8, One4k10
     sizes = [(32 if ty in (10, 11, 12, 13) else 24) * mi]   # DqOneBig<T>
     if ty in (8, 9, 15):
-        sizes.append(6 * mi)                        # One8k8 for the Q8 family
+        sizes.append(6 * mi)                        # the Q8 family's own small-tensor ring (8192 x 3 stages x 128 threads)
     return sizes
 
 

@@ -186,7 +186,19 @@ int main(int argc, char **argv) {
 #else
 #define SWEEP_A(T, NAME, N)
 #endif
-#if SWEEP_SET == 6
+#if SWEEP_SET == 7
+// ring (MODE 0) with small CTAs and forced occupancy, for small tensors
+#define SWEEP_B(T, NAME, N)                    \
+    V(T, NAME, N, 8192, 3, 256, 3, 0, 0);      \
+    V(T, NAME, N, 8192, 3, 128, 8, 0, 0);      \
+    V(T, NAME, N, 8192, 2, 128, 8, 0, 0);      \
+    V(T, NAME, N, 4096, 3, 128, 8, 0, 0);      \
+    V(T, NAME, N, 4096, 4, 128, 10, 0, 0);     \
+    V(T, NAME, N, 8192, 3, 128, 6, 0, 0);      \
+    V(T, NAME, N, 4096, 3, 64, 16, 0, 0);      \
+    V(T, NAME, N, 8192, 4, 256, 4, 0, 0);      \
+    V(T, NAME, N, 4096, 3, 256, 4, 0, 0);
+#elif SWEEP_SET == 6
 // MODE 3: 2-4 consecutive tiles per short-lived CTA, all bulk copies issued up front
 #define SWEEP_B(T, NAME, N)                    \
     V(T, NAME, N, 8192, 3, 256, 3, 0, 0);      \
