@@ -361,6 +361,39 @@ def test_big_tensor_decoder_shapes_bit_exact(ggq, oracle, ty, fdt):
             del src, d
 
 
+@pytest.mark.parametrize("fdt", FDTS)
+@pytest.mark.parametrize("ty", LEGACY + [15])
+def test_big_tensor_legacy_quantize_bit_exact(ggq, oracle, ty, fdt):
+    """The short-lived-CTA quantize kernels (two 64-row tiles per CTA from 16-bit input, one 128-row tile from f32,
+    straight-line path for full aligned tiles) on a grid of tens of thousands of CTAs: 4 Mi elements plus a ragged
+    tail, heavy-tailed values with NaN / inf / zero rows mixed in, at aligned and element-offset device pointers,
+    with guard zones."""
+    import torch
+    n, b = oracle.block_info(ty)
+    nb = (4 << 20) // n + (7 if n == 32 else 3)
+    rng = np.random.default_rng(4000 + ty)
+    x = (rng.standard_t(3, n * nb) * 0.02).astype(np.float32)
+    x[rng.integers(0, x.size, 400)] = np.nan
+    x[rng.integers(0, x.size, 100)] = np.inf
+    x[rng.integers(0, x.size, 100)] = -np.inf
+    zr = rng.integers(0, nb, 50)
+    x.reshape(nb, n)[zr] = 0.0
+    x = to_fdt(x, fdt)
+    want = oracle.quantize(ty, fdt, x, threads=16)
+    st = torch.cuda.current_stream().cuda_stream
+    G = 64
+    for off in (0, 4 if fdt == F32 else 2):
+        src = torch.zeros(x.nbytes + 2 * G, dtype=torch.uint8, device="cuda")
+        src[G + off:G + off + x.nbytes] = torch.from_numpy(x.view(np.uint8)).cuda()
+        q = torch.full((nb * b + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        ggq.quantize_slice_device(ty, fdt, q.data_ptr() + G + off, nb, src.data_ptr() + G + off, n * nb, st)
+        torch.cuda.synchronize()
+        gq = q.cpu().numpy()
+        assert same_blocks(gq[G + off:G + off + nb * b], want, ty, b)
+        assert (gq[:G + off] == 0xA5).all() and (gq[G + off + nb * b:] == 0xA5).all(), "quantize wrote outside dst"
+        del src, q
+
+
 def test_host_api_rejects_device_pointers(ggq):
     import ctypes, torch
     from gguf_b200._lib import lib
