@@ -270,6 +270,31 @@ def ours(args, rank, world, local_rank):
         per_kernel.append({"kernel": f"dequant_kernel<{NAMES[w['ty']]},f16>", "shape": w["shape"], "us": ms * 1e3,
                            "GBps": w["bytes"] / (ms * 1e-3) / 1e9, "bytes": w["bytes"], "launches_timed": R})
         del sets
+    # ---- informational: the quantize direction of the same four types on the FFN shape (f16 -> packed), same method.
+    # BASELINE.json's metric names both directions; `value` and `roofline` stay the dequantize workload's. ----
+    quant_per_kernel = []
+    if rank == 0:
+        ffn = [w for w in work if w["shape"] == "ffn"]
+        xs = [(torch.randn(ffn[0]["n"], device=dev) * 0.02).to(torch.float16) for _ in range(3)]
+        for w in ffn:
+            outs = [torch.empty_like(w["packed"]) for _ in range(3)]
+            rq = 6 if w["ty"] in (g.Q4K, g.Q6K) else R
+            for i in range(3):
+                g.quantize_slice_device(w["ty"], F16, outs[i], w["nb"], xs[i], w["n"], stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(rq):
+                g.quantize_slice_device(w["ty"], F16, outs[i % 3], w["nb"], xs[i % 3], w["n"], stream)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / rq
+            launches += rq + 3
+            quant_per_kernel.append({"kernel": f"quantize<{NAMES[w['ty']]},f16>", "shape": "ffn", "us": ms * 1e3,
+                                     "GBps": w["bytes"] / (ms * 1e-3) / 1e9, "bytes": w["bytes"], "launches_timed": rq,
+                                     "bound": "fp32 issue (bit-faithful scale search)" if w["ty"] in (g.Q4K, g.Q6K) else "hbm"})
+            del outs
+        del xs
     clocks = sampler.stop()
     dom = max(per_kernel, key=lambda r: r["us"])
     peak, peak_src = measured_peak()
@@ -354,7 +379,7 @@ def ours(args, rank, world, local_rank):
                        "l2": "per-step footprint (packed+f16 of 8 tensors = %.0f MB) exceeds the 126 MB L2; no flush needed" % (step_bytes / 1e6),
                        "sharding": "by tensor, one replica of the workload per GPU, no collective", "cpu_binding_rank0": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "frac_of_peak_whole_step": value / world / peak, "per_kernel": per_kernel,
+            "frac_of_peak_whole_step": value / world / peak, "per_kernel": per_kernel, "quant_per_kernel": quant_per_kernel,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
