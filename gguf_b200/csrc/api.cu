@@ -390,12 +390,7 @@ int run_jobs_io(const std::vector<ChainJob> &jobs) {
     return GGQ_OK;
 }
 
-// Runs one cast chain over `n_elems` elements: chunks flow through NSLOTS (stream, device ping-pong,
-// pinned in/out) slots so H2D(c+1), kernels(c) and D2H(c-1) overlap; intermediates of a multi-hop chain
-// never leave the device.  `io` supplies and consumes the bytes:
-//   direct_src / direct_dst  non-null => pinned caller memory, DMA straight from / to it;
-//   otherwise read(pinned, byte_off, nbytes) fills a pinned bounce buffer and
-//   write(pinned, byte_off, nbytes) drains one (memcpy for pageable memory, pread/pwrite for files).
+// One job through run_jobs_io.
 int run_chain_io(const std::vector<uint32_t> &chain, size_t n_elems, const ggq::ChainIO &io) {
     if (n_elems == 0) return GGQ_OK;
     std::vector<ChainJob> jobs(1);
@@ -426,10 +421,10 @@ int run_chain_host(const std::vector<uint32_t> &chain, void *dst, const void *sr
         memmove(dst, src, type_nbytes(chain.front(), n_elems));
         return GGQ_OK;
     }
-    const cudaMemoryType ks = pointer_kind(src), kd = pointer_kind(dst);
-    if (ks == cudaMemoryTypeDevice || kd == cudaMemoryTypeDevice)
-        return fail(GGQ_ERR_INVALID, "device pointer passed to a host-pointer entry point (use the *_device variants)");
-    const bool pin_src = ks == cudaMemoryTypeHost, pin_dst = kd == cudaMemoryTypeHost;
+    ggq::ChainIO whole;
+    int rc0 = make_mem_io(dst, src, &whole);  // rejects device pointers, notes which side is pinned
+    if (rc0 != GGQ_OK) return rc0;
+    const bool pin_src = whole.direct_src != nullptr, pin_dst = whole.direct_dst != nullptr;
     auto make_io = [&](size_t elem0) {  // the sub-tensor starting at element `elem0`
         const char *s0 = static_cast<const char *>(src) + type_nbytes(chain.front(), elem0);
         char *d0 = static_cast<char *>(dst) + type_nbytes(chain.back(), elem0);
