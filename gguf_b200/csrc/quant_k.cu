@@ -99,18 +99,24 @@ __device__ __forceinline__ float2 round_clamped2(float2 v, float lo, float hi) {
     return make_float2(rintf(c.x), rintf(c.y));
 }
 
-template <int N, bool USE_MAD>
-__device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const float (&w)[N], const int nmax, float &the_min, const float rmin,
-                                                  const float rdelta, const int nstep, float &isc_best, float &mn_best) {
+// The weights are a function of the element alone — |x| for Q2K, av_x + |x| for Q4K / Q5K — so they need not be kept
+// in registers across the search: WMODE 0 takes |x| as an operand modifier, WMODE 1 recomputes av + |x| with one packed
+// add wherever a pair is used (same operation, same bits), WMODE 2 reads the array `w` as upstream's signature does.
+// Q2K ships WMODE 0 (its 16 freed registers buy a seventh resident CTA per SM), Q4K / Q5K WMODE 2 (see k45_lane).
+template <int N, bool USE_MAD, int WMODE>
+__device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const float (&w)[N], const float av, const int nmax, float &the_min,
+                                                  const float rmin, const float rdelta, const int nstep, float &isc_best, float &mn_best) {
+    auto w1 = [&](int i) { return WMODE == 0 ? fabsf(x[i]) : WMODE == 1 ? av + fabsf(x[i]) : w[i]; };
     float mn = x[0], mx = x[0];
-    float sum_w = w[0];
+    float sum_w = w1(0);
     float sum_x = sum_w * x[0];
 #pragma unroll
     for (int i = 1; i < N; ++i) {
         if (x[i] < mn) mn = x[i];
         if (x[i] > mx) mx = x[i];
-        sum_w += w[i];
-        sum_x += w[i] * x[i];
+        const float wi = w1(i);
+        sum_w += wi;
+        sum_x += wi * x[i];
     }
     if (mn > 0) mn = 0;
     if (mx == mn) {  // L[i] = 0: iscale 0 reproduces that
@@ -119,9 +125,14 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
         mn_best = mn;
         return 0.f;
     }
-    float2 x2[N / 2], w2[N / 2];
+    float2 x2[N / 2];
 #pragma unroll
-    for (int k = 0; k < N / 2; ++k) { x2[k] = make_float2(x[2 * k], x[2 * k + 1]); w2[k] = make_float2(w[2 * k], w[2 * k + 1]); }
+    for (int k = 0; k < N / 2; ++k) x2[k] = make_float2(x[2 * k], x[2 * k + 1]);
+    auto w2 = [&](int k) {
+        if constexpr (WMODE == 0) return abs2(x2[k]);
+        else if constexpr (WMODE == 1) return __fadd2_rn(bcast2(av), abs2(x2[k]));
+        else return make_float2(w[2 * k], w[2 * k + 1]);
+    };
     const float fmax_l = (float)nmax;
     float iscale = fmax_l / (mx - mn);
     float scale = 1 / iscale;
@@ -137,7 +148,7 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
             const float2 l = round_clamped2(__fmul2_rn(__fadd2_rn(x2[k], nmn), isc2), 0.f, fmax_l);
             float2 d = __fadd2_rn(x2[k], affine2_two_roundings(l, -scale, -mn));
             d = USE_MAD ? abs2(d) : __fmul2_rn(d, d);
-            const float2 e = __fmul2_rn(w2[k], d);
+            const float2 e = __fmul2_rn(w2(k), d);
             best_mad += e.x;
             best_mad += e.y;
         }
@@ -151,7 +162,7 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
 #pragma unroll
             for (int k = 0; k < N / 2; ++k) {
                 lf[k] = round_clamped2(__fmul2_rn(__fadd2_rn(x2[k], nmn), isc2), 0.f, fmax_l);
-                const float2 wl = __fmul2_rn(w2[k], lf[k]);
+                const float2 wl = __fmul2_rn(w2(k), lf[k]);
                 const float2 wl2 = __fmul2_rn(wl, lf[k]), wlx = __fmul2_rn(wl, x2[k]);
                 sum_l += wl.x;
                 sum_l2 += wl2.x;
@@ -174,7 +185,7 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
             for (int k = 0; k < N / 2; ++k) {
                 float2 d = __fadd2_rn(x2[k], affine2_two_roundings(lf[k], -this_scale, -this_min));
                 d = USE_MAD ? abs2(d) : __fmul2_rn(d, d);
-                const float2 e = __fmul2_rn(w2[k], d);
+                const float2 e = __fmul2_rn(w2(k), d);
                 mad += e.x;
                 mad += e.y;
             }
@@ -381,12 +392,14 @@ template <int NMAX> __device__ __forceinline__ void k45_lane(const float (&x)[32
 #pragma unroll
     for (int l = 0; l < 32; ++l) sum_x2 += x[l] * x[l];
     const float av_x = sqrtf(sum_x2 / 32);
+    // weights kept in registers (WMODE 2): with 32-element sub-blocks a fifth CTA per SM would need <= 96 registers,
+    // which spills (measured: 940 vs 841 us for Q4K), and without it recomputing the weights is only extra work
     float w[32];
 #pragma unroll
     for (int l = 0; l < 32; ++l) w[l] = av_x + fabsf(x[l]);
     uint32_t L[8];
     float the_min, isc_best, mn_best;
-    const float scale = make_qkx2_quants<32, false>(x, w, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best);
+    const float scale = make_qkx2_quants<32, false, 2>(x, w, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best);
     const float max_scale = group_max_from_zero<8>(scale), max_min = group_max_from_zero<8>(the_min);
     const float inv_scale = max_scale > 0 ? 63.f / max_scale : 0.f;
     const float inv_min = max_min > 0 ? 63.f / max_min : 0.f;
@@ -436,7 +449,7 @@ __device__ __forceinline__ uint32_t code_word(const KScratch &s, int w) { return
 // returned by tail(s).
 template <> struct KQuant<T_Q4K> {
     static constexpr int SUB = 32;
-    static constexpr int WORDS = 36, TAIL = 0;
+    static constexpr int WORDS = 36, TAIL = 0, MINB = 4;
     static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
         if (w < 4) return k45_header_word(s, w);
         const int t = w - 4, p = t >> 3, jj = t & 7;
@@ -446,7 +459,7 @@ template <> struct KQuant<T_Q4K> {
 };
 template <> struct KQuant<T_Q5K> {
     static constexpr int SUB = 32;
-    static constexpr int WORDS = 44, TAIL = 0;
+    static constexpr int WORDS = 44, TAIL = 0, MINB = 4;
     static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
         if (w < 4) return k45_header_word(s, w);
         if (w < 12) {  // qh: bit 2p / 2p+1 of byte l = fifth bit of elements 64p+l / 64p+32+l
@@ -465,7 +478,7 @@ template <> struct KQuant<T_Q5K> {
 
 template <> struct KQuant<T_Q6K> {
     static constexpr int SUB = 16;
-    static constexpr int WORDS = 52, TAIL = 1;  // 210 bytes = 52 words (ql 32, qh 16, scales 4) + the 16-bit delta
+    static constexpr int WORDS = 52, TAIL = 1, MINB = 4;  // compiles to 93 registers = 5 CTAs per SM; capping it at 6 CTAs is slower  // 210 bytes = 52 words (ql 32, qh 16, scales 4) + the 16-bit delta
     static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
         if (s.zero) return 0;
         if (w < 32) {  // ql
@@ -514,7 +527,7 @@ template <> struct KQuant<T_Q6K> {
 
 template <> struct KQuant<T_Q2K> {
     static constexpr int SUB = 16;
-    static constexpr int WORDS = 21, TAIL = 0;
+    static constexpr int WORDS = 21, TAIL = 0, MINB = 7;  // 72 registers once the weights are recomputed
     static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
         if (w < 4) return *reinterpret_cast<const uint32_t *>(&s.a[4 * w]);
         if (w < 20) {
@@ -524,12 +537,10 @@ template <> struct KQuant<T_Q2K> {
         return (uint32_t)s.d16 | ((uint32_t)s.dmin16 << 16);
     }
     static __device__ __forceinline__ void lane(const float (&x)[16], int j, int, KScratch &s) {
-        float w[16];
-#pragma unroll
-        for (int l = 0; l < 16; ++l) w[l] = fabsf(x[l]);
+        // weights = |x|: an operand modifier, never materialised (WMODE 0) — 7 CTAs per SM instead of 6, -4 % time
         uint32_t L[4];
         float the_min, isc_best, mn_best;
-        const float scale = make_qkx2_quants<16, true>(x, w, 3, the_min, -0.5f, 0.1f, 15, isc_best, mn_best);
+        const float scale = make_qkx2_quants<16, true, 0>(x, x, 0.f, 3, the_min, -0.5f, 0.1f, 15, isc_best, mn_best);
         const float max_scale = group_max_from_zero<16>(scale), max_min = group_max_from_zero<16>(the_min);
         uint32_t b = 0;
         uint16_t d16 = 0, dmin16 = 0;
@@ -566,7 +577,7 @@ template <> struct KQuant<T_Q2K> {
 
 template <> struct KQuant<T_Q3K> {
     static constexpr int SUB = 16;
-    static constexpr int WORDS = 27, TAIL = 1;  // 110 bytes = 27 words (hmask 8, qs 16, scales 3) + the 16-bit delta
+    static constexpr int WORDS = 27, TAIL = 1, MINB = 5;  // 96 registers: a fifth resident CTA per SM, -8 % time  // 110 bytes = 27 words (hmask 8, qs 16, scales 3) + the 16-bit delta
     static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
         if (w < 8) {  // hmask: bit bq of byte o = (code[32 bq + o] > 3) = bit 2 of a 3-bit code
             uint32_t m = 0;
@@ -616,7 +627,7 @@ template <> struct KQuant<T_Q3K> {
 
 // ---------------------------------------------------------------------------------------------
 template <uint32_t T, class FT>
-__global__ void __launch_bounds__(KQ_THREADS, 4)
+__global__ void __launch_bounds__(KQ_THREADS, KQuant<T>::MINB)
 quant_k_kernel(const typename FT::raw *__restrict__ src, uint8_t *__restrict__ dst, size_t nblocks) {
     using KQ = KQuant<T>;
     constexpr int SUB = KQ::SUB, NSUB = 256 / SUB, SBW = 32 / NSUB;  // super-blocks per warp pass
