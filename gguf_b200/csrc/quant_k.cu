@@ -478,7 +478,9 @@ template <> struct KQuant<T_Q5K> {
 
 template <> struct KQuant<T_Q6K> {
     static constexpr int SUB = 16;
-    static constexpr int WORDS = 52, TAIL = 1, MINB = 4;  // compiles to 93 registers = 5 CTAs per SM; capping it at 6 CTAs is slower  // 210 bytes = 52 words (ql 32, qh 16, scales 4) + the 16-bit delta
+    // 210 bytes = 52 words (ql 32, qh 16, scales 4) + the 16-bit delta.  MINB 4 compiles to 93 registers = 5 CTAs per SM;
+    // capping the kernel at 6 CTAs per SM is slower
+    static constexpr int WORDS = 52, TAIL = 1, MINB = 4;
     static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
         if (s.zero) return 0;
         if (w < 32) {  // ql
@@ -527,7 +529,7 @@ template <> struct KQuant<T_Q6K> {
 
 template <> struct KQuant<T_Q2K> {
     static constexpr int SUB = 16;
-    static constexpr int WORDS = 21, TAIL = 0, MINB = 7;  // 72 registers once the weights are recomputed
+    static constexpr int WORDS = 21, TAIL = 0, MINB = 7;  // 72 registers now that the weights are an operand modifier
     static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
         if (w < 4) return *reinterpret_cast<const uint32_t *>(&s.a[4 * w]);
         if (w < 20) {
@@ -577,7 +579,9 @@ template <> struct KQuant<T_Q2K> {
 
 template <> struct KQuant<T_Q3K> {
     static constexpr int SUB = 16;
-    static constexpr int WORDS = 27, TAIL = 1, MINB = 5;  // 96 registers: a fifth resident CTA per SM, -8 % time  // 110 bytes = 27 words (hmask 8, qs 16, scales 3) + the 16-bit delta
+    // 110 bytes = 27 words (hmask 8, qs 16, scales 3) + the 16-bit delta.  MINB 5 = 96 registers, no spills: a fifth
+    // resident CTA per SM, -8 % time
+    static constexpr int WORDS = 27, TAIL = 1, MINB = 5;
     static __device__ __forceinline__ uint32_t word(const KScratch &s, int w) {
         if (w < 8) {  // hmask: bit bq of byte o = (code[32 bq + o] > 3) = bit 2 of a 3-bit code
             uint32_t m = 0;
