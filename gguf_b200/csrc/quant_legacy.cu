@@ -566,8 +566,8 @@ template <> struct Encoder<T_Q8K> {
 
 // ---------------------------------------------------------------------------------------------
 // QL_THREADS = rows per tile (one thread per row); chosen per type in launch_quant
-template <uint32_t T, class FT, int QS, int QL_THREADS>
-__global__ void __launch_bounds__(QL_THREADS)
+template <uint32_t T, class FT, int QS, int QL_THREADS, int MINB>
+__global__ void __launch_bounds__(QL_THREADS, MINB)
 quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t nblocks) {
     using TR = BlockTraits<T>;
     using E = Encoder<T>;
@@ -785,12 +785,12 @@ static cudaError_t launch_quant_oneshot(const void *src, void *dst, size_t nbloc
     return launch_pdl(quant_rows_oneshot<T, FT, ROWS, K>, (unsigned)grid, ROWS, 0, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
 }
 
-template <uint32_t T, class FT, int QS, int QL_THREADS>
+template <uint32_t T, class FT, int QS, int QL_THREADS, int MINB>
 static cudaError_t launch_quant_ring(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
     using TR = BlockTraits<T>;
     constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = QL_THREADS / RPB;
     constexpr int SMEM = QS * QL_THREADS * (32 * FT::SIZE + 16) + 2 * ((TILE_BLOCKS * TR::BYTES + 15) & ~15);
-    auto kern = quant_rows_kernel<T, FT, QS, QL_THREADS>;
+    auto kern = quant_rows_kernel<T, FT, QS, QL_THREADS, MINB>;
     static std::atomic<int> occ_cache[MAX_DEVICES];
     int ctas_per_sm = 0;
     cudaError_t e = cached_occupancy(kern, QL_THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
@@ -819,7 +819,8 @@ static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cuda
     } else {  // Q8K: persistent ring, 64-row tiles
         // 2 input stages and 64-row tiles: 3-4 stages or 128-row tiles are 2-8 points slower (the encoder's
         // eight-lane shuffles, not bytes in flight, bound this one)
-        return launch_quant_ring<T, FT, 2, 64>(src, dst, nblocks, stream, dev);
+        // capped at 64 registers (14 CTAs of 64 threads per SM): +1..4 points over the 80-84 the compiler takes unasked
+        return launch_quant_ring<T, FT, 2, 64, 14>(src, dst, nblocks, stream, dev);
     }
 }
 
