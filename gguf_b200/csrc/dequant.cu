@@ -40,10 +40,9 @@ using Ring4k3x128 = DqCfg<4096, 3, 128, 8, 0>;   // small CTAs, 8 per SM: +3..5 
 using Ring4k3x256 = DqCfg<4096, 3, 256, 4, 0>;   // best below ~6 Mi elements
 using Ring8k3x128 = DqCfg<8192, 3, 128, 6, 0>;
 using One16k8 = DqCfg<16384, 1, 128, 8, 1>;
-using One16k9 = DqCfg<16384, 1, 128, 9, 1>;
-using One16k10 = DqCfg<16384, 1, 128, 10, 1>;
-using One16k12 = DqCfg<16384, 1, 128, 12, 1>;
 using One8k8 = DqCfg<8192, 1, 128, 8, 1>;
+using Two8k10 = DqCfg<8192, 2, 128, 10, 3>;      // MODE 3: two consecutive tiles per short-lived CTA, both requested up front
+using Four4k8 = DqCfg<4096, 4, 128, 8, 3>;
 using One4k10 = DqCfg<4096, 1, 128, 10, 1>;
 
 constexpr size_t Mi = size_t(1) << 20;
@@ -52,10 +51,11 @@ template <uint32_t T> constexpr bool is_k2345() { return T == T_Q2K || T == T_Q3
 
 // 16-bit output, big tensors
 template <uint32_t T> struct DqOneBig { using type = One16k8; };
-template <> struct DqOneBig<T_Q2K> { using type = One16k12; };
-template <> struct DqOneBig<T_Q3K> { using type = One16k9; };
-template <> struct DqOneBig<T_Q4K> { using type = One16k10; };
-template <> struct DqOneBig<T_Q5K> { using type = One16k9; };
+// the instruction-heavier K decoders gain another 1-2.5 % from several smaller tiles per CTA (r01_dq_sweep_mode3.txt)
+template <> struct DqOneBig<T_Q2K> { using type = Four4k8; };
+template <> struct DqOneBig<T_Q3K> { using type = Two8k10; };
+template <> struct DqOneBig<T_Q4K> { using type = Two8k10; };
+template <> struct DqOneBig<T_Q5K> { using type = Two8k10; };
 // small tensors that stay on the ring (16-bit output, 6 Mi elements and up)
 template <uint32_t T> struct DqRingSmall { using type = Ring4k3x128; };
 template <> struct DqRingSmall<T_Q6K> { using type = Ring16k3; };
@@ -74,9 +74,10 @@ static cudaError_t launch_dequant_cfg(const void *src, void *dst, size_t nblocks
     cudaError_t e = cached_occupancy(kern, CFG::THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
     if (e != cudaSuccess) return e;
     const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
-    // RING: one persistent CTA per slot.  ONE: one CTA per tile (capped only where the grid would overflow)
+    // RING: one persistent CTA per slot.  ONE: one CTA per tile, or per STAGES consecutive tiles (MODE 3)
+    const size_t want = CFG::MODE == 3 ? (ntiles + CFG::STAGES - 1) / CFG::STAGES : ntiles;
     size_t grid = CFG::MODE == 0 ? (size_t)dev.sm_count * ctas_per_sm : (size_t)0x7FFFFFFF;
-    if (grid > ntiles) grid = ntiles;
+    if (grid > want) grid = want;
     return launch_pdl(kern, (unsigned)grid, CFG::THREADS, SMEM, stream, static_cast<const uint8_t *>(src),
                       static_cast<typename FT::raw *>(dst), nblocks);
 }
