@@ -20,13 +20,15 @@
 namespace ggq {
 
 // Shipped configurations, chosen with tools/dq_sweep.cu (profiles/r01_dq_sweep_modes*.txt; repeatable to
-// +-0.5 %).  Two kernel shapes (dequant_kernel.cuh):
+// +-0.5 %).  Kernel shapes (dequant_kernel.cuh):
 //   ONE  (MODE 1)  one tile per CTA, 128-thread CTAs, the register cap forced down (MINB) so that 8-12 CTAs are
 //                  resident per SM: while one CTA waits for its bulk copy its neighbours decode and store, and the
 //                  hardware block scheduler keeps the window of addresses in flight contiguous.  A persistent
 //                  grid-stride fill tops out at 5.3-5.6 TB/s on this GPU, the same fill as one 16 KB tile per CTA
 //                  reaches 6.3 TB/s; the decoders follow: 6.3-6.6 TB/s (96-101 % of the measured copy peak) on
 //                  58.7 M elements against 5.7-5.9 TB/s for the ring.  Needs a few waves of CTAs to overlap.
+//   MANY (MODE 3)  the same with 2-4 smaller consecutive tiles per CTA, all requested up front: the instruction-
+//                  heavier Q2K..Q5K decoders gain another 1.5-2.5 points on big tensors.
 //   RING (MODE 0)  persistent CTAs with a STAGES-deep bulk-copy ring: still the better shape for small tensors
 //                  (less than ~2 waves of tiles), where ONE's CTAs would all load and then all store in step.  Small
 //                  tiles (4096 elements) and small CTAs (128 threads, 8 per SM) balance these 3-9 us launches best.
@@ -34,7 +36,6 @@ template <int TILE_, int STAGES_, int THREADS_, int MINB_, int MODE_> struct DqC
     static constexpr int TILE = TILE_, STAGES = STAGES_, THREADS = THREADS_, MINB = MINB_, MODE = MODE_;
 };
 using Ring8k3 = DqCfg<8192, 3, 256, 3, 0>;
-using Ring8k2 = DqCfg<8192, 2, 256, 3, 0>;
 using Ring16k3 = DqCfg<16384, 3, 256, 3, 0>;
 using Ring4k3x128 = DqCfg<4096, 3, 128, 8, 0>;   // small CTAs, 8 per SM: +3..5 % on 8-24 Mi-element tensors (r01_dq_sweep_ring_small.txt)
 using Ring4k3x256 = DqCfg<4096, 3, 256, 4, 0>;   // best below ~6 Mi elements
