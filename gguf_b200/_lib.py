@@ -40,6 +40,10 @@ class SliceJob(_c.Structure):
                 ("src", _c.c_void_p), ("src_len", _c.c_size_t)]
 
 
+class ShardPiece(_c.Structure):
+    _fields_ = [("job", _c.c_uint32), ("device", _c.c_int), ("elem_begin", _c.c_size_t), ("elem_end", _c.c_size_t)]
+
+
 class ConvertStats(_c.Structure):
     _fields_ = [("n_tensors", _c.c_uint64), ("n_cast_tensors", _c.c_uint64), ("cast_elems", _c.c_uint64), ("bytes_in", _c.c_uint64),
                 ("bytes_out", _c.c_uint64), ("seconds_plan", _c.c_double), ("seconds_convert", _c.c_double),
@@ -60,6 +64,7 @@ SYMBOLS += [
     ("ggq_rearrange_device", _c.c_int, [_c.c_void_p, _c.POINTER(Layout), _c.c_void_p, _c.POINTER(Layout), _c.c_size_t, _c.c_void_p]),
     ("ggq_rearrange", _c.c_int, [_c.c_void_p, _c.POINTER(Layout), _c.c_void_p, _c.POINTER(Layout), _c.c_size_t]),
     ("ggq_slices", _c.c_int, [_c.POINTER(SliceJob), _c.c_size_t]),
+    ("ggq_plan_shards", _c.c_size_t, [_c.POINTER(SliceJob), _c.c_size_t, _c.c_int, _c.POINTER(ShardPiece), _c.c_size_t]),
     ("ggq_convert_gguf", _c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_int, _c.POINTER(ConvertStats)]),
     ("ggq_convert_gguf_ex", _c.c_int, [_c.POINTER(_c.c_char_p), _c.c_size_t, _c.c_char_p, _c.c_char_p, _c.POINTER(ConvertOptions),
                                        _c.POINTER(ConvertStats)]),

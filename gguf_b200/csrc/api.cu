@@ -28,7 +28,7 @@ using namespace ggq;
 thread_local std::string t_err;
 thread_local int t_device = -1;  // ggq_set_device override for the calling thread
 std::atomic<uint64_t> g_launches{0};
-std::atomic<int> g_shard_devices{1};  // ggq_set_shard_devices: GPUs one host-pointer call is split over
+thread_local int t_shard_devices = 1;  // ggq_set_shard_devices: GPUs the calling thread's host-pointer calls are split over
 
 int fail(int code, const std::string &msg) {
     t_err = msg;
@@ -307,6 +307,7 @@ struct ChainJob {
     std::vector<uint32_t> chain;  // >= 2 types
     size_t n_elems;
     ggq::ChainIO io;
+    size_t elem_base = 0;  // this job covers elements [elem_base, elem_base + n_elems) of the tensor `io` addresses
 };
 
 // Streams every job, back to back, through ONE pipeline: the D2H of job k's last chunks overlaps the
@@ -353,14 +354,14 @@ int run_jobs_io(const std::vector<ChainJob> &jobs) {
             const ChainJob &rj = jobs[r.job];
             if ((e = cudaEventSynchronize(s.done)) != cudaSuccess) break;
             const uint32_t t_out = rj.chain.back();
-            if (!rj.io.direct_dst) io_ok = rj.io.write(s.h_out, type_nbytes(t_out, r.e0), type_nbytes(t_out, r.e1 - r.e0));
+            if (!rj.io.direct_dst) io_ok = rj.io.write(s.h_out, type_nbytes(t_out, rj.elem_base + r.e0), type_nbytes(t_out, r.e1 - r.e0));
         }
         if (c < nchunks && io_ok) {
             const Chunk &k = chunks[c];
             const ChainJob &job = jobs[k.job];
             const uint32_t t_in = job.chain.front(), t_out = job.chain.back();
             const size_t ne = k.e1 - k.e0;
-            const size_t in_off = type_nbytes(t_in, k.e0), out_off = type_nbytes(t_out, k.e0);
+            const size_t in_off = type_nbytes(t_in, job.elem_base + k.e0), out_off = type_nbytes(t_out, job.elem_base + k.e0);
             const char *hsrc;
             if (job.io.direct_src) {
                 hsrc = static_cast<const char *>(job.io.direct_src) + in_off;
@@ -414,6 +415,82 @@ int make_mem_io(void *dst, const void *src, ggq::ChainIO *io) {
     return GGQ_OK;
 }
 
+// ---- the ONE multi-GPU partitioner (ggq_plan_shards) -----------------------------------------------
+// Blocks are independent (lib.rs:129-131), so a call's jobs are split "by tensor and by block range" with a
+// single rule: lay the jobs end to end in SHARD_UNIT-element units (a multiple of every block size and of 8
+// blocks, so every cut keeps both sides 16-byte aligned), weigh a unit by the bytes it moves over PCIe
+// (input + output representation), and give device d the units whose weight midpoint falls in
+// [W d / n, W (d+1) / n).  Consecutive units of one job on one device form one piece.  Each device then streams
+// its pieces through its own pipeline over its own PCIe link; there is no inter-GPU traffic.  A call moving
+// less than MIN_BYTES_PER_DEVICE per device uses fewer devices.
+constexpr size_t SHARD_UNIT = size_t(1) << 20;
+constexpr uint64_t MIN_BYTES_PER_DEVICE = uint64_t(16) << 20;
+struct Piece { uint32_t job; int device; size_t e0, e1; };
+struct JobGeom { size_t n_elems; uint32_t t_in, t_out; };
+
+std::vector<Piece> plan_pieces(const std::vector<JobGeom> &jobs, int ndev) {
+    std::vector<Piece> out;
+    uint64_t total = 0;
+    for (const auto &j : jobs) total += type_nbytes(j.t_in, j.n_elems) + type_nbytes(j.t_out, j.n_elems);
+    if (ndev < 1) ndev = 1;
+    ndev = (int)std::min<uint64_t>((uint64_t)ndev, std::max<uint64_t>(1, total / MIN_BYTES_PER_DEVICE));
+    uint64_t before = 0;  // weight of the units already placed
+    for (uint32_t ji = 0; ji < jobs.size(); ji++) {
+        const JobGeom &j = jobs[ji];
+        for (size_t e = 0; e < j.n_elems; e += SHARD_UNIT) {
+            const size_t ne = std::min(SHARD_UNIT, j.n_elems - e);
+            const uint64_t w = type_nbytes(j.t_in, ne) + type_nbytes(j.t_out, ne);
+            // device of the unit's midpoint: floor((before + w/2) * ndev / total), in 128-bit-safe arithmetic
+            const unsigned __int128 mid2 = (unsigned __int128)(2 * before + w) * (unsigned)ndev;
+            int d = total ? (int)(mid2 / (2 * (unsigned __int128)total)) : 0;
+            if (d >= ndev) d = ndev - 1;
+            before += w;
+            if (!out.empty() && out.back().job == ji && out.back().device == d && out.back().e1 == e) out.back().e1 = e + ne;
+            else out.push_back({ji, d, e, e + ne});
+        }
+    }
+    return out;
+}
+
+// Runs the jobs on the calling thread's device, or — after ggq_set_shard_devices(n > 1) on this thread — split
+// over devices 0..n-1 by plan_pieces().  The caller's CUDA device and ggq_set_device() state are restored.
+int run_jobs_sharded(const std::vector<ChainJob> &jobs) {
+    const int ndev = (t_device >= 0) ? 1 : t_shard_devices;
+    if (ndev <= 1 || jobs.empty()) return run_jobs_io(jobs);
+    std::vector<JobGeom> geom;
+    for (const auto &j : jobs) geom.push_back({j.n_elems, j.chain.front(), j.chain.back()});
+    const std::vector<Piece> pieces = plan_pieces(geom, ndev);
+    int used = 0;
+    for (const auto &p : pieces) used = std::max(used, p.device + 1);
+    if (used <= 1) return run_jobs_io(jobs);
+    std::vector<std::vector<ChainJob>> per_dev(used);
+    for (const auto &p : pieces) {
+        ChainJob c = jobs[p.job];
+        c.elem_base = jobs[p.job].elem_base + p.e0;
+        c.n_elems = p.e1 - p.e0;
+        per_dev[p.device].push_back(std::move(c));
+    }
+    std::vector<int> rcs(used, GGQ_OK);
+    std::vector<std::string> errs(used);
+    auto dev_fn = [&](int d) {
+        t_device = d;  // pin this thread to device d
+        rcs[d] = run_jobs_io(per_dev[d]);
+        if (rcs[d] != GGQ_OK) errs[d] = t_err;
+    };
+    const int saved = t_device;
+    int saved_cuda = -1;
+    if (cudaGetDevice(&saved_cuda) != cudaSuccess) { cudaGetLastError(); saved_cuda = -1; }
+    std::vector<std::thread> th;
+    for (int d = 1; d < used; d++) th.emplace_back(dev_fn, d);
+    dev_fn(0);
+    t_device = saved;
+    if (saved_cuda >= 0) cudaSetDevice(saved_cuda);
+    for (auto &t : th) t.join();
+    for (int d = 0; d < used; d++)
+        if (rcs[d] != GGQ_OK) return fail(rcs[d], errs[d]);
+    return GGQ_OK;
+}
+
 int run_chain_host(const std::vector<uint32_t> &chain, void *dst, const void *src, size_t n_elems) {
     if (n_elems == 0) return GGQ_OK;
     if (!dst || !src) return fail(GGQ_ERR_INVALID, "null pointer with non-zero length");
@@ -421,45 +498,12 @@ int run_chain_host(const std::vector<uint32_t> &chain, void *dst, const void *sr
         memmove(dst, src, type_nbytes(chain.front(), n_elems));
         return GGQ_OK;
     }
-    ggq::ChainIO whole;
-    int rc0 = make_mem_io(dst, src, &whole);  // rejects device pointers, notes which side is pinned
-    if (rc0 != GGQ_OK) return rc0;
-    const bool pin_src = whole.direct_src != nullptr, pin_dst = whole.direct_dst != nullptr;
-    auto make_io = [&](size_t elem0) {  // the sub-tensor starting at element `elem0`
-        const char *s0 = static_cast<const char *>(src) + type_nbytes(chain.front(), elem0);
-        char *d0 = static_cast<char *>(dst) + type_nbytes(chain.back(), elem0);
-        ggq::ChainIO io;
-        io.direct_src = pin_src ? s0 : nullptr;
-        io.direct_dst = pin_dst ? d0 : nullptr;
-        io.read = [s0](void *pinned, size_t off, size_t n) { parallel_memcpy(pinned, s0 + off, n); return true; };
-        io.write = [d0](const void *pinned, size_t off, size_t n) { parallel_memcpy(d0 + off, pinned, n); return true; };
-        return io;
-    };
-    // Blocks are independent (lib.rs:129-131): split the element range over the configured GPUs in
-    // contiguous, chunk-aligned parts; each part runs its own pipeline on its own device, there is
-    // no inter-GPU traffic.  Small calls and an explicit ggq_set_device() stay on one GPU.
-    const int ndev = (t_device >= 0) ? 1 : g_shard_devices.load();
-    const size_t nchunks = (n_elems + CHUNK_ELEMS - 1) / CHUNK_ELEMS;
-    if (ndev <= 1 || nchunks < 2) return run_chain_io(chain, n_elems, make_io(0));
-    const size_t parts = std::min<size_t>((size_t)ndev, nchunks);
-    std::vector<int> rcs(parts, GGQ_OK);
-    std::vector<std::string> errs(parts);
-    std::vector<std::thread> th;
-    auto part_fn = [&](size_t k) {
-        const size_t c0 = nchunks * k / parts, c1 = nchunks * (k + 1) / parts;
-        const size_t e0 = c0 * CHUNK_ELEMS, e1 = std::min(n_elems, c1 * CHUNK_ELEMS);
-        t_device = (int)k;  // worker thread: pin to device k
-        rcs[k] = run_chain_io(chain, e1 - e0, make_io(e0));
-        if (rcs[k] != GGQ_OK) errs[k] = t_err;
-    };
-    const int saved = t_device;
-    for (size_t k = 1; k < parts; k++) th.emplace_back(part_fn, k);
-    part_fn(0);
-    t_device = saved;
-    for (auto &t : th) t.join();
-    for (size_t k = 0; k < parts; k++)
-        if (rcs[k] != GGQ_OK) return fail(rcs[k], errs[k]);
-    return GGQ_OK;
+    std::vector<ChainJob> jobs(1);
+    jobs[0].chain = chain;
+    jobs[0].n_elems = n_elems;
+    int rc = make_mem_io(dst, src, &jobs[0].io);  // rejects device pointers, notes which side is pinned
+    if (rc != GGQ_OK) return rc;
+    return run_jobs_sharded(jobs);
 }
 
 int run_host(bool quant, const Plan &p, void *dst, const void *src) {
@@ -724,7 +768,7 @@ int ggq_set_shard_devices(int n_devices) {
     if (n_devices <= 0) n_devices = avail;
     if (n_devices > avail) return fail(GGQ_ERR_INVALID, "more shard devices than CUDA devices");
     if (n_devices < 1) n_devices = 1;
-    g_shard_devices.store(n_devices);
+    t_shard_devices = n_devices;
     return n_devices;
 }
 
@@ -766,35 +810,26 @@ int ggq_slices(const struct ggq_slice_job *jobs, size_t n_jobs) {
         if ((rc = make_mem_io(j.dst, j.src, &c.io)) != GGQ_OK) return rc;
         cj.push_back(std::move(c));
     }
-    // by-tensor sharding over the configured GPUs (largest first, least-loaded device); no collective
-    const int ndev = (t_device >= 0) ? 1 : g_shard_devices.load();
-    if (ndev <= 1 || cj.size() < 2) return run_jobs_io(cj);
-    std::vector<size_t> order(cj.size());
-    for (size_t i = 0; i < order.size(); i++) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cj[a].n_elems != cj[b].n_elems ? cj[a].n_elems > cj[b].n_elems : a < b; });
-    std::vector<std::vector<ChainJob>> per_dev(ndev);
-    std::vector<size_t> load(ndev, 0);
-    for (size_t i : order) {
-        const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-        load[d] += cj[i].n_elems;
-        per_dev[d].push_back(std::move(cj[i]));
+    return run_jobs_sharded(cj);
+}
+
+size_t ggq_plan_shards(const struct ggq_slice_job *jobs, size_t n_jobs, int n_devices, struct ggq_shard_piece *out, size_t cap) {
+    if (n_jobs && !jobs) return 0;
+    std::vector<JobGeom> geom;
+    std::vector<size_t> index;  // geom entry -> caller's job index (empty jobs carry no piece)
+    for (size_t i = 0; i < n_jobs; i++) {
+        const ggq_slice_job &j = jobs[i];
+        Plan p;
+        int rc = j.quantize ? plan_quantize(j.type, j.fdt, j.dst_len, j.src_len, &p) : plan_dequantize(j.type, j.fdt, j.dst_len, j.src_len, &p);
+        if (rc != GGQ_OK) return 0;
+        if (p.nblocks == 0) continue;
+        geom.push_back({p.nblocks * p.ti->elems, j.quantize ? p.fdt : p.ti->type, j.quantize ? p.ti->type : p.fdt});
+        index.push_back(i);
     }
-    std::vector<int> rcs(ndev, GGQ_OK);
-    std::vector<std::string> errs(ndev);
-    auto dev_fn = [&](int d) {
-        t_device = d;
-        rcs[d] = run_jobs_io(per_dev[d]);
-        if (rcs[d] != GGQ_OK) errs[d] = t_err;
-    };
-    const int saved = t_device;
-    std::vector<std::thread> th;
-    for (int d = 1; d < ndev; d++) th.emplace_back(dev_fn, d);
-    dev_fn(0);
-    t_device = saved;
-    for (auto &t : th) t.join();
-    for (int d = 0; d < ndev; d++)
-        if (rcs[d] != GGQ_OK) return fail(rcs[d], errs[d]);
-    return GGQ_OK;
+    const std::vector<Piece> pieces = plan_pieces(geom, n_devices);
+    for (size_t k = 0; k < pieces.size() && k < cap && out; k++)
+        out[k] = {(uint32_t)index[pieces[k].job], pieces[k].device, pieces[k].e0, pieces[k].e1};
+    return pieces.size();
 }
 
 int ggq_cast(const uint32_t *types, int n_types, void *dst, const void *src, size_t n_elems) {

@@ -505,7 +505,7 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
         std::vector<int> in_fds;
         for (const auto &f : files) in_fds.push_back(f->fd);
         ResidentBudget budget;
-        auto worker = [&](int dev) {
+        auto worker_body = [&](int dev) {
             if (need_gpu && ggq_set_device(dev) != GGQ_OK) { set_err(GGQ_ERR_CUDA, ggq_last_error()); return; }
             std::vector<uint8_t> copy_buf;
             std::unique_ptr<ggq::Resident> res;
@@ -531,11 +531,22 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
                 if (io.used_resident) rearranged += 1;
             }
         };
+        // Every worker, the first included, is a spawned thread: ggq_set_device() pins the thread it is called on,
+        // and the caller's thread must come back from this call as it went in (device, sharding state).  The layout
+        // helpers and allocations below emit() can throw; an exception must become a status, not std::terminate.
+        auto worker = [&](int dev) {
+            try {
+                worker_body(dev);
+            } catch (const std::exception &e) {
+                set_err(GGQ_ERR_INVALID, e.what());
+            } catch (...) {
+                set_err(GGQ_ERR_INVALID, "unknown exception in a convert worker");
+            }
+        };
         if (!o.no_data) {
             std::vector<std::thread> th;
             const int nworkers = ndev * WORKERS_PER_DEVICE;  // plain copies are file I/O: they want the threads too
-            for (int w = 1; w < nworkers; w++) th.emplace_back(worker, w % ndev);
-            worker(0);
+            for (int w = 0; w < nworkers; w++) th.emplace_back(worker, w % ndev);
             for (auto &x : th) x.join();
             if (rc_all.load() != GGQ_OK) return failc(rc_all.load(), first_err);
         }

@@ -28,7 +28,12 @@ struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
 
 enum MetaType : uint32_t { U8 = 0, I8, U16, I16, U32, I32, F32, BOOL, STRING, ARRAY, U64, I64, F64 };
 
-// GGmlType::size() (ggus/src/tensor.rs:102-144): {block elements, block bytes}; 0 = not supported here
+// GGmlType::size() (ggus/src/tensor.rs:102-144): {block elements, block bytes} — the whole table, so that a
+// tensor of a type this library has no codec for still passes through untouched (the reference hands such
+// tensors on as borrowed bytes).  Sizes are size_of of the REFERENCE's repr(C) structs
+// (ggml-quants/src/structs/iq*.rs), which is what its reader computes nbytes from; IQ3XXS / IQ4NL / IQ4XS are
+// wider there than in upstream ggml (194 / 34 / 264 vs 98 / 18 / 136 bytes).  Q4_0_4_4 / _4_8 / _8_8 (31..33)
+// are `todo!()` in the reference's table and stay unsupported.
 inline bool type_size(uint32_t ty, uint64_t *elems, uint64_t *bytes) {
     switch (ty) {
         case 0: *elems = 1; *bytes = 4; return true;     // F32
@@ -45,11 +50,20 @@ inline bool type_size(uint32_t ty, uint64_t *elems, uint64_t *bytes) {
         case 13: *elems = 256; *bytes = 176; return true; // Q5K
         case 14: *elems = 256; *bytes = 210; return true; // Q6K
         case 15: *elems = 256; *bytes = 290; return true; // Q8K (reference layout)
+        case 16: *elems = 256; *bytes = 66; return true;  // IQ2XXS  f16 + [u16; 32]
+        case 17: *elems = 256; *bytes = 74; return true;  // IQ2XS   f16 + [u16; 32] + [u8; 8]
+        case 18: *elems = 256; *bytes = 194; return true; // IQ3XXS  f16 + [u16; 96]
+        case 19: *elems = 256; *bytes = 50; return true;  // IQ1S    f16 + [u8; 32] + [u16; 8]
+        case 20: *elems = 32; *bytes = 34; return true;   // IQ4NL   f16 + [u16; 16]
+        case 21: *elems = 256; *bytes = 110; return true; // IQ3S    f16 + [u8; 64] + [u8; 8] + [u8; 32] + [u8; 4]
+        case 22: *elems = 256; *bytes = 82; return true;  // IQ2S    f16 + [u8; 64] + [u8; 8] + [u8; 8]
+        case 23: *elems = 256; *bytes = 264; return true; // IQ4XS   f16 + u16 + [u8; 4] + [u16; 128]
         case 24: *elems = 1; *bytes = 1; return true;    // I8
         case 25: *elems = 1; *bytes = 2; return true;    // I16
         case 26: *elems = 1; *bytes = 4; return true;    // I32
         case 27: *elems = 1; *bytes = 8; return true;    // I64
         case 28: *elems = 1; *bytes = 8; return true;    // F64
+        case 29: *elems = 256; *bytes = 56; return true;  // IQ1M    [u8; 32] + [u8; 16] + [u8; 8]
         case 30: *elems = 1; *bytes = 2; return true;    // BF16
     }
     return false;

@@ -68,11 +68,13 @@ const char *ggq_last_error(void);
 int ggq_device_count(void);
 int ggq_set_device(int device);
 
-/* Spread every large host-pointer call (slice API and ggq_cast) over the first `n_devices` GPUs by
- * contiguous block range — blocks are independent (lib.rs:129-131), so there is no inter-GPU
- * traffic: each GPU pulls and pushes its own range over its own PCIe link.  <= 0 selects all visible
- * devices.  Returns the device count now in effect (>= 1) or a negative status.  Default 1.  A
- * thread that called ggq_set_device() is not sharded. */
+/* Spread every large host-pointer call THE CALLING THREAD makes afterwards (slice API, ggq_slices, ggq_cast)
+ * over the GPUs 0 .. n_devices-1 — blocks are independent (lib.rs:129-131), so there is no inter-GPU
+ * traffic: each GPU pulls and pushes its own ranges over its own PCIe link.  The split is the one
+ * ggq_plan_shards() reports.  <= 0 selects all visible devices.  Returns the device count now in effect
+ * (>= 1) or a negative status.  Default 1.  Per-thread state (other threads' calls are unaffected); a
+ * thread that called ggq_set_device() is not sharded.  The caller's current CUDA device is restored
+ * before the call returns. */
 int ggq_set_shard_devices(int n_devices);
 
 /* ---- host-pointer slice API (the drop-in) ------------------------------------------------- */
@@ -105,6 +107,24 @@ struct ggq_slice_job {
     size_t src_len;    /* elements when quantizing, blocks when dequantizing */
 };
 int ggq_slices(const struct ggq_slice_job *jobs, size_t n_jobs);
+
+/* The library's multi-GPU partitioner, as a pure host function (no CUDA call, usable without a GPU): how a
+ * ggq_slices / slice / cast call with these jobs is split over `n_devices` GPUs — "by tensor and by block
+ * range"  as one rule: the jobs are laid end to end in units of 2^20 elements (a multiple of
+ * every block size and of 8 blocks, so both sides of every cut stay 16-byte aligned), a unit weighs the
+ * bytes it moves over PCIe (input + output representation), and device d takes the units whose weight
+ * midpoint lies in [W d / n, W (d+1) / n).  Pieces come out in job order, element ranges ascending;
+ * together they cover every element of every job exactly once.  Fewer devices are used when a device
+ * would move less than 16 MiB.  Writes at most `cap` pieces to `out` (may be NULL) and returns the number
+ * of pieces of the full plan; 0 when a job fails the slice calls' length checks. */
+struct ggq_shard_piece {
+    uint32_t job;      /* index into `jobs` */
+    int device;        /* 0 .. n_devices-1 */
+    size_t elem_begin; /* element range [elem_begin, elem_end) of that job's float side */
+    size_t elem_end;
+};
+size_t ggq_plan_shards(const struct ggq_slice_job *jobs, size_t n_jobs, int n_devices,
+                       struct ggq_shard_piece *out, size_t cap);
 
 /* ---- device-pointer slice API (device-resident chains, pipelining, kernel timing) ---------- */
 

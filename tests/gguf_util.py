@@ -4,7 +4,9 @@ import struct
 import numpy as np
 
 TYPE_SIZE = {0: (1, 4), 1: (1, 2), 2: (32, 18), 3: (32, 20), 6: (32, 22), 7: (32, 24), 8: (32, 34), 9: (32, 36), 10: (256, 84),
-             11: (256, 110), 12: (256, 144), 13: (256, 176), 14: (256, 210), 15: (256, 290), 30: (1, 2), 26: (1, 4)}
+             11: (256, 110), 12: (256, 144), 13: (256, 176), 14: (256, 210), 15: (256, 290), 30: (1, 2), 26: (1, 4),
+             16: (256, 66), 17: (256, 74), 18: (256, 194), 19: (256, 50), 20: (32, 34), 21: (256, 110), 22: (256, 82), 23: (256, 264),
+             29: (256, 56)}
 U32, STRING, ARRAY, U64 = 4, 8, 9, 10
 
 

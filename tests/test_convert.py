@@ -60,6 +60,30 @@ def test_copy_only_layout_matches_reference_writer(ggq, tmp_path):
     assert open(dst, "rb").read() == open(dst2, "rb").read()
 
 
+def test_types_without_a_codec_pass_through_untouched(ggq, tmp_path):
+    """A file holding tensors of types this library has no codec for (IQ*, sizes = size_of the reference's
+    structs, ggus/src/tensor.rs:102-144) still converts: untouched tensors are borrowed bytes in the
+    reference (utils/mod.rs:104-138); only a cast that reads or targets such a type is refused."""
+    from gguf_b200.convert import convert
+    from gguf_b200 import GgqError
+    from gguf_util import TYPE_SIZE
+    rng = np.random.default_rng(5)
+    ts = llama_like(layers=1)
+    for ty in (16, 17, 18, 19, 20, 21, 22, 23, 29):
+        e, b = TYPE_SIZE[ty]
+        ts.append((f"blk.0.iq{ty}.weight", (e * 2, 3), ty, rng.integers(0, 256, 2 * 3 * b, dtype=np.uint8).tobytes()))
+    src, dst = tmp_path / "in.gguf", tmp_path / "out.gguf"
+    write_gguf(src, KVS, ts, alignment=64)
+    st = convert(src, dst, "")
+    _, tensors, _, _ = read_gguf(dst)
+    for name, shape, ty, data in ts:
+        assert tensors[name] == (shape, ty, data), name
+    assert st["n_tensors"] == len(ts)
+    with pytest.raises(GgqError) as ei:          # "linear" matches the 2-D IQ tensors: refused by name, nothing written
+        convert(src, tmp_path / "bad.gguf", "cast:linear:f16")
+    assert "unsupported type" in str(ei.value)
+
+
 @pytest.mark.parametrize("mutate,msg", [
     (dict(magic=b"GGUX"), "MagicMismatch"), (dict(version=2), "VersionNotSupport"),
 ])
@@ -301,3 +325,30 @@ def test_sharded_convert_with_cast_matches_oracle(ggq, oracle, tmp_path):
     assert list(seen) == [t[0] for t in ts]
     for name, (shape, ty, data) in seen.items():
         assert (ty, data) == want[name], name
+
+
+@pytest.mark.gpu
+def test_convert_leaves_the_callers_thread_state_alone(ggq, oracle, tmp_path):
+    """ggq_convert_gguf must not pin the calling thread to a device (its workers are all spawned threads) nor
+    change the thread's current CUDA device; a sharded slice call afterwards still shards and also restores it."""
+    import torch
+    from gguf_b200._lib import lib
+    from gguf_b200.convert import convert
+    ndev = lib().ggq_device_count()
+    cur = ndev - 1
+    torch.cuda.set_device(cur)
+    src, dst = tmp_path / "in.gguf", tmp_path / "out.gguf"
+    write_gguf(src, KVS, llama_like(), alignment=64)
+    convert(src, dst, "cast:linear:q8_0")
+    assert torch.cuda.current_device() == cur
+    n = (1 << 23) * 3 + 32 * 5
+    x = to_fdt(gaussian(n, 77), F16)
+    assert lib().ggq_set_shard_devices(0) == ndev          # accepted: the thread was not pinned by convert
+    try:
+        got = ggq.quantize(Q8_0, x, F16)
+    finally:
+        lib().ggq_set_shard_devices(1)
+    assert np.array_equal(got, oracle.quantize(Q8_0, F16, x, threads=8))
+    assert torch.cuda.current_device() == cur
+    y = torch.zeros(4, device="cuda")                      # the caller's own CUDA work still targets its device
+    assert y.device.index == cur

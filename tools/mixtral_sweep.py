@@ -7,7 +7,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch, torch.distributed as dist
 import gguf_b200 as g
-from gguf_b200.sharding import assign_tensors, max_over_ranks
+
+
+def max_over_ranks(value, dist=None, device=None):
+    if dist is None:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -17,7 +25,7 @@ if world > 1:
 PEAK = 6543.4
 n = 4096 * 14336 * 8
 n_tensors = 8 * world if len(sys.argv) < 2 else int(sys.argv[1])   # global tensor count, sharded by tensor
-mine = assign_tensors([n] * n_tensors, world)[rank]
+mine = list(range(rank, n_tensors, world))   # equal-sized tensors: by-tensor sharding is round-robin
 st = torch.cuda.current_stream().cuda_stream
 x = (torch.randn(n, device=dev) * 0.02).to(torch.float16)
 out = [torch.empty(n, dtype=torch.float16, device=dev) for _ in range(2)]
