@@ -64,6 +64,7 @@ SYMBOLS += [
     ("ggq_rearrange_device", _c.c_int, [_c.c_void_p, _c.POINTER(Layout), _c.c_void_p, _c.POINTER(Layout), _c.c_size_t, _c.c_void_p]),
     ("ggq_rearrange", _c.c_int, [_c.c_void_p, _c.POINTER(Layout), _c.c_void_p, _c.POINTER(Layout), _c.c_size_t]),
     ("ggq_slices", _c.c_int, [_c.POINTER(SliceJob), _c.c_size_t]),
+    ("ggq_slices_device", _c.c_int, [_c.POINTER(SliceJob), _c.c_size_t, _c.c_void_p]),
     ("ggq_plan_shards", _c.c_size_t, [_c.POINTER(SliceJob), _c.c_size_t, _c.c_int, _c.POINTER(ShardPiece), _c.c_size_t]),
     ("ggq_convert_gguf", _c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_int, _c.POINTER(ConvertStats)]),
     ("ggq_convert_gguf_ex", _c.c_int, [_c.POINTER(_c.c_char_p), _c.c_size_t, _c.c_char_p, _c.c_char_p, _c.POINTER(ConvertOptions),

@@ -813,6 +813,68 @@ int ggq_slices(const struct ggq_slice_job *jobs, size_t n_jobs) {
     return run_jobs_sharded(cj);
 }
 
+int ggq_slices_device(const struct ggq_slice_job *jobs, size_t n_jobs, void *stream) {
+    if (n_jobs && !jobs) return fail(GGQ_ERR_INVALID, "null job table");
+    std::vector<Plan> plans(n_jobs);
+    for (size_t i = 0; i < n_jobs; i++) {  // validate everything before anything is enqueued
+        const ggq_slice_job &j = jobs[i];
+        int rc = j.quantize ? plan_quantize(j.type, j.fdt, j.dst_len, j.src_len, &plans[i]) : plan_dequantize(j.type, j.fdt, j.dst_len, j.src_len, &plans[i]);
+        if (rc != GGQ_OK) return rc;
+        if (plans[i].nblocks == 0) continue;
+        if (!j.dst || !j.src) return fail(GGQ_ERR_INVALID, "null pointer with non-zero length");
+        const void *fl = j.quantize ? j.src : j.dst, *pk = j.quantize ? (const void *)j.dst : j.src;
+        if ((reinterpret_cast<uintptr_t>(fl) & (fdt_size(j.fdt) - 1)) || (reinterpret_cast<uintptr_t>(pk) & 1))
+            return fail(GGQ_ERR_INVALID, "data is not aligned");
+    }
+    DevInfo dev;
+    int rc = resolve_device(&dev);
+    if (rc != GGQ_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // Stream order = job order, so a later job may read what an earlier one wrote.  Runs of consecutive dequantize jobs
+    // with one float side and a real block type share one grid (dequant.cu: dequant_blocks_batch); everything
+    // else (quantize jobs, f16 / bf16 "blocks") is one launch per job.
+    size_t i = 0;
+    while (i < n_jobs) {
+        const ggq_slice_job &j = jobs[i];
+        const bool batchable = !j.quantize && !is_float_type(j.type);
+        if (!batchable) {
+            if (plans[i].nblocks) {
+                const Plan &p = plans[i];
+                const uint32_t from = j.quantize ? p.fdt : p.ti->type, to = j.quantize ? p.ti->type : p.fdt;
+                // from == to (quantize::<f16, f16, 1>) is still mediated by f32 inside the cast kernel (lib.rs:66-73)
+                cudaError_t e = enqueue_hop(from, to, j.dst, j.src, p.nblocks * p.ti->elems, st, dev);
+                if (e != cudaSuccess) return fail_cuda(e, "ggq_slices_device");
+            }
+            i++;
+            continue;
+        }
+        std::vector<DequantJob> run;
+        const uint32_t fdt = j.fdt;
+        static const size_t split_big = getenv("GGQ_BATCH_SPLIT_BIG") ? (size_t)atoll(getenv("GGQ_BATCH_SPLIT_BIG")) : 0;  // tuning knob (elements)
+        cudaError_t e = cudaSuccess;
+        for (; i < n_jobs && !jobs[i].quantize && !is_float_type(jobs[i].type) && jobs[i].fdt == fdt; i++) {
+            if (!plans[i].nblocks) continue;
+            if (split_big && plans[i].nblocks * plans[i].ti->elems >= split_big) {  // big tensors on their dedicated kernels
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                if ((e = dequant_blocks(jobs[i].type, fdt, jobs[i].src, jobs[i].dst, plans[i].nblocks, st, dev)) != cudaSuccess) return fail_cuda(e, "ggq_slices_device");
+                continue;
+            }
+            run.push_back({jobs[i].type, jobs[i].src, jobs[i].dst, plans[i].nblocks});
+        }
+        if (run.empty()) continue;
+        if (run.size() == 1) {
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            e = dequant_blocks(run[0].type, fdt, run[0].src, run[0].dst, run[0].nblocks, st, dev);
+        } else {
+            uint64_t launches = 0;
+            e = dequant_blocks_batch(fdt, run.data(), run.size(), st, dev, &launches);
+            g_launches.fetch_add(launches, std::memory_order_relaxed);
+        }
+        if (e != cudaSuccess) return fail_cuda(e, "ggq_slices_device");
+    }
+    return GGQ_OK;
+}
+
 size_t ggq_plan_shards(const struct ggq_slice_job *jobs, size_t n_jobs, int n_devices, struct ggq_shard_piece *out, size_t cap) {
     if (n_jobs && !jobs) return 0;
     std::vector<JobGeom> geom;

@@ -98,6 +98,139 @@ static cudaError_t launch_dequant(const void *src, void *dst, size_t nblocks, cu
     }
 }
 
+// ---- batched launch: the tiles of up to DQ_BATCH_MAX tensors (any mix of block types, one float side) in ONE grid ----
+// A 4096x4096 tensor is a 7-9 us launch of which ramp and tail are a quarter; back to back with PDL the
+// attention-shaped tensors of a step still ran at 79-84 % of the copy peak.  Here every CTA takes one tile of
+// whichever tensor its block index falls into (descriptor table in the kernel parameters, a CTA-uniform switch
+// over the block type), so a step's tensors share one ramp and one tail and the hardware block scheduler streams
+// through all of them like through one big tensor (shape ONE above: short-lived 128-thread CTAs, 8 per SM, one
+// bulk copy per tile).
+constexpr int DQ_BATCH_MAX = 16;
+struct DqBatchJob {
+    const uint8_t *src;
+    void *dst;
+    unsigned long long nblocks;
+    unsigned int tile0;  // first tile (= block index) of this job in the grid
+    uint32_t type;
+};
+struct DqBatch {
+    DqBatchJob job[DQ_BATCH_MAX];
+    int n;
+};
+
+template <uint32_t T, class FT, int TILE_ELEMS, int THREADS>
+__device__ __forceinline__ void dequant_one_tile(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ dst, size_t nblocks, size_t t,
+                                                 uint64_t *bar, uint8_t *stage) {
+    using TR = BlockTraits<T>;
+    constexpr int TILE_BLOCKS = TILE_ELEMS / TR::ELEMS;
+    constexpr int TILE_BYTES = TILE_BLOCKS * TR::BYTES;
+    constexpr int UNITS = Decoder<T>::template units<FT::V>();
+    static_assert(TILE_BYTES % 16 == 0, "tile must be a whole number of 16-byte chunks");
+    const int tid = threadIdx.x;
+    const size_t full_tiles = nblocks / TILE_BLOCKS;
+    const bool vec = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+    const bool bulk = t < full_tiles && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    const int nb = t < full_tiles ? TILE_BLOCKS : (int)(nblocks % TILE_BLOCKS);
+    if (bulk) {
+        if (tid == 0) {
+            mbar_expect_tx(bar, TILE_BYTES);
+            bulk_g2s(stage, src + t * (size_t)TILE_BYTES, TILE_BYTES, bar);
+        }
+        mbar_wait(bar, 0);
+    } else {
+        cta_copy_g2s(stage, src + t * (size_t)TILE_BYTES, (uint32_t)nb * TR::BYTES, tid, THREADS);
+        __syncthreads();
+    }
+    typename FT::raw *out = dst + t * (size_t)TILE_ELEMS;
+    if (nb == TILE_BLOCKS) {
+#pragma unroll 2
+        for (int u = tid; u < TILE_BLOCKS * UNITS; u += THREADS)
+            Decoder<T>::template run<FT, 0>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
+    } else {
+        for (int u = tid; u < nb * UNITS; u += THREADS)
+            Decoder<T>::template run<FT, 0>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
+    }
+}
+
+template <class FT, int TILE_ELEMS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) dequant_batch_kernel(const __grid_constant__ DqBatch batch) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *stage = smem + 128;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    pdl_launch_dependents();
+    __syncthreads();
+    pdl_wait();
+    int j = 0;  // the job this CTA's tile belongs to (CTA-uniform)
+#pragma unroll
+    for (int k = 1; k < DQ_BATCH_MAX; k++)
+        if (k < batch.n && blockIdx.x >= batch.job[k].tile0) j = k;
+    const DqBatchJob &jb = batch.job[j];
+    const size_t t = blockIdx.x - jb.tile0;
+    typename FT::raw *dst = static_cast<typename FT::raw *>(jb.dst);
+#define GGQ_DQ_CASE(T) \
+    case T: dequant_one_tile<T, FT, TILE_ELEMS, THREADS>(jb.src, dst, (size_t)jb.nblocks, t, bar, stage); break;
+    switch (jb.type) {
+        GGQ_DQ_CASE(T_Q4_0) GGQ_DQ_CASE(T_Q4_1) GGQ_DQ_CASE(T_Q5_0) GGQ_DQ_CASE(T_Q5_1) GGQ_DQ_CASE(T_Q8_0) GGQ_DQ_CASE(T_Q8_1)
+        GGQ_DQ_CASE(T_Q2K) GGQ_DQ_CASE(T_Q3K) GGQ_DQ_CASE(T_Q4K) GGQ_DQ_CASE(T_Q5K) GGQ_DQ_CASE(T_Q6K) GGQ_DQ_CASE(T_Q8K)
+    }
+#undef GGQ_DQ_CASE
+}
+
+static int block_elems_of(uint32_t t) { return (t >= T_Q2K && t <= T_Q8K) ? 256 : 32; }
+static int block_bytes_of(uint32_t t) {
+    switch (t) {
+        case T_Q4_0: return 18; case T_Q4_1: return 20; case T_Q5_0: return 22; case T_Q5_1: return 24; case T_Q8_0: return 34; case T_Q8_1: return 36;
+        case T_Q2K: return 84; case T_Q3K: return 110; case T_Q4K: return 144; case T_Q5K: return 176; case T_Q6K: return 210; case T_Q8K: return 290;
+    }
+    return 0;
+}
+
+template <class FT, int TILE>
+static cudaError_t launch_dequant_batch(const DequantJob *jobs, size_t n, cudaStream_t stream, DevInfo dev, uint64_t *launches) {
+    constexpr int THREADS = 128, MINB = 8;
+    constexpr int SMEM = 128 + TILE / 256 * 290 + 16;  // the widest tile: Q8K
+    auto kern = dequant_batch_kernel<FT, TILE, THREADS, MINB>;
+    static std::atomic<int> occ_cache[MAX_DEVICES];
+    int ctas_per_sm = 0;
+    cudaError_t e = cached_occupancy(kern, THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);  // also raises the smem limit
+    if (e != cudaSuccess) return e;
+    size_t i = 0;
+    while (i < n) {
+        DqBatch b{};
+        unsigned long long tiles = 0;
+        for (; i < n && b.n < DQ_BATCH_MAX; i++) {
+            if (jobs[i].nblocks == 0) continue;
+            if (!block_bytes_of(jobs[i].type)) return cudaErrorInvalidValue;
+            const unsigned long long tb = TILE / block_elems_of(jobs[i].type);
+            const unsigned long long nt = (jobs[i].nblocks + tb - 1) / tb;
+            if (tiles + nt > 0x7FFFFFFFull) {  // grid.x limit: close this batch (a single job beyond it is split by the caller)
+                if (b.n == 0) return cudaErrorInvalidValue;
+                break;
+            }
+            b.job[b.n++] = {static_cast<const uint8_t *>(jobs[i].src), jobs[i].dst, (unsigned long long)jobs[i].nblocks, (unsigned int)tiles, jobs[i].type};
+            tiles += nt;
+        }
+        if (b.n == 0) continue;
+        e = launch_pdl(kern, (unsigned)tiles, THREADS, SMEM, stream, b);
+        if (e != cudaSuccess) return e;
+        if (launches) ++*launches;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t dequant_blocks_batch(uint32_t fdt, const DequantJob *jobs, size_t n, cudaStream_t stream, DevInfo dev, uint64_t *launches) {
+    switch (fdt) {
+        case T_F32: return launch_dequant_batch<F32, 8192>(jobs, n, stream, dev, launches);
+        case T_F16: return launch_dequant_batch<F16, 16384>(jobs, n, stream, dev, launches);
+        case T_BF16: return launch_dequant_batch<BF16, 16384>(jobs, n, stream, dev, launches);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <uint32_t T>
 static cudaError_t launch_dequant_fdt(uint32_t fdt, const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
     switch (fdt) {

@@ -17,6 +17,14 @@ struct DevInfo {
 
 // packed blocks -> float side.  `type` is a block type (legacy / K / Q8K).
 cudaError_t dequant_blocks(uint32_t type, uint32_t fdt, const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev);
+// the same for several tensors of one float side in ONE grid (descriptor table; see dequant.cu)
+struct DequantJob {
+    uint32_t type;
+    const void *src;
+    void *dst;
+    size_t nblocks;
+};
+cudaError_t dequant_blocks_batch(uint32_t fdt, const DequantJob *jobs, size_t n, cudaStream_t stream, DevInfo dev, uint64_t *launches);
 // float side -> packed blocks, legacy 32-element blocks and Q8K.
 cudaError_t quant_blocks_legacy(uint32_t type, uint32_t fdt, const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev);
 // float side -> packed blocks, K-quants (Q2K..Q6K).

@@ -157,6 +157,20 @@ def dequantize_slice_device(ty, fdt, dst, dst_elems, src, src_blocks, stream=0):
     _check(lib().ggq_dequantize_slice_device(ty, fdt, _ptr(dst), dst_elems, _ptr(src), src_blocks, stream))
 
 
+def slices_device(jobs, stream=0):
+    """`ggq_slices_device`: several device-pointer slice calls enqueued as one call; consecutive dequantize jobs of
+    one float side share a single grid.  `jobs`: ("quantize" | "dequantize", type, fdt, dst, dst_len, src, src_len)
+    with the lengths of the per-call entry points; or a prebuilt ctypes SliceJob array."""
+    from ._lib import SliceJob
+    if isinstance(jobs, ctypes.Array):
+        arr = jobs
+    else:
+        arr = (SliceJob * len(jobs))()
+        for i, (kind, ty, fdt, dst, dst_len, src, src_len) in enumerate(jobs):
+            arr[i] = SliceJob(ty, fdt, 1 if kind == "quantize" else 0, _ptr(dst), dst_len, _ptr(src), src_len)
+    _check(lib().ggq_slices_device(arr, len(arr), stream))
+
+
 class PinnedBuffer:
     """Page-locked host buffer from `ggq_host_alloc`, exposed as a numpy uint8 array (`.array`)."""
 

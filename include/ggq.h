@@ -136,6 +136,14 @@ int ggq_quantize_slice_device(uint32_t type, uint32_t fdt, void *dst, size_t dst
 int ggq_dequantize_slice_device(uint32_t type, uint32_t fdt, void *dst, size_t dst_elems,
                                 const void *src, size_t src_blocks, void *stream);
 
+/* Several device-pointer slice calls as ONE call, enqueued on `stream` in job order without synchronising
+ * (the device-side counterpart of ggq_slices).  Every job is validated first, with the checks and order of its
+ * slice call; on a failure nothing is enqueued.  Runs of consecutive dequantize jobs with the same `fdt` share a
+ * single grid — one descriptor-table launch whose CTAs each take one tile of whichever tensor they fall into —
+ * so the small tensors of a step (a 4096x4096 attention weight is a 7-9 us kernel on its own) pay one ramp and
+ * one tail between them instead of one each.  Results are identical to the per-call entry points. */
+int ggq_slices_device(const struct ggq_slice_job *jobs, size_t n_jobs, void *stream);
+
 /* ---- tensor casts (the caller of the slice API) ---------------------------------------------- */
 
 /* `cast(row, data, from, to)` — xtask/src/utils/operator/cast.rs:93-138, for every pair of supported

@@ -488,3 +488,79 @@ def test_fuzz_random_small_cases(ggq, oracle):
         want_d = oracle.dequantize(ty, fdt, want_q)
         gd = d.cpu().numpy()[foff:foff + x.nbytes].view(want_d.dtype)
         assert same_floats(gd, want_d), (case, ty, fdt, nb, foff, poff)
+
+
+@pytest.mark.parametrize("fdt", FDTS)
+def test_slices_device_batched_grid_bit_exact(ggq, oracle, fdt):
+    """ggq_slices_device: every block type dequantized in ONE descriptor-table grid (plus a quantize job and
+    f16 'blocks' in the same call) gives the bytes of the per-call entry points = the oracle's.  Sizes are
+    ragged (partial last tile), one source is only 2-byte aligned, one job is empty, and there are more than
+    16 dequantize jobs so the table spills into a second launch."""
+    import torch
+    from gguf_b200._lib import lib
+    st = torch.cuda.current_stream().cuda_stream
+    jobs, checks, keep = [], [], []
+    fdtype = torch.float32 if fdt == F32 else torch.uint16
+    for rep in range(2):
+        for k, ty in enumerate(ALLQ):
+            n, b = oracle.block_info(ty)
+            nb = (16384 // n) * (2 + k % 3) + 7 * (k + 1) + rep           # a few full tiles and a ragged one
+            blocks = random_packed(ty, nb, b, 900 + 31 * rep + ty)
+            want = oracle.dequantize(ty, fdt, blocks, threads=8)
+            off = 2 if (k == 3 and rep == 0) else 0                       # one misaligned source
+            d_src = torch.zeros(blocks.size + 16, dtype=torch.uint8, device="cuda")
+            d_src[off:off + blocks.size] = torch.from_numpy(blocks).cuda()
+            d_dst = torch.zeros(nb * n, dtype=fdtype, device="cuda")
+            keep += [d_src, d_dst]
+            jobs.append(("dequantize", ty, fdt, d_dst, nb * n, d_src.data_ptr() + off, nb))
+            checks.append((d_dst, want, None, None))
+    assert len(jobs) > 16
+    jobs.insert(5, ("dequantize", 8, fdt, 0, 0, 0, 0))                    # empty job inside the run
+    x = to_fdt(gaussian(32 * 4099, 5), F16)
+    d_x = torch.from_numpy(x).cuda()
+    d_q = torch.zeros(4099 * 34, dtype=torch.uint8, device="cuda")
+    jobs.insert(9, ("quantize", 8, F16, d_q, 4099, d_x, 32 * 4099))       # splits the dequantize run in two
+    checks.append((d_q, oracle.quantize(8, F16, x, threads=8), 8, 34))
+    d_h = torch.zeros(32 * 4099, dtype=torch.float32, device="cuda")
+    jobs.append(("dequantize", 1, F32, d_h, 32 * 4099, d_x, 32 * 4099))   # f16 as a 1-element block -> f32
+    checks.append((d_h, x.view(np.float16).astype(np.float32), None, None))
+    before = lib().ggq_launch_count()
+    ggq.slices_device(jobs, st)
+    torch.cuda.synchronize()
+    launches = lib().ggq_launch_count() - before
+    assert launches <= 6, launches                                        # 24 dequantize jobs in <= 4 grids + 2 single launches
+    for d, want, ty, b in checks:
+        got = d.cpu().numpy()
+        if ty is None:
+            assert same_floats(got, want)
+        else:
+            assert same_blocks(got, want, ty, b)
+    # validation happens before anything is enqueued, in the slice calls' order
+    bad = list(jobs) + [("dequantize", 2, fdt, checks[0][0], 31, keep[0], 1)]
+    with pytest.raises(ggq.QuantizeError) as e:
+        ggq.slices_device(bad, st)
+    assert e.value.kind == "Indivisible"
+
+
+def test_slices_device_full_size_step_equals_per_call(ggq):
+    """bench.py's step (4 types x {4096x14336, 4096x4096} -> f16) through the batched grid equals the eight
+    per-call launches byte for byte."""
+    import torch
+    st = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator(device="cuda"); gen.manual_seed(3)
+    jobs, pairs = [], []
+    for ty in (2, 8, 12, 14):
+        e, b = ggq.block_info(ty)
+        for n in (4096 * 14336, 4096 * 4096):
+            x = (torch.randn(n, device="cuda", generator=gen) * 0.02).to(torch.float16)
+            packed = torch.empty(n // e * b, dtype=torch.uint8, device="cuda")
+            ggq.quantize_slice_device(ty, F16, packed, n // e, x, n, st)
+            a, c = torch.zeros(n, dtype=torch.float16, device="cuda"), torch.zeros(n, dtype=torch.float16, device="cuda")
+            ggq.dequantize_slice_device(ty, F16, a, n, packed, n // e, st)
+            jobs.append(("dequantize", ty, F16, c, n, packed, n // e))
+            pairs.append((a, c))
+            del x
+    ggq.slices_device(jobs, st)
+    torch.cuda.synchronize()
+    for a, c in pairs:
+        assert torch.equal(a.view(torch.int16), c.view(torch.int16))

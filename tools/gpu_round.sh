@@ -1,0 +1,14 @@
+#!/bin/bash
+# One gpurun call's worth of work; phases selected by arguments (tests bench ncu_bench ...).  Output -> gpurun_out/.
+mkdir -p gpurun_out
+for phase in "$@"; do
+  case $phase in
+    tests)   timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/tests.log; tail -3 gpurun_out/tests.log ;;
+    bench)   timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 600 gpurun_out/bench_n1.err; head -c 300 gpurun_out/bench_n1.json; echo ;;
+    bench_split) GGQ_BATCH_SPLIT_BIG=25165824 timeout 600 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu > gpurun_out/bench_n1_split.json 2> gpurun_out/bench_n1_split.err; head -c 300 gpurun_out/bench_n1_split.json; echo ;;
+    ref)     timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2>&1 ;;
+    pcie)    timeout 300 python tools/pcie_probe.py > gpurun_out/pcie_probe.txt 2>&1 ;;
+    sweep)   timeout 900 python tools/codec_sweep.py > gpurun_out/codec_sweep.txt 2>&1; tail -5 gpurun_out/codec_sweep.txt ;;
+    *) echo "unknown phase $phase" ;;
+  esac
+done
