@@ -176,7 +176,7 @@ class CpuPort:
         for ty, n, packed, out in self.work:
             e, _ = BLOCK[ty]
             if cold:  # cast.rs:158-161: the caller maps a fresh anonymous region for every tensor it produces
-                m = mmap.mmap(-1, n * 2)
+                m = mmap.mmap(-1, n * 2, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)  # what memmap2's map_anon maps
                 dst = np.frombuffer(m, np.uint16)
             else:
                 dst = out
@@ -451,7 +451,7 @@ def ours(args, rank, world, local_rank):
             pj = (SliceJob * len(host))()
             for i, (w, _, _) in enumerate(host):
                 if cold:
-                    m = mmap.mmap(-1, w["n"] * 2)
+                    m = mmap.mmap(-1, w["n"] * 2, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
                     maps.append(m)
                     dst = np.frombuffer(m, np.uint16)
                 else:
