@@ -1,0 +1,105 @@
+// kq_sweep.cu — times configurations of the shipped K-quant quantize kernel template (gguf_b200/csrc/quant_k_kernel.cuh)
+// on a 4096x14336 f16 (or f32) Gaussian tensor and checks that every configuration writes the same bytes as the first.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -fmad=false --ftz=false --prec-div=true --prec-sqrt=true \
+//        -I gguf_b200/csrc tools/kq_sweep.cu -o tools/kq_sweep
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "quant_k_kernel.cuh"
+
+using namespace ggq;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+static int g_sms = 148;
+static std::vector<uint8_t> g_ref;
+static const char *g_only = nullptr;   // argv[2]: run only configurations whose name contains this (e.g. T_Q6K)
+static bool g_first_only = false;      // argv[3] == "first": only the reference configuration of each type (for ncu)
+
+template <uint32_t T, class FT, class CFG>
+void run(const char *name, const void *d_x, uint8_t *d_out, size_t nblocks, bool is_ref) {
+    if (g_only && !strstr(name, g_only)) return;
+    if (g_first_only && !is_ref) return;
+    constexpr int SBW = 32 / (256 / KQuant<T>::SUB);
+    constexpr int BYTES = BlockTraits<T>::BYTES;
+    auto kern = quant_k_kernel<T, FT, CFG>;
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, kern));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CFG::THREADS, 0));
+    const size_t ngroups = (nblocks + SBW - 1) / SBW;
+    size_t grid = (size_t)g_sms * occ;
+    if (grid > (ngroups + CFG::WARPS - 1) / CFG::WARPS) grid = (ngroups + CFG::WARPS - 1) / CFG::WARPS;
+    CK(cudaMemset(d_out, 0xEE, nblocks * BYTES));
+    kern<<<(unsigned)grid, CFG::THREADS>>>(static_cast<const typename FT::raw *>(d_x), d_out, nblocks, 1.0f);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int reps = 3;
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < reps; r++) kern<<<(unsigned)grid, CFG::THREADS>>>(static_cast<const typename FT::raw *>(d_x), d_out, nblocks, 1.0f);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<uint8_t> out(nblocks * BYTES);
+    CK(cudaMemcpy(out.data(), d_out, out.size(), cudaMemcpyDeviceToHost));
+    const char *same = "ref";
+    if (is_ref) g_ref = out;
+    else same = (out.size() == g_ref.size() && memcmp(out.data(), g_ref.data(), out.size()) == 0) ? "same bytes" : "BYTES DIFFER";
+    printf("%-26s regs %3d  spill %3zu  smem %6zu  warps/SM %2d  %9.1f us   %s\n", name, fa.numRegs, (size_t)fa.localSizeBytes, (size_t)fa.sharedSizeBytes, occ * CFG::WARPS,
+           ms * 1000.f / reps, same);
+    fflush(stdout);
+}
+
+#define RUN(T, FT, W, REGS, LF, WM, ST, ref) run<T, FT, KqCfg<W, REGS, LF, WM, ST>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST ">", d_x, d_out, nblocks, ref)
+#define RUNA(T, FT, W, REGS, LF, WM, ST, AF) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF ">", d_x, d_out, nblocks, false)
+
+int main(int argc, char **argv) {
+    const bool f32 = argc > 1 && !strcmp(argv[1], "f32");
+    if (argc > 2 && strcmp(argv[2], "all")) g_only = argv[2];
+    g_first_only = argc > 3 && !strcmp(argv[3], "first");
+    const size_t n = (size_t)4096 * 14336, nblocks = n / 256;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    g_sms = prop.multiProcessorCount;
+    std::vector<float> x(n);
+    std::mt19937 rng(2);
+    std::normal_distribution<float> nd(0.f, 0.02f);
+    for (auto &v : x) v = nd(rng);
+    void *d_x;
+    uint8_t *d_out;
+    CK(cudaMalloc(&d_out, nblocks * 210));
+    if (f32) {
+        CK(cudaMalloc(&d_x, n * 4));
+        CK(cudaMemcpy(d_x, x.data(), n * 4, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<__half> h(n);
+        for (size_t i = 0; i < n; i++) h[i] = __float2half_rn(x[i]);
+        CK(cudaMalloc(&d_x, n * 2));
+        CK(cudaMemcpy(d_x, h.data(), n * 2, cudaMemcpyHostToDevice));
+    }
+    printf("%s input, %zu elements, %d SMs; config <WARPS, REGS, LF, WM, STAGES>\n", f32 ? "f32" : "f16", n, g_sms);
+    if (!f32) {
+        RUN(T_Q4K, F16, 4, 128, 0, 2, 2, true);
+        RUNA(T_Q4K, F16, 4, 128, 0, 2, 2, 1);
+        RUNA(T_Q4K, F16, 4, 128, 0, 2, 1, 1);
+        RUN(T_Q5K, F16, 4, 128, 0, 2, 2, true);
+        RUNA(T_Q5K, F16, 4, 128, 0, 2, 2, 1);
+        RUN(T_Q2K, F16, 4, 72, 0, 2, 2, true);
+        RUNA(T_Q2K, F16, 4, 72, 0, 2, 2, 1);
+        RUNA(T_Q2K, F16, 4, 64, 0, 2, 2, 1);
+        RUNA(T_Q2K, F16, 1, 64, 0, 2, 2, 1);
+        RUN(T_Q6K, F16, 4, 96, 0, 2, 2, true);
+        RUN(T_Q3K, F16, 4, 96, 0, 2, 2, true);
+    } else {
+        RUN(T_Q4K, F32, 4, 128, 0, 2, 2, true);
+        RUNA(T_Q4K, F32, 4, 128, 0, 2, 2, 1);
+        RUN(T_Q2K, F32, 4, 72, 0, 2, 2, true);
+        RUNA(T_Q2K, F32, 4, 72, 0, 2, 2, 1);
+    }
+    return 0;
+}
