@@ -57,6 +57,7 @@ void run(const char *name, const void *d_x, uint8_t *d_out, size_t nblocks, bool
 
 #define RUN(T, FT, W, REGS, LF, WM, ST, ref) run<T, FT, KqCfg<W, REGS, LF, WM, ST>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST ">", d_x, d_out, nblocks, ref)
 #define RUNA(T, FT, W, REGS, LF, WM, ST, AF) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF ">", d_x, d_out, nblocks, false)
+#define RUNR(T, FT, W, REGS, LF, WM, ST, AF, RM) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM ">", d_x, d_out, nblocks, false)
 
 int main(int argc, char **argv) {
     const bool f32 = argc > 1 && !strcmp(argv[1], "f32");
@@ -86,20 +87,21 @@ int main(int argc, char **argv) {
     if (!f32) {
         RUN(T_Q4K, F16, 4, 128, 0, 2, 2, true);
         RUNA(T_Q4K, F16, 4, 128, 0, 2, 2, 1);
-        RUNA(T_Q4K, F16, 4, 128, 0, 2, 1, 1);
+        RUNR(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 2);
+        RUNR(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 1);
         RUN(T_Q5K, F16, 4, 128, 0, 2, 2, true);
-        RUNA(T_Q5K, F16, 4, 128, 0, 2, 2, 1);
+        RUNR(T_Q5K, F16, 4, 128, 0, 2, 2, 1, 2);
         RUN(T_Q2K, F16, 4, 72, 0, 2, 2, true);
-        RUNA(T_Q2K, F16, 4, 72, 0, 2, 2, 1);
-        RUNA(T_Q2K, F16, 4, 64, 0, 2, 2, 1);
         RUNA(T_Q2K, F16, 1, 64, 0, 2, 2, 1);
+        RUNR(T_Q2K, F16, 1, 64, 0, 2, 2, 1, 2);
         RUN(T_Q6K, F16, 4, 96, 0, 2, 2, true);
+        RUNR(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 2);
+        RUNR(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 1);
+        RUNR(T_Q6K, F16, 4, 80, 0, 2, 2, 0, 2);
         RUN(T_Q3K, F16, 4, 96, 0, 2, 2, true);
     } else {
-        RUN(T_Q4K, F32, 4, 128, 0, 2, 2, true);
-        RUNA(T_Q4K, F32, 4, 128, 0, 2, 2, 1);
-        RUN(T_Q2K, F32, 4, 72, 0, 2, 2, true);
-        RUNA(T_Q2K, F32, 4, 72, 0, 2, 2, 1);
+        RUN(T_Q6K, F32, 4, 96, 0, 2, 2, true);
+        RUNR(T_Q6K, F32, 4, 96, 0, 2, 2, 0, 2);
     }
     return 0;
 }
