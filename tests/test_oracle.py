@@ -145,3 +145,76 @@ def test_kquant_quantize_matches_independent_numpy_restatement(oracle, ty):
     _, b = oracle.block_info(ty)
     bad = np.flatnonzero((got.reshape(-1, b) != want.reshape(-1, b)).any(axis=1))
     assert bad.size == 0, f"{bad.size} of {x.size // 256} super-blocks differ, first at {bad[:5]}"
+
+
+# ---- known answers derived from the Rust text by a third, scalar numpy restatement (tests/golden/rust_restatement.py) ----
+KAT_TYPES = [2, 3, 6, 7, 8, 9, 15]
+KAT_FDT = [(0, "f32"), (1, "f16"), (30, "bf16")]
+
+
+def test_rust_restatement_reproduces_the_hand_derived_readme_block():
+    """The restatement the KATs come from is itself pinned: README block (App. C.1) and gguf-py on non-zero blocks."""
+    import sys
+    sys.path.insert(0, G)
+    import rust_restatement as R
+    k = np.load(os.path.join(G, "readme_block.npz"))
+    for name, ty in [("q8_0", 8), ("q4_0", 2), ("q4_1", 3), ("q5_0", 6), ("q8_1", 9)]:
+        assert R.quantize(ty, k["x"]).tobytes() == k[name].tobytes(), name
+    g = np.load(os.path.join(G, "gguf_py_legacy.npz"))
+    x = g["x"][:32 * 96]
+    for name, ty in LEGACY.items():
+        b = {2: 18, 3: 20, 6: 22, 7: 24, 8: 34}[ty]
+        assert np.array_equal(R.quantize(ty, x), g[name][:96 * b]), name
+        assert np.array_equal(R.dequantize(ty, g[name][:96 * b]).view(np.uint32), g[name + "_deq"][:32 * 96].view(np.uint32)), name
+
+
+@pytest.mark.parametrize("ty", KAT_TYPES)
+def test_oracle_matches_rust_kat(oracle, ty):
+    """Q8K, Q5_1, Q8_1 (sum from the unrounded delta), the f16 / bf16 float sides, NaN / inf / tie / zero rows:
+    quantize bytes and dequantize bits equal the known answers of tests/golden/rust_kat.npz."""
+    k = np.load(os.path.join(G, "rust_kat.npz"))
+    for fdt, name in KAT_FDT:
+        x = k[f"x_{ty}"] if fdt == 0 else k[f"x_{ty}_{name}"]
+        assert np.array_equal(oracle.quantize(ty, fdt, x), k[f"q_{ty}_{name}"]), (ty, name)
+        want = k[f"d_{ty}_{name}"]
+        got = oracle.dequantize(ty, fdt, k[f"b_{ty}"])
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), (ty, name)
+
+
+def test_oracle_matches_rust_reference_dump_when_present(oracle):
+    """`cargo run --example dump_golden` (rust/ggml-quants-cuda) writes the REFERENCE's own outputs to
+    tests/golden/rust_reference.bin; when that file is there, every record must be reproduced by the oracle."""
+    import struct
+    path = os.path.join(G, "rust_reference.bin")
+    if not os.path.exists(path):
+        pytest.skip("no Rust toolchain here: tests/golden/rust_reference.bin has not been generated")
+    from data import same_blocks, same_floats
+    buf = open(path, "rb").read()
+    assert buf[:4] == b"GGQR" and struct.unpack_from("<I", buf, 4)[0] == 1
+    p, n_rec = 8, 0
+    while p < len(buf):
+        kind, ty, fdt, n, nin, nout = struct.unpack_from("<IIIQQQ", buf, p)
+        p += 36
+        din, dout = np.frombuffer(buf, np.uint8, nin, p), np.frombuffer(buf, np.uint8, nout, p + nin)
+        p += nin + nout
+        fl = np.float32 if fdt == 0 else np.uint16
+        if kind == 0:
+            got = oracle.quantize(ty, fdt, din.view(fl))
+            _, b = oracle.block_info(ty)
+            assert same_blocks(got, dout, ty, b) if ty not in (1, 30) else np.array_equal(got, dout), (kind, ty, fdt)
+        else:
+            got = oracle.dequantize(ty, fdt, din)
+            assert same_floats(got, dout.view(fl)), (kind, ty, fdt)
+        n_rec += 1
+    assert n_rec >= 60
+
+
+def test_rust_ffi_declares_every_header_symbol():
+    """rust/ggml-quants-cuda-sys/src/lib.rs is source-only here (no cargo); at least its extern block must name
+    exactly the functions include/ggq.h declares."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "ggq.h")).read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(ggq_[a-z_0-9]+)\s*\(", hdr)))
+    rs = open(os.path.join(root, "rust", "ggml-quants-cuda-sys", "src", "lib.rs")).read()
+    assert sorted(set(re.findall(r"pub fn (ggq_[a-z_0-9]+)\s*\(", rs))) == declared

@@ -564,3 +564,17 @@ def test_slices_device_full_size_step_equals_per_call(ggq):
     torch.cuda.synchronize()
     for a, c in pairs:
         assert torch.equal(a.view(torch.int16), c.view(torch.int16))
+
+
+@pytest.mark.parametrize("ty", [2, 3, 6, 7, 8, 9, 15])
+def test_gpu_matches_rust_kat_without_the_oracle(ggq, ty):
+    """libggq against the known answers derived from the Rust text (tests/golden/rust_kat.npz, made by the scalar numpy
+    restatement in tests/golden/rust_restatement.py): Q8K, Q5_1, Q8_1's sum, f16 / bf16 float sides, NaN / inf / tie /
+    zero rows.  The oracle is not involved."""
+    import os
+    k = np.load(os.path.join(os.path.dirname(__file__), "golden", "rust_kat.npz"))
+    for fdt, name in ((F32, "f32"), (F16, "f16"), (BF16, "bf16")):
+        x = k[f"x_{ty}"] if fdt == F32 else k[f"x_{ty}_{name}"]
+        assert np.array_equal(ggq.quantize(ty, x, fdt), k[f"q_{ty}_{name}"]), (ty, name)
+        got = ggq.dequantize(ty, k[f"b_{ty}"], fdt)
+        assert np.array_equal(got.view(np.uint8), k[f"d_{ty}_{name}"].view(np.uint8)), (ty, name)
