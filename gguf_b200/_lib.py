@@ -47,7 +47,9 @@ class ShardPiece(_c.Structure):
 class ConvertStats(_c.Structure):
     _fields_ = [("n_tensors", _c.c_uint64), ("n_cast_tensors", _c.c_uint64), ("cast_elems", _c.c_uint64), ("bytes_in", _c.c_uint64),
                 ("bytes_out", _c.c_uint64), ("seconds_plan", _c.c_double), ("seconds_convert", _c.c_double),
-                ("seconds_sync", _c.c_double), ("n_devices", _c.c_int), ("n_out_files", _c.c_int), ("n_rearranged_tensors", _c.c_uint64)]
+                ("seconds_sync", _c.c_double), ("n_devices", _c.c_int), ("n_out_files", _c.c_int), ("n_rearranged_tensors", _c.c_uint64),
+                ("n_workers", _c.c_int), ("worker_seconds_read", _c.c_double), ("worker_seconds_write", _c.c_double),
+                ("worker_seconds_gpu_wait", _c.c_double), ("h2d_bytes", _c.c_uint64), ("d2h_bytes", _c.c_uint64)]
 
 
 class ConvertOptions(_c.Structure):

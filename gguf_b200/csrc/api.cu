@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <condition_variable>
@@ -28,6 +29,14 @@ namespace {
 using namespace ggq;
 
 thread_local std::string t_err;
+thread_local ggq::PipeCounters t_pipe;  // see ggq_internal.h
+uint64_t now_ns() { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+cudaError_t timed_event_sync(cudaEvent_t ev) {  // cudaEventSynchronize, counted as time blocked on the GPU
+    const uint64_t t0 = now_ns();
+    const cudaError_t e = cudaEventSynchronize(ev);
+    t_pipe.gpu_wait_ns += now_ns() - t0;
+    return e;
+}
 thread_local int t_device = -1;  // ggq_set_device override for the calling thread
 std::atomic<uint64_t> g_launches{0};
 thread_local int t_shard_devices = 1;  // ggq_set_shard_devices: GPUs the calling thread's host-pointer calls are split over
@@ -354,7 +363,7 @@ int run_jobs_io(const std::vector<ChainJob> &jobs) {
         if (c >= NSLOTS) {  // retire chunk c - NSLOTS
             const Chunk &r = chunks[c - NSLOTS];
             const ChainJob &rj = jobs[r.job];
-            if ((e = cudaEventSynchronize(s.done)) != cudaSuccess) break;
+            if ((e = timed_event_sync(s.done)) != cudaSuccess) break;
             const uint32_t t_out = rj.chain.back();
             if (!rj.io.direct_dst) io_ok = rj.io.write(s.h_out, type_nbytes(t_out, rj.elem_base + r.e0), type_nbytes(t_out, r.e1 - r.e0));
         }
@@ -372,6 +381,8 @@ int run_jobs_io(const std::vector<ChainJob> &jobs) {
                 hsrc = static_cast<const char *>(s.h_in);
             }
             if ((e = cudaMemcpyAsync(s.d_a, hsrc, type_nbytes(t_in, ne), cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) break;
+            t_pipe.h2d_bytes += type_nbytes(t_in, ne);
+            t_pipe.d2h_bytes += type_nbytes(t_out, ne);
             void *cur = s.d_a, *nxt = s.d_b;
             for (size_t h = 0; h + 1 < job.chain.size(); h++) {
                 if ((e = enqueue_hop(job.chain[h], job.chain[h + 1], nxt, cur, ne, s.stream, dev)) != cudaSuccess) break;
@@ -623,6 +634,12 @@ void configure_mem_pool(int device) {  // keep freed stream-ordered allocations 
 
 namespace ggq {
 
+PipeCounters take_pipe_counters() {
+    const PipeCounters c = t_pipe;
+    t_pipe = PipeCounters();
+    return c;
+}
+
 size_t device_free_bytes() {
     DevInfo dev;
     if (resolve_device(&dev) != GGQ_OK) return 0;
@@ -685,8 +702,9 @@ int Resident::upload(void *d_dst, size_t nbytes, const ReadFn &read) {
     for (size_t off = 0; off < nbytes; off += CH, c++) {
         Slot &s = impl_->pl->slots[c % NSLOTS];
         const size_t n = std::min(CH, nbytes - off);
-        cudaError_t e = cudaEventSynchronize(s.done);  // the H2D that last used this bounce buffer
+        cudaError_t e = timed_event_sync(s.done);  // the H2D that last used this bounce buffer
         if (e != cudaSuccess) return fail_cuda(e, "upload");
+        t_pipe.h2d_bytes += n;
         if (!read(s.h_in, off, n)) return fail(GGQ_ERR_INVALID, "I/O callback failed while uploading a tensor");
         if ((e = cudaMemcpyAsync(static_cast<char *>(d_dst) + off, s.h_in, n, cudaMemcpyHostToDevice, impl_->stream)) != cudaSuccess ||
             (e = cudaEventRecord(s.done, impl_->stream)) != cudaSuccess)
@@ -712,8 +730,9 @@ int Resident::download(const void *d_src, size_t nbytes, const WriteFn &write) {
             const size_t r = c - (NSLOTS - 1);
             Slot &s = impl_->pl->slots[r % NSLOTS];
             const size_t off = r * CH, n = std::min(CH, nbytes - off);
-            cudaError_t e = cudaEventSynchronize(s.done);
+            cudaError_t e = timed_event_sync(s.done);
             if (e != cudaSuccess) return fail_cuda(e, "download");
+            t_pipe.d2h_bytes += n;
             if (!write(s.h_out, off, n)) return fail(GGQ_ERR_INVALID, "I/O callback failed while downloading a tensor");
         }
     }

@@ -73,7 +73,16 @@ struct InFile {
     ~InFile() { if (fd >= 0) close(fd); }
 };
 
+thread_local uint64_t t_read_ns = 0, t_write_ns = 0;  // this worker's time inside pread / pwrite (ggq_convert_stats)
+struct ScopedNs {
+    uint64_t &acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit ScopedNs(uint64_t &a) : acc(a) {}
+    ~ScopedNs() { acc += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 bool pread_all(int fd, void *buf, size_t n, uint64_t off) {
+    ScopedNs timer(t_read_ns);
     char *p = static_cast<char *>(buf);
     while (n) {
         ssize_t r = pread(fd, p, n, (off_t)off);
@@ -83,6 +92,7 @@ bool pread_all(int fd, void *buf, size_t n, uint64_t off) {
     return true;
 }
 bool pwrite_all(int fd, const void *buf, size_t n, uint64_t off) {
+    ScopedNs timer(t_write_ns);
     const char *p = static_cast<const char *>(buf);
     while (n) {
         ssize_t r = pwrite(fd, p, n, (off_t)off);
@@ -488,6 +498,7 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
         std::atomic<size_t> next{0};
         std::atomic<int> rc_all{GGQ_OK};
         std::atomic<uint64_t> cast_elems{0}, cast_tensors{0}, rearranged{0};
+        std::atomic<uint64_t> read_ns{0}, write_ns{0}, gpu_wait_ns{0}, h2d_bytes{0}, d2h_bytes{0};
         std::string first_err;
         std::mutex err_mu;
         const int ndev_avail = ggq_device_count();
@@ -535,6 +546,15 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
         // and the caller's thread must come back from this call as it went in (device, sharding state).  The layout
         // helpers and allocations below emit() can throw; an exception must become a status, not std::terminate.
         auto worker = [&](int dev) {
+            t_read_ns = t_write_ns = 0;
+            ggq::take_pipe_counters();
+            struct Flush {  // whatever way the worker leaves, its counters reach the totals
+                std::atomic<uint64_t> &r, &w, &g, &h, &d;
+                ~Flush() {
+                    const ggq::PipeCounters c = ggq::take_pipe_counters();
+                    r += t_read_ns; w += t_write_ns; g += c.gpu_wait_ns; h += c.h2d_bytes; d += c.d2h_bytes;
+                }
+            } flush{read_ns, write_ns, gpu_wait_ns, h2d_bytes, d2h_bytes};
             try {
                 worker_body(dev);
             } catch (const std::exception &e) {
@@ -543,9 +563,9 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
                 set_err(GGQ_ERR_INVALID, "unknown exception in a convert worker");
             }
         };
+        const int nworkers = ndev * WORKERS_PER_DEVICE;  // plain copies are file I/O: they want the threads too
         if (!o.no_data) {
             std::vector<std::thread> th;
-            const int nworkers = ndev * WORKERS_PER_DEVICE;  // plain copies are file I/O: they want the threads too
             for (int w = 0; w < nworkers; w++) th.emplace_back(worker, w % ndev);
             for (auto &x : th) x.join();
             if (rc_all.load() != GGQ_OK) return failc(rc_all.load(), first_err);
@@ -563,6 +583,12 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
             stats->n_devices = ndev;
             stats->n_out_files = (int)outs.size();
             stats->n_rearranged_tensors = rearranged.load();
+            stats->n_workers = o.no_data ? 0 : nworkers;
+            stats->worker_seconds_read = read_ns.load() * 1e-9;
+            stats->worker_seconds_write = write_ns.load() * 1e-9;
+            stats->worker_seconds_gpu_wait = gpu_wait_ns.load() * 1e-9;
+            stats->h2d_bytes = h2d_bytes.load();
+            stats->d2h_bytes = d2h_bytes.load();
         }
         return GGQ_OK;
     } catch (const std::exception &e) {

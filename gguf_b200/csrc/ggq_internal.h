@@ -27,6 +27,11 @@ int cast_chain_io(const uint32_t *types, int n_types, size_t n_elems, const Chai
 // memcpy with non-temporal stores (host_copy.cpp): for the bounce copies to / from pinned staging buffers.
 void stream_copy(void *dst, const void *src, size_t n);
 
+// Per-thread accounting of the host pipelines (run_jobs_io, Resident::upload / download): nanoseconds the calling
+// thread spent blocked on the GPU and the bytes it moved over PCIe since the last take.  For ggq_convert_stats.
+struct PipeCounters { uint64_t gpu_wait_ns = 0, h2d_bytes = 0, d2h_bytes = 0; };
+PipeCounters take_pipe_counters();
+
 // Free device memory (bytes) on the calling thread's device, 0 when it cannot be queried.
 size_t device_free_bytes();
 

@@ -199,6 +199,13 @@ struct ggq_convert_stats {
     int n_devices;
     int n_out_files;
     uint64_t n_rearranged_tensors; /* tensors evaluated device-resident (rows moved by the rearrange kernel) */
+    /* per-stage accounting of the streaming pipeline, summed over the worker threads (so each can exceed the wall
+     * clock `seconds_convert`; divide by n_workers for a per-thread average): */
+    int n_workers;
+    double worker_seconds_read;     /* pread of input bytes into pinned staging */
+    double worker_seconds_write;    /* pwrite of output bytes from pinned staging */
+    double worker_seconds_gpu_wait; /* blocked on the GPU: H2D + kernels + D2H of a chunk not finished yet */
+    uint64_t h2d_bytes, d2h_bytes;  /* bytes that crossed PCIe in each direction */
 };
 
 /* `OutputArgs` of xtask (xtask/src/utils/output.rs:8-53); zero means "unlimited" / "off". */

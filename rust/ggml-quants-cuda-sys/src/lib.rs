@@ -43,6 +43,12 @@ pub struct GgqConvertStats {
     pub n_devices: c_int,
     pub n_out_files: c_int,
     pub n_rearranged_tensors: u64,
+    pub n_workers: c_int,
+    pub worker_seconds_read: f64,
+    pub worker_seconds_write: f64,
+    pub worker_seconds_gpu_wait: f64,
+    pub h2d_bytes: u64,
+    pub d2h_bytes: u64,
 }
 
 #[repr(C)]

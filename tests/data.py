@@ -111,3 +111,25 @@ def same_blocks(a, b, ty, bytes_per_block):
         a[both_nan, o] = b[both_nan, o]
         a[both_nan, o + 1] = b[both_nan, o + 1]
     return bool(np.array_equal(a, b))
+
+
+def nan_rule_usage(got, want, ty, blocks, bytes_per_block):
+    """How much of a dequantize comparison leans on the NaN ~ NaN rule of same_floats().
+    Returns (n_relaxed, n_total, ok): `n_relaxed` elements are NaN on both sides with different payloads; `ok` is False
+    if any of them sits in a block whose f16 header fields are all finite — there the comparison must be bit-exact,
+    the rule is only for arithmetic on a NaN / infinite scale (inf * 0, NaN * q), whose payload is the platform's."""
+    got = np.asarray(got); want = np.asarray(want)
+    if got.dtype == np.float32:
+        ua, ub = got.view(np.uint32), want.view(np.uint32)
+        na, nb = (ua & 0x7FFFFFFF) > 0x7F800000, (ub & 0x7FFFFFFF) > 0x7F800000
+    else:
+        ua, ub = got.view(np.uint16), want.view(np.uint16)
+        na, nb = (ua & 0x7FFF) > 0x7C00, (ub & 0x7FFF) > 0x7C00
+    relaxed = (ua != ub) & na & nb
+    blk = np.asarray(blocks, np.uint8).reshape(-1, bytes_per_block)
+    finite = np.ones(len(blk), bool)
+    for o in FIELDS_F16[ty]:
+        h = blk[:, o].astype(np.uint16) | (blk[:, o + 1].astype(np.uint16) << 8)
+        finite &= (h & 0x7C00) != 0x7C00
+    per_block = relaxed.reshape(len(blk), -1).any(axis=1)
+    return int(relaxed.sum()), int(relaxed.size), not bool((per_block & finite).any())

@@ -6,7 +6,7 @@ import threading
 import numpy as np
 import pytest
 
-from data import (BF16, F16, F32, edge_blocks, gaussian, random_packed, same_blocks, same_floats, to_fdt)
+from data import (BF16, F16, F32, edge_blocks, gaussian, nan_rule_usage, random_packed, same_blocks, same_floats, to_fdt)
 
 pytestmark = pytest.mark.gpu
 
@@ -49,6 +49,30 @@ def test_dequantize_bit_exact(ggq, oracle, ty, fdt, wild):
     got = ggq.dequantize(ty, blocks, fdt)
     want = oracle.dequantize(ty, fdt, blocks, threads=8)
     assert same_floats(got, want)
+    # the NaN ~ NaN rule may only ever act inside blocks whose scale fields are NaN / inf (random bytes: ~3 % of the
+    # f16 patterns); blocks with finite fields are compared bit for bit.  The share is recorded for DESIGN.md §5.
+    relaxed, total, ok = nan_rule_usage(got, want, ty, blocks, b)
+    assert ok, "NaN ~ NaN was needed in a block with finite scale fields"
+    if not wild:
+        assert relaxed == 0
+    NAN_RULE.append({"type": ty, "fdt": fdt, "wild": wild, "relaxed_elements": relaxed, "elements": total})
+
+
+NAN_RULE = []
+
+
+def test_zz_nan_rule_report():
+    """Writes gpurun_out/nan_rule.json: how many dequantize outputs of the wild (random-byte) cases were accepted as
+    NaN ~ NaN instead of bit-equal (all of them inside blocks with a NaN / infinite scale field)."""
+    import json, os
+    if not NAN_RULE:
+        pytest.skip("runs after test_dequantize_bit_exact")
+    wild = [r for r in NAN_RULE if r["wild"]]
+    out = {"cases": len(NAN_RULE), "relaxed_elements_wild": sum(r["relaxed_elements"] for r in wild), "elements_wild": sum(r["elements"] for r in wild),
+           "relaxed_elements_finite_scales": sum(r["relaxed_elements"] for r in NAN_RULE if not r["wild"]), "rows": NAN_RULE}
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open(os.path.join("gpurun_out", "nan_rule.json"), "w"), indent=1)
+    assert out["relaxed_elements_finite_scales"] == 0
 
 
 @pytest.mark.parametrize("ty", ALLQ)
@@ -578,3 +602,69 @@ def test_gpu_matches_rust_kat_without_the_oracle(ggq, ty):
         assert np.array_equal(ggq.quantize(ty, x, fdt), k[f"q_{ty}_{name}"]), (ty, name)
         got = ggq.dequantize(ty, k[f"b_{ty}"], fdt)
         assert np.array_equal(got.view(np.uint8), k[f"d_{ty}_{name}"].view(np.uint8)), (ty, name)
+
+
+def _student_t3(n, gen):
+    import torch
+    z = torch.randn(n, device="cuda", generator=gen)
+    chi = sum(torch.randn(n, device="cuda", generator=gen) ** 2 for _ in range(3)) / 3
+    return (z / chi.sqrt() * 0.02).clamp(-60000, 60000).to(torch.float16)
+
+
+@pytest.mark.parametrize("ty", KQ)
+def test_kquant_ffn_sized_tensor_sampled_vs_oracle(ggq, oracle, ty):
+    """Every K-quant type on a full 4096x14336 f16 tensor (the size the kernels' persistent grid is tuned for),
+    Gaussian and heavy-tailed (Student-t, nu = 3): every 101st super-block is re-quantised by the oracle."""
+    import torch
+    n = 4096 * 14336
+    st = torch.cuda.current_stream().cuda_stream
+    e, b = ggq.block_info(ty)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(40 + ty)
+    for variant in ("gaussian", "student_t3"):
+        x = (torch.randn(n, device="cuda", generator=gen) * 0.02).to(torch.float16) if variant == "gaussian" else _student_t3(n, gen)
+        packed = torch.empty(n // e * b, dtype=torch.uint8, device="cuda")
+        ggq.quantize_slice_device(ty, F16, packed, n // e, x, n, st)
+        idx = torch.arange(0, n // 256, 101, device="cuda")
+        xs = x.view(-1, 256)[idx].contiguous().cpu().numpy().view(np.uint16).reshape(-1)
+        got = packed.view(-1, b)[idx].contiguous().cpu().numpy().reshape(-1)
+        assert same_blocks(got, oracle.quantize(ty, F16, xs, threads=8), ty, b), (ty, variant)
+        del x, packed
+
+
+def test_q4_k_m_llama3_8b_mix_sampled_vs_oracle(ggq, oracle):
+    """BASELINE configs[2] inside the test suite: the whole Llama-3-8B-shaped F16 -> Q4_K_M mix (Q4_K everywhere, Q6_K
+    for output.weight and for attn_v / ffn_down on upstream's `use_more_bits` layers), Gaussian and Student-t inputs;
+    every 1009th super-block of every tensor (31 204 per input distribution) must equal the oracle's bytes: 0 differing code bytes,
+    0 differing scale bytes."""
+    import torch
+    st = torch.cuda.current_stream().cuda_stream
+    layers = 32
+
+    def more(i):
+        return i < layers // 8 or i >= 7 * layers // 8 or (i - layers // 8) % 3 == 2
+    tensors = [(4096 * 128256, 12), (4096 * 128256, 14)]
+    for l in range(layers):
+        tensors += [(4096 * 4096, 12), (4096 * 1024, 12), (4096 * 1024, 14 if more(l) else 12), (4096 * 4096, 12),
+                    (4096 * 14336, 12), (4096 * 14336, 12), (14336 * 4096, 14 if more(l) else 12)]
+    sampled = 0
+    for variant in ("gaussian", "student_t3"):
+        gen = torch.Generator(device="cuda"); gen.manual_seed(2)
+        xs_all = {12: [], 14: []}
+        got_all = {12: [], 14: []}
+        for n, ty in tensors:
+            x = (torch.randn(n, device="cuda", generator=gen) * 0.02).to(torch.float16) if variant == "gaussian" else _student_t3(n, gen)
+            e, b = ggq.block_info(ty)
+            packed = torch.empty(n // e * b, dtype=torch.uint8, device="cuda")
+            ggq.quantize_slice_device(ty, F16, packed, n // e, x, n, st)
+            idx = torch.arange(0, n // 256, 1009, device="cuda")
+            xs_all[ty].append(x.view(-1, 256)[idx].contiguous().cpu().numpy().view(np.uint16).reshape(-1))
+            got_all[ty].append(packed.view(-1, b)[idx].contiguous().cpu().numpy().reshape(-1))
+            del x, packed
+        for ty in (12, 14):
+            _, b = oracle.block_info(ty)
+            xs, got = np.concatenate(xs_all[ty]), np.concatenate(got_all[ty])
+            want = oracle.quantize(ty, F16, xs, threads=8)
+            bad = np.flatnonzero((got.reshape(-1, b) != want.reshape(-1, b)).any(axis=1))
+            assert bad.size == 0, f"{variant} type {ty}: {bad.size} of {got.size // b} sampled super-blocks differ"
+            sampled += got.size // b
+    assert sampled == 2 * 31204

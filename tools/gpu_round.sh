@@ -13,6 +13,10 @@ for phase in "$@"; do
     kq_ncu)  for t in T_Q4K T_Q6K; do timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_k_kernel -c 1 -f -o gpurun_out/kq_${t} tools/kq_sweep f16 $t first > gpurun_out/kq_ncu_${t}.log 2>&1; tail -2 gpurun_out/kq_ncu_${t}.log; done ;;
     ncu_batch) timeout 900 ncu --set full --import-source on --clock-control none -k regex:dequant_batch -c 1 -f -o gpurun_out/r02_dequant_batch python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_batch.log 2>&1; tail -2 gpurun_out/ncu_batch.log ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launches.log 2>&1; tail -2 gpurun_out/ncu_launches.log; wc -l gpurun_out/r02_bench_launches.csv ;;
+    c70_small) timeout 900 python tools/convert_llama70b.py 4 0 > gpurun_out/c70_small.log 2>&1; tail -4 gpurun_out/c70_small.log | cut -c1-1500 ;;
+    c70)     timeout 1700 python tools/convert_llama70b.py 80 0 > gpurun_out/c70.log 2>&1; tail -3 gpurun_out/c70.log | cut -c1-3000 ;;
+    bench8)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err; tail -c 600 gpurun_out/bench_n8.err; head -c 400 gpurun_out/bench_n8.json; echo ;;
+    bench4)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/bench_n4.json 2> gpurun_out/bench_n4.err; tail -c 600 gpurun_out/bench_n4.err; head -c 400 gpurun_out/bench_n4.json; echo ;;
     box)     bash tools/box_probe.sh > gpurun_out/box_probe.txt 2>&1 ;;
     bench2)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 800 gpurun_out/bench_n2.err; head -c 300 gpurun_out/bench_n2.json; echo ;;
     mixtral2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/mixtral_sweep.py > gpurun_out/mixtral_n2.txt 2>&1; tail -13 gpurun_out/mixtral_n2.txt ;;
