@@ -405,15 +405,20 @@ def ours(args, rank, world, local_rank):
                 fn()
             torch.cuda.synchronize()
             return time.perf_counter() - t0
-        t_both = timed(raw_step, e2e_steps)
+        t_both = min(timed(raw_step, e2e_steps) for _ in range(2))
         t_up = timed(lambda: raw_step(True, False), e2e_steps)
         t_down = timed(lambda: raw_step(False, True), e2e_steps)
         t_both, t_up, t_down = max_over_ranks([t_both, t_up, t_down])
-        floor = {"value": step_bytes * e2e_steps * world / t_both / 1e9, "unit": UNIT, "ms_per_step": t_both / e2e_steps * 1e3,
+        # The floor is what full duplex allows: the slower direction alone (measured), the other hidden behind it.  The
+        # measured concurrent pair is reported beside it: the copy engines do not always overlap two single large
+        # copies (one run of this bench measured 44 GB/s for the pair and 71 GB/s for the chunked pipeline on the same box).
+        t_floor = max(t_up, t_down)
+        floor = {"value": step_bytes * e2e_steps * world / t_floor / 1e9, "unit": UNIT, "ms_per_step": t_floor / e2e_steps * 1e3,
                  "h2d_alone_GBps_per_gpu": h2d_bytes * e2e_steps / t_up / 1e9, "d2h_alone_GBps_per_gpu": d2h_bytes * e2e_steps / t_down / 1e9,
-                 "concurrent_link_GBps_per_gpu": (h2d_bytes + d2h_bytes) * e2e_steps / t_both / 1e9,
-                 "what": "every rank copies exactly h2d_bytes_per_step up and d2h_bytes_per_step down (pinned, one cudaMemcpyAsync each, two streams, "
-                         "concurrently) per step, no kernels; value = the step's algorithmic bytes / that time, max over ranks"}
+                 "concurrent_pair_measured": step_bytes * e2e_steps * world / t_both / 1e9,
+                 "what": "every rank copies exactly h2d_bytes_per_step up and d2h_bytes_per_step down per step (pinned, one cudaMemcpyAsync each, no "
+                         "kernels), each direction alone; value = the step's algorithmic bytes / the slower direction's time (full duplex hides the "
+                         "other), max over ranks; concurrent_pair_measured = both copies issued together on two streams"}
         del h_in, h_out, d_in, d_out
 
         # (b) pinned host buffers through ggq_slices

@@ -513,7 +513,11 @@ template <uint32_t T, bool WITH_SUM> struct Encoder8 {
                 int s = 0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) s = __dp4a((int)w[k], 0x01010101, s);
-                s16 = f2h(__fmul_rn((float)s, d));
+                // sum as f32 * delta: the only NaN this can produce is 0 * inf (amax = inf makes delta inf, recip 0 and every
+                // code 0).  The reference computes it on x86, whose invalid-operation result is the negative quiet NaN
+                // 0xFFC00000 -> f16 0xFE00 through half's payload-keeping narrow; the GPU's would be 0x7FFF.
+                const float sf = __fmul_rn((float)s, d);
+                s16 = (sf != sf) ? 0xFE00u : f2h(sf);
             }
         }
         if constexpr (WITH_SUM) {
