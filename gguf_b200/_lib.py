@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libggq.so")
+SO_PATH = os.environ.get("GGQ_SO") or os.path.join(_HERE, "libggq.so")  # GGQ_SO: A/B builds of the same sources (tools/)
 
 # every symbol include/ggq.h declares: (name, restype, argtypes)
 _c = ctypes

@@ -142,14 +142,18 @@ __device__ __forceinline__ void dequant_one_tile(const uint8_t *__restrict__ src
         __syncthreads();
     }
     typename FT::raw *out = dst + t * (size_t)TILE_ELEMS;
+    bool bad = false;  // see dequant_kernel
     if (nb == TILE_BLOCKS) {
 #pragma unroll 2
         for (int u = tid; u < TILE_BLOCKS * UNITS; u += THREADS)
-            Decoder<T>::template run<FT, 0>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
+            bad |= Decoder<T>::template run<FT, 0>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
     } else {
         for (int u = tid; u < nb * UNITS; u += THREADS)
-            Decoder<T>::template run<FT, 0>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
+            bad |= Decoder<T>::template run<FT, 0>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
     }
+#ifndef GGQ_AB_NO_EXACT_PASS
+    if (bad) fix_units_exact<T, FT, THREADS>(stage, out, nb * UNITS, tid);
+#endif
 }
 
 template <class FT, int TILE_ELEMS, int THREADS, int MINB>

@@ -100,6 +100,114 @@ template <class FT, int SP, int BIAS> __device__ __forceinline__ void emit_sym(t
     else emit_scaled<FT, SP>(out, codes, (float)BIAS, h2f((uint16_t)dbits), vec);
 }
 
+// ---- blocks whose f16 scale fields are NaN or infinite -------------------------------------------------------------
+// With finite fields no decoder can produce a NaN (every product and sum stays far inside f32's range), and the fast
+// paths below are bit-exact.  A NaN / infinite field is garbage input, but the reference still defines the result: its
+// arithmetic runs on x86 SSE, where an operation with a NaN operand returns that operand quieted (payload kept; the
+// first operand when both are NaN) and an invalid operation (inf * 0, inf - inf) returns the negative quiet NaN
+// 0xFFC00000; `half`'s narrowing then keeps sign and top payload bits.  The GPU would return 0x7FFFFFFF for all of
+// these.  So a unit whose block has such a field leaves the fast path (one test of bits already in a register) and
+// evaluates the reference's expression element by element, operation by operation, with these rules.
+__device__ __forceinline__ bool f16_nonfinite(uint32_t h) { return (h & 0x7C00u) == 0x7C00u; }
+__device__ __forceinline__ float x86_result(float r, float a, float b) {
+    if (r == r) return r;
+    if (a != a) return __uint_as_float(__float_as_uint(a) | 0x00400000u);
+    if (b != b) return __uint_as_float(__float_as_uint(b) | 0x00400000u);
+    return __uint_as_float(0xFFC00000u);
+}
+__device__ __forceinline__ float xmul(float a, float b) { return x86_result(__fmul_rn(a, b), a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return x86_result(__fadd_rn(a, b), a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return x86_result(__fsub_rn(a, b), a, b); }
+__device__ __forceinline__ float fld16(const uint8_t *p) { return h2f_exact((uint16_t)lds16(p)); }
+__device__ __forceinline__ uint32_t fld32u(const uint8_t *p) { return lds16(p) | (lds16(p + 2) << 16); }
+// 6-bit (scale, min) pair j of Q4K / Q5K from the 12 bytes at s (upstream get_scale_min_k4)
+__device__ __forceinline__ void scale_min_bytes(int j, const uint8_t *s, uint32_t &sc, uint32_t &m) {
+    if (j < 4) {
+        sc = s[j] & 63u;
+        m = s[j + 4] & 63u;
+    } else {
+        sc = (s[j + 4] & 0xFu) | ((uint32_t)(s[j - 4] >> 6) << 4);
+        m = (s[j + 4] >> 4) | ((uint32_t)(s[j] >> 6) << 4);
+    }
+}
+
+// element i of block b, the reference's expression (structs/*.rs; upstream dequantize_row_qN_K for the K-quants)
+template <uint32_t T> __device__ __forceinline__ float ref_elem(const uint8_t *b, int i);
+template <> __device__ __forceinline__ float ref_elem<T_Q4_0>(const uint8_t *b, int i) {
+    const uint32_t q = b[2 + (i & 15)];
+    return xmul((float)((int)(i < 16 ? (q & 0xFu) : (q >> 4)) - 8), fld16(b));
+}
+template <> __device__ __forceinline__ float ref_elem<T_Q4_1>(const uint8_t *b, int i) {
+    const uint32_t q = b[4 + (i & 15)];
+    return xadd(xmul((float)(i < 16 ? (q & 0xFu) : (q >> 4)), fld16(b)), fld16(b + 2));
+}
+__device__ __forceinline__ int code5(const uint8_t *ql, uint32_t qh, int i) {
+    const uint32_t q = ql[i & 15];
+    return (int)((i < 16 ? (q & 0xFu) : (q >> 4)) | (((qh >> i) & 1u) << 4));
+}
+template <> __device__ __forceinline__ float ref_elem<T_Q5_0>(const uint8_t *b, int i) {
+    return xmul((float)(code5(b + 6, fld32u(b + 2), i) - 16), fld16(b));
+}
+template <> __device__ __forceinline__ float ref_elem<T_Q5_1>(const uint8_t *b, int i) {
+    return xadd(xmul((float)code5(b + 8, fld32u(b + 4), i), fld16(b)), fld16(b + 2));
+}
+template <> __device__ __forceinline__ float ref_elem<T_Q8_0>(const uint8_t *b, int i) { return xmul((float)(int8_t)b[2 + i], fld16(b)); }
+template <> __device__ __forceinline__ float ref_elem<T_Q8_1>(const uint8_t *b, int i) { return xmul((float)(int8_t)b[4 + i], fld16(b)); }
+template <> __device__ __forceinline__ float ref_elem<T_Q8K>(const uint8_t *b, int i) { return xmul((float)(int8_t)b[2 + i], fld16(b)); }
+template <> __device__ __forceinline__ float ref_elem<T_Q2K>(const uint8_t *b, int i) {
+    const int n = i >> 7, j = (i & 127) >> 5, l = i & 31;
+    const uint32_t s = b[8 * n + 2 * j + (l >> 4)];
+    const float dl = xmul(fld16(b + 80), (float)(s & 0xFu)), ml = xmul(fld16(b + 82), (float)(s >> 4));
+    return xsub(xmul(dl, (float)((b[16 + 32 * n + l] >> (2 * j)) & 3u)), ml);
+}
+template <> __device__ __forceinline__ float ref_elem<T_Q3K>(const uint8_t *b, int i) {
+    const int n = i >> 7, j = (i & 127) >> 5, l = i & 31, is = 8 * n + 2 * j + (l >> 4);
+    const uint8_t *sc = b + 96;
+    const uint32_t lo4 = is < 8 ? (sc[is] & 15u) : (uint32_t)(sc[is - 8] >> 4);
+    const uint32_t hi2 = (sc[8 + (is & 3)] >> (2 * (is >> 2))) & 3u;
+    const float dl = xmul(fld16(b + 108), (float)((int)(lo4 | (hi2 << 4)) - 32));
+    const int q = (int)((b[32 + 32 * n + l] >> (2 * j)) & 3u) - ((b[l] & (1u << (4 * n + j))) ? 0 : 4);
+    return xmul(dl, (float)q);
+}
+template <> __device__ __forceinline__ float ref_elem<T_Q4K>(const uint8_t *b, int i) {
+    const int g = i >> 6, hi = (i >> 5) & 1, l = i & 31;
+    uint32_t sc, m;
+    scale_min_bytes(2 * g + hi, b + 4, sc, m);
+    const float d1 = xmul(fld16(b), (float)sc), m1 = xmul(fld16(b + 2), (float)m);
+    const uint32_t q = b[16 + 32 * g + l];
+    return xsub(xmul(d1, (float)(hi ? (q >> 4) : (q & 0xFu))), m1);
+}
+template <> __device__ __forceinline__ float ref_elem<T_Q5K>(const uint8_t *b, int i) {
+    const int g = i >> 6, hi = (i >> 5) & 1, l = i & 31;
+    uint32_t sc, m;
+    scale_min_bytes(2 * g + hi, b + 4, sc, m);
+    const float d1 = xmul(fld16(b), (float)sc), m1 = xmul(fld16(b + 2), (float)m);
+    const uint32_t q = b[48 + 32 * g + l];
+    const uint32_t c = (hi ? (q >> 4) : (q & 0xFu)) + ((b[16 + l] & (1u << (2 * g + hi))) ? 16u : 0u);
+    return xsub(xmul(d1, (float)c), m1);
+}
+template <> __device__ __forceinline__ float ref_elem<T_Q6K>(const uint8_t *b, int i) {
+    const int n = i >> 7, grp = (i & 127) >> 5, l = i & 31;
+    const uint32_t ql = b[64 * n + l + ((grp & 1) ? 32 : 0)], qh = b[128 + 32 * n + l];
+    const int q = (int)(((grp & 2) ? (ql >> 4) : (ql & 0xFu)) | (((qh >> (2 * grp)) & 3u) << 4)) - 32;
+    const float sc = (float)(int8_t)b[192 + 8 * n + (l >> 4) + 2 * grp];
+    return xmul(xmul(fld16(b + 208), sc), (float)q);
+}
+template <class FT> __device__ __forceinline__ void store_exact(typename FT::raw *p, float y);
+template <> __device__ __forceinline__ void store_exact<F32>(float *p, float y) { *p = y; }
+template <> __device__ __forceinline__ void store_exact<F16>(uint16_t *p, float y) { *p = f2h_exact(y); }
+template <> __device__ __forceinline__ void store_exact<BF16>(uint16_t *p, float y) { *p = f2bf_exact(y); }
+// `nruns` runs of V consecutive elements, `stride` elements apart, starting at element s0 of the block: what one unit
+// of a fast decoder writes.  Out of line: it must not cost the fast path registers.
+template <uint32_t T, class FT>
+__device__ __forceinline__ void decode_exact_runs(const uint8_t *b, typename FT::raw *out, int s0, int stride, int nruns) {
+    for (int r = 0; r < nruns; r++)
+        for (int k = 0; k < FT::V; k++) {
+            const int i = s0 + r * stride + k;
+            store_exact<FT>(out + i, ref_elem<T>(b, i));
+        }
+}
+
 // Decoder<T>::units<V>() units per block; unit `u` of block `b` writes its outputs under `out`
 // (pointer to the block's first output element).
 template <uint32_t T> struct Decoder;
@@ -107,7 +215,7 @@ template <uint32_t T> struct Decoder;
 // ---- Q4_0: q4_0.rs:46-57   y[i] = ((b&15) - 8) * d ; y[i+16] = ((b>>4) - 8) * d ----------------
 template <> struct Decoder<T_Q4_0> {
     template <int V> static __host__ __device__ constexpr int units() { return 16 / V; }
-    template <class FT, int SP> static __device__ __forceinline__ void run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
+    template <class FT, int SP> static __device__ __forceinline__ bool run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
         constexpr int V = FT::V, NW = V / 4;
         const uint32_t dbits = lds16(b);
         uint32_t w[NW], lo[NW], hi[NW];
@@ -116,13 +224,14 @@ template <> struct Decoder<T_Q4_0> {
         for (int i = 0; i < NW; i++) { lo[i] = w[i] & 0x0F0F0F0Fu; hi[i] = (w[i] >> 4) & 0x0F0F0F0Fu; }
         emit_sym<FT, SP, 8>(out + u * V, lo, dbits, vec);
         emit_sym<FT, SP, 8>(out + 16 + u * V, hi, dbits, vec);
+        return f16_nonfinite(dbits);
     }
 };
 
 // ---- Q4_1: q4_1.rs:49-60   y = q * d + m -------------------------------------------------------
 template <> struct Decoder<T_Q4_1> {
     template <int V> static __host__ __device__ constexpr int units() { return 16 / V; }
-    template <class FT, int SP> static __device__ __forceinline__ void run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
+    template <class FT, int SP> static __device__ __forceinline__ bool run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
         constexpr int V = FT::V, NW = V / 4;
         const uint32_t dm = lds32<4>(b);
         const float d = h2f((uint16_t)(dm & 0xFFFF)), m = h2f((uint16_t)(dm >> 16));
@@ -132,13 +241,14 @@ template <> struct Decoder<T_Q4_1> {
         for (int i = 0; i < NW; i++) { lo[i] = w[i] & 0x0F0F0F0Fu; hi[i] = (w[i] >> 4) & 0x0F0F0F0Fu; }
         emit_affine<FT, SP>(out + u * V, lo, d, m, vec);
         emit_affine<FT, SP>(out + 16 + u * V, hi, d, m, vec);
+        return f16_nonfinite(dm) || f16_nonfinite(dm >> 16);
     }
 };
 
 // ---- Q5_0: q5_0.rs:60-73   5th bit of element i is bit i of qh ---------------------------------
 template <> struct Decoder<T_Q5_0> {
     template <int V> static __host__ __device__ constexpr int units() { return 16 / V; }
-    template <class FT, int SP> static __device__ __forceinline__ void run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
+    template <class FT, int SP> static __device__ __forceinline__ bool run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
         constexpr int V = FT::V, NW = V / 4;
         const uint32_t dbits = lds16(b);
         const uint32_t qh = lds32<2>(b + 2);
@@ -151,13 +261,14 @@ template <> struct Decoder<T_Q5_0> {
         }
         emit_sym<FT, SP, 16>(out + u * V, lo, dbits, vec);
         emit_sym<FT, SP, 16>(out + 16 + u * V, hi, dbits, vec);
+        return f16_nonfinite(dbits);
     }
 };
 
 // ---- Q5_1: q5_1.rs:64-77 -----------------------------------------------------------------------
 template <> struct Decoder<T_Q5_1> {
     template <int V> static __host__ __device__ constexpr int units() { return 16 / V; }
-    template <class FT, int SP> static __device__ __forceinline__ void run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
+    template <class FT, int SP> static __device__ __forceinline__ bool run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
         constexpr int V = FT::V, NW = V / 4;
         const uint32_t dm = lds32<4>(b);
         const float d = h2f((uint16_t)(dm & 0xFFFF)), m = h2f((uint16_t)(dm >> 16));
@@ -171,13 +282,14 @@ template <> struct Decoder<T_Q5_1> {
         }
         emit_affine<FT, SP>(out + u * V, lo, d, m, vec);
         emit_affine<FT, SP>(out + 16 + u * V, hi, d, m, vec);
+        return f16_nonfinite(dm) || f16_nonfinite(dm >> 16);
     }
 };
 
 // ---- Q8_0 / Q8_1 / Q8K: q8_0.rs:43-47, q8_1.rs:57-61, q8_k.rs:56-60   y = q * d ----------------
 template <uint32_t T, int QOFF> struct Decoder8 {
     template <int V> static __host__ __device__ constexpr int units() { return BlockTraits<T>::ELEMS / V; }
-    template <class FT, int SP> static __device__ __forceinline__ void run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
+    template <class FT, int SP> static __device__ __forceinline__ bool run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
         constexpr int V = FT::V, NW = V / 4;
         const uint32_t dbits = lds16(b);
         uint32_t w[NW];
@@ -185,6 +297,7 @@ template <uint32_t T, int QOFF> struct Decoder8 {
 #pragma unroll
         for (int i = 0; i < NW; i++) w[i] ^= 0x80808080u;  // int8 -> biased unsigned (q + 128)
         emit_sym<FT, SP, 128>(out + u * V, w, dbits, vec);
+        return f16_nonfinite(dbits);
     }
 };
 template <> struct Decoder<T_Q8_0> : Decoder8<T_Q8_0, 2> {};
@@ -210,7 +323,7 @@ __device__ __forceinline__ void scale_min_k4(int j, uint32_t s0, uint32_t s1, ui
 
 template <> struct Decoder<T_Q4K> {
     template <int V> static __host__ __device__ constexpr int units() { return 128 / V; }
-    template <class FT, int SP> static __device__ __forceinline__ void run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
+    template <class FT, int SP> static __device__ __forceinline__ bool run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
         constexpr int V = FT::V, NW = V / 4, CP = 32 / V;
         const int p = u / CP, c = u % CP;
         const uint4 hdr = *reinterpret_cast<const uint4 *>(b);  // delta, min, scales[12]
@@ -226,12 +339,13 @@ template <> struct Decoder<T_Q4K> {
         for (int i = 0; i < NW; i++) { lo[i] = w[i] & 0x0F0F0F0Fu; hi[i] = (w[i] >> 4) & 0x0F0F0F0Fu; }
         emit_affine<FT, SP>(out + 64 * p + c * V, lo, d1, -mm1, vec);
         emit_affine<FT, SP>(out + 64 * p + 32 + c * V, hi, d2, -mm2, vec);
+        return f16_nonfinite(hdr.x) || f16_nonfinite(hdr.x >> 16);
     }
 };
 
 template <> struct Decoder<T_Q5K> {
     template <int V> static __host__ __device__ constexpr int units() { return 128 / V; }
-    template <class FT, int SP> static __device__ __forceinline__ void run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
+    template <class FT, int SP> static __device__ __forceinline__ bool run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
         constexpr int V = FT::V, NW = V / 4, CP = 32 / V;
         const int p = u / CP, c = u % CP;
         const uint4 hdr = *reinterpret_cast<const uint4 *>(b);
@@ -251,15 +365,17 @@ template <> struct Decoder<T_Q5K> {
         }
         emit_affine<FT, SP>(out + 64 * p + c * V, lo, d1, -mm1, vec);
         emit_affine<FT, SP>(out + 64 * p + 32 + c * V, hi, d2, -mm2, vec);
+        return f16_nonfinite(hdr.x) || f16_nonfinite(hdr.x >> 16);
     }
 };
 
 template <> struct Decoder<T_Q6K> {
     template <int V> static __host__ __device__ constexpr int units() { return 64 / V; }
-    template <class FT, int SP> static __device__ __forceinline__ void run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
+    template <class FT, int SP> static __device__ __forceinline__ bool run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
         constexpr int V = FT::V, NW = V / 4, CP = 32 / V;
         const int n = u / CP, l0 = (u % CP) * V;
-        const float d = h2f((uint16_t)lds16(b + 208));
+        const uint32_t dbits = lds16(b + 208);
+        const float d = h2f((uint16_t)dbits);
         uint32_t qa[NW], qb[NW], qh[NW], c1[NW], c2[NW], c3[NW], c4[NW];
         lds_words<NW, 2>(b + 64 * n + l0, qa);
         lds_words<NW, 2>(b + 64 * n + 32 + l0, qb);
@@ -279,12 +395,13 @@ template <> struct Decoder<T_Q6K> {
         emit_scaled<FT, SP>(o + 32, c2, 32.0f, s2, vec);
         emit_scaled<FT, SP>(o + 64, c3, 32.0f, s3, vec);
         emit_scaled<FT, SP>(o + 96, c4, 32.0f, s4, vec);
+        return f16_nonfinite(dbits);
     }
 };
 
 template <> struct Decoder<T_Q2K> {
     template <int V> static __host__ __device__ constexpr int units() { return 64 / V; }
-    template <class FT, int SP> static __device__ __forceinline__ void run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
+    template <class FT, int SP> static __device__ __forceinline__ bool run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
         constexpr int V = FT::V, NW = V / 4, CP = 32 / V;
         const int n = u / CP, l0 = (u % CP) * V;
         const uint32_t dm = lds32<4>(b + 80);
@@ -302,15 +419,17 @@ template <> struct Decoder<T_Q2K> {
             for (int i = 0; i < NW; i++) c[i] = (w[i] >> (2 * k)) & 0x03030303u;
             emit_affine<FT, SP>(o + 32 * k, c, dl, -ml, vec);
         }
+        return f16_nonfinite(dm) || f16_nonfinite(dm >> 16);
     }
 };
 
 template <> struct Decoder<T_Q3K> {
     template <int V> static __host__ __device__ constexpr int units() { return 64 / V; }
-    template <class FT, int SP> static __device__ __forceinline__ void run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
+    template <class FT, int SP> static __device__ __forceinline__ bool run(const uint8_t *b, int u, typename FT::raw *out, bool vec) {
         constexpr int V = FT::V, NW = V / 4, CP = 32 / V;
         const int n = u / CP, l0 = (u % CP) * V;
-        const float d = h2f((uint16_t)lds16(b + 108));
+        const uint32_t dbits = lds16(b + 108);
+        const float d = h2f((uint16_t)dbits);
         uint32_t w[NW], hm[NW];
         lds_words<NW, 2>(b + 32 + 32 * n + l0, w);
         lds_words<NW, 2>(b + l0, hm);
@@ -329,8 +448,50 @@ template <> struct Decoder<T_Q3K> {
             for (int i = 0; i < NW; i++) c[i] = ((w[i] >> (2 * k)) & 0x03030303u) | (((hm[i] >> bit) & 0x01010101u) << 2);
             emit_scaled<FT, SP>(o + 32 * k, c, 4.0f, dl, vec);
         }
+        return f16_nonfinite(dbits);
     }
 };
+
+// What unit u of Decoder<T> writes: `nruns` runs of V elements, `stride` apart, from element s0 of its block; and which
+// f16 fields of the block decide whether the unit must be re-evaluated exactly.
+template <uint32_t T> struct UnitGeom;
+#define GGQ_GEOM(T, S0, STRIDE, NRUNS, BAD)                                                                          \
+    template <> struct UnitGeom<T> {                                                                                 \
+        static __device__ __forceinline__ void runs(int u, int V, int &s0, int &stride, int &nruns) {               \
+            const int CP = 32 / V; (void)CP;                                                                         \
+            s0 = S0; stride = STRIDE; nruns = NRUNS;                                                                 \
+        }                                                                                                            \
+        static __device__ __forceinline__ bool nonfinite(const uint8_t *b) { return BAD; }                           \
+    }
+GGQ_GEOM(T_Q4_0, u * V, 16, 2, f16_nonfinite(lds16(b)));
+GGQ_GEOM(T_Q4_1, u * V, 16, 2, f16_nonfinite(lds16(b)) || f16_nonfinite(lds16(b + 2)));
+GGQ_GEOM(T_Q5_0, u * V, 16, 2, f16_nonfinite(lds16(b)));
+GGQ_GEOM(T_Q5_1, u * V, 16, 2, f16_nonfinite(lds16(b)) || f16_nonfinite(lds16(b + 2)));
+GGQ_GEOM(T_Q8_0, u * V, 0, 1, f16_nonfinite(lds16(b)));
+GGQ_GEOM(T_Q8_1, u * V, 0, 1, f16_nonfinite(lds16(b)));
+GGQ_GEOM(T_Q8K, u * V, 0, 1, f16_nonfinite(lds16(b)));
+GGQ_GEOM(T_Q4K, 64 * (u / CP) + (u % CP) * V, 32, 2, f16_nonfinite(lds16(b)) || f16_nonfinite(lds16(b + 2)));
+GGQ_GEOM(T_Q5K, 64 * (u / CP) + (u % CP) * V, 32, 2, f16_nonfinite(lds16(b)) || f16_nonfinite(lds16(b + 2)));
+GGQ_GEOM(T_Q6K, 128 * (u / CP) + (u % CP) * V, 32, 4, f16_nonfinite(lds16(b + 208)));
+GGQ_GEOM(T_Q2K, 128 * (u / CP) + (u % CP) * V, 32, 4, f16_nonfinite(lds16(b + 80)) || f16_nonfinite(lds16(b + 82)));
+GGQ_GEOM(T_Q3K, 128 * (u / CP) + (u % CP) * V, 32, 4, f16_nonfinite(lds16(b + 108)));
+#undef GGQ_GEOM
+
+// Second pass over this thread's units of a tile, taken only when the fast pass met a block with a NaN / infinite scale
+// field: those units are evaluated again, exactly (see above), over what the fast path wrote.  A thread rewrites only
+// its own outputs, so no synchronisation is needed; out of line so the fast loop pays one OR per unit and nothing else.
+template <uint32_t T, class FT, int THREADS>
+__device__ __noinline__ void fix_units_exact(const uint8_t *stage, typename FT::raw *out, int nunits, int tid) {
+    using TR = BlockTraits<T>;
+    constexpr int UNITS = Decoder<T>::template units<FT::V>();
+    for (int u = tid; u < nunits; u += THREADS) {
+        const uint8_t *b = stage + (u / UNITS) * TR::BYTES;
+        if (!UnitGeom<T>::nonfinite(b)) continue;
+        int s0, stride, nruns;
+        UnitGeom<T>::runs(u % UNITS, FT::V, s0, stride, nruns);
+        decode_exact_runs<T, FT>(b, out + (size_t)(u / UNITS) * TR::ELEMS, s0, stride, nruns);
+    }
+}
 
 // MODE 0: persistent CTAs, static round-robin over tiles, STAGES-deep bulk-copy (TMA) ring.
 // MODE 1: one tile per CTA (grid = ntiles), the tile arrives by one bulk copy: the hardware block scheduler
@@ -400,14 +561,18 @@ dequant_kernel(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ d
             __syncthreads();
         }
         typename FT::raw *out = dst + t * (size_t)TILE_ELEMS;
+        bool bad = false;  // some unit of this thread met a NaN / infinite scale field
         if (nb == TILE_BLOCKS) {
 #pragma unroll 2
             for (int u = tid; u < TILE_BLOCKS * UNITS; u += THREADS)
-                Decoder<T>::template run<FT, SP>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
+                bad |= Decoder<T>::template run<FT, SP>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
         } else {
             for (int u = tid; u < nb * UNITS; u += THREADS)
-                Decoder<T>::template run<FT, SP>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
+                bad |= Decoder<T>::template run<FT, SP>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
         }
+#ifndef GGQ_AB_NO_EXACT_PASS  /* A/B builds only (tools/gpu_round.sh ab_exact) */
+        if (bad) fix_units_exact<T, FT, THREADS>(stage, out, nb * UNITS, tid);
+#endif
         if constexpr (MODE == 0) {
             __syncthreads();  // stage s fully consumed
             if (tid == 0) issue(i + NST);

@@ -116,8 +116,10 @@ def same_blocks(a, b, ty, bytes_per_block):
 def nan_rule_usage(got, want, ty, blocks, bytes_per_block):
     """How much of a dequantize comparison leans on the NaN ~ NaN rule of same_floats().
     Returns (n_relaxed, n_total, ok): `n_relaxed` elements are NaN on both sides with different payloads; `ok` is False
-    if any of them sits in a block whose f16 header fields are all finite — there the comparison must be bit-exact,
-    the rule is only for arithmetic on a NaN / infinite scale (inf * 0, NaN * q), whose payload is the platform's."""
+    if any of them sits in a block with FEWER THAN TWO non-finite f16 header fields.  With one NaN / infinite field the
+    reference's result is fully determined (x86: the NaN operand quieted, or 0xFFC00000 for inf * 0) and the kernels
+    reproduce it bit for bit; only when two such fields meet in one expression (delta and min both NaN, ...) does the
+    payload depend on the operand order the reference's compiler happened to pick."""
     got = np.asarray(got); want = np.asarray(want)
     if got.dtype == np.float32:
         ua, ub = got.view(np.uint32), want.view(np.uint32)
@@ -127,9 +129,9 @@ def nan_rule_usage(got, want, ty, blocks, bytes_per_block):
         na, nb = (ua & 0x7FFF) > 0x7C00, (ub & 0x7FFF) > 0x7C00
     relaxed = (ua != ub) & na & nb
     blk = np.asarray(blocks, np.uint8).reshape(-1, bytes_per_block)
-    finite = np.ones(len(blk), bool)
+    nonfinite = np.zeros(len(blk), np.int32)
     for o in FIELDS_F16[ty]:
         h = blk[:, o].astype(np.uint16) | (blk[:, o + 1].astype(np.uint16) << 8)
-        finite &= (h & 0x7C00) != 0x7C00
+        nonfinite += (h & 0x7C00) == 0x7C00
     per_block = relaxed.reshape(len(blk), -1).any(axis=1)
-    return int(relaxed.sum()), int(relaxed.size), not bool((per_block & finite).any())
+    return int(relaxed.sum()), int(relaxed.size), not bool((per_block & (nonfinite < 2)).any())

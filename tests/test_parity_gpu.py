@@ -49,10 +49,11 @@ def test_dequantize_bit_exact(ggq, oracle, ty, fdt, wild):
     got = ggq.dequantize(ty, blocks, fdt)
     want = oracle.dequantize(ty, fdt, blocks, threads=8)
     assert same_floats(got, want)
-    # the NaN ~ NaN rule may only ever act inside blocks whose scale fields are NaN / inf (random bytes: ~3 % of the
-    # f16 patterns); blocks with finite fields are compared bit for bit.  The share is recorded for DESIGN.md §5.
+    # NaN / infinite scale fields (random bytes: ~3 % of the f16 patterns) are reproduced bit for bit too — the decoders
+    # evaluate such blocks with the reference platform's NaN rules — except where TWO non-finite fields meet in one
+    # expression (the payload then depends on the reference compiler's operand order).  The share is recorded for DESIGN.md §5.
     relaxed, total, ok = nan_rule_usage(got, want, ty, blocks, b)
-    assert ok, "NaN ~ NaN was needed in a block with finite scale fields"
+    assert ok, "NaN ~ NaN was needed in a block with fewer than two non-finite scale fields"
     if not wild:
         assert relaxed == 0
     NAN_RULE.append({"type": ty, "fdt": fdt, "wild": wild, "relaxed_elements": relaxed, "elements": total})
@@ -63,7 +64,7 @@ NAN_RULE = []
 
 def test_zz_nan_rule_report():
     """Writes gpurun_out/nan_rule.json: how many dequantize outputs of the wild (random-byte) cases were accepted as
-    NaN ~ NaN instead of bit-equal (all of them inside blocks with a NaN / infinite scale field)."""
+    NaN ~ NaN instead of bit-equal (all of them inside blocks with two NaN / infinite scale fields)."""
     import json, os
     if not NAN_RULE:
         pytest.skip("runs after test_dequantize_bit_exact")

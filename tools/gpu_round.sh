@@ -9,6 +9,7 @@ for phase in "$@"; do
     ref)     timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2>&1 ;;
     pcie)    timeout 300 python tools/pcie_probe.py > gpurun_out/pcie_probe.txt 2>&1 ;;
     sweep)   timeout 900 python tools/codec_sweep.py > gpurun_out/codec_sweep.txt 2>&1; tail -5 gpurun_out/codec_sweep.txt ;;
+    sweep_dq) timeout 900 python tools/codec_sweep.py 58720256 dequant > gpurun_out/codec_sweep_dq.txt 2>&1; timeout 900 python tools/codec_sweep.py 16777216 dequant > gpurun_out/codec_sweep_dq_16m.txt 2>&1; timeout 900 python tools/codec_sweep.py 4194304 dequant > gpurun_out/codec_sweep_dq_4m.txt 2>&1; tail -3 gpurun_out/codec_sweep_dq_4m.txt ;;
     kq)      timeout 600 tools/kq_sweep f16 > gpurun_out/kq_sweep_f16.txt 2>&1; timeout 300 tools/kq_sweep f32 > gpurun_out/kq_sweep_f32.txt 2>&1; cat gpurun_out/kq_sweep_f16.txt gpurun_out/kq_sweep_f32.txt ;;
     kq_ncu)  for t in T_Q4K T_Q6K; do timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_k_kernel -c 1 -f -o gpurun_out/kq_${t} tools/kq_sweep f16 $t first > gpurun_out/kq_ncu_${t}.log 2>&1; tail -2 gpurun_out/kq_ncu_${t}.log; done ;;
     ncu_batch) timeout 900 ncu --set full --import-source on --clock-control none -k regex:dequant_batch -c 1 -f -o gpurun_out/r02_dequant_batch python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_batch.log 2>&1; tail -2 gpurun_out/ncu_batch.log ;;
@@ -17,9 +18,12 @@ for phase in "$@"; do
     c70)     timeout 1700 python tools/convert_llama70b.py 80 0 > gpurun_out/c70.log 2>&1; tail -3 gpurun_out/c70.log | cut -c1-3000 ;;
     bench8)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err; tail -c 600 gpurun_out/bench_n8.err; head -c 400 gpurun_out/bench_n8.json; echo ;;
     bench4)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/bench_n4.json 2> gpurun_out/bench_n4.err; tail -c 600 gpurun_out/bench_n4.err; head -c 400 gpurun_out/bench_n4.json; echo ;;
+    ncu_q40) timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_rows_oneshot -c 1 -f -o gpurun_out/r02_quant_q40_f16 python tools/codec_sweep.py 58720256 Q4_0:quant > gpurun_out/ncu_q40.log 2>&1; tail -2 gpurun_out/ncu_q40.log ;;
     box)     bash tools/box_probe.sh > gpurun_out/box_probe.txt 2>&1 ;;
     bench2)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 800 gpurun_out/bench_n2.err; head -c 300 gpurun_out/bench_n2.json; echo ;;
     mixtral2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/mixtral_sweep.py > gpurun_out/mixtral_n2.txt 2>&1; tail -13 gpurun_out/mixtral_n2.txt ;;
+    tests_dq) timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "dequantize or slices or kat or nan_rule or alignment or big" 2>&1 | tail -4 ;;
+    ab_exact) for i in 1 2; do GGQ_SO=$PWD/gguf_b200/libggq_ab_noexact.so timeout 600 python tools/codec_sweep.py 58720256 dequant > gpurun_out/ab_noexact_$i.txt 2>&1; timeout 600 python tools/codec_sweep.py 58720256 dequant > gpurun_out/ab_exact_$i.txt 2>&1; done; tail -2 gpurun_out/ab_exact_2.txt ;;
     tests2)  timeout 1500 python -m pytest tests -m gpu -x -q -k "shard or slices or convert" 2>&1 | tail -5 ;;
     *) echo "unknown phase $phase" ;;
   esac
