@@ -520,6 +520,37 @@ def ours(args, rank, world, local_rank):
         for _, pi, po in host:
             pi.free(); po.free()
 
+    # ---- informational (rank 0, N=1): the QUANTIZE direction end to end, where the arithmetic, not the host link, is the
+    # reference's cost: f16 -> Q4_K / Q8_0 of one 4096x14336 tensor through ggq_quantize_slice (pinned host buffers, H2D +
+    # kernel + D2H timed) against the CPU port on a bounded sample with all host threads ----
+    e2e_quant = None
+    if rank == 0 and world == 1 and not args.no_e2e and not args.no_cpu:
+        from oracle import oracle as O
+        n = SHAPES["ffn"][0] * SHAPES["ffn"][1]
+        threads = os.cpu_count() or 1
+        px = g.PinnedBuffer(n * 2)
+        px.view(np.uint16)[:] = (np.random.default_rng(5).standard_normal(n, dtype=np.float32) * np.float32(0.02)).astype(np.float16).view(np.uint16)
+        e2e_quant = {"unit": UNIT, "tensor": "4096x14336 f16", "cpu_threads": threads, "rows": []}
+        for ty, name, sample in ((Q4K, "Q4_K", 1 << 22), (Q8_0, "Q8_0", n)):
+            e, b = BLOCK[ty]
+            pq = g.PinnedBuffer(n // e * b)
+            nbytes = n * 2 + n // e * b
+            for _ in range(2):
+                assert L.ggq_quantize_slice(ty, F16, pq.ptr, n // e, px.ptr, n) == 0, L.ggq_last_error()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                L.ggq_quantize_slice(ty, F16, pq.ptr, n // e, px.ptr, n)
+            gpu_gbs = nbytes * 3 / (time.perf_counter() - t0) / 1e9
+            xs = np.array(px.view(np.uint16)[:sample], copy=True)
+            O.quantize(ty, O.F16, xs[:1 << 20], threads=threads)
+            t0 = time.perf_counter()
+            want = O.quantize(ty, O.F16, xs, threads=threads)
+            cpu_gbs = (sample * 2 + sample // e * b) / (time.perf_counter() - t0) / 1e9
+            assert np.array_equal(pq.array[:want.size], want), "e2e quantize differs from the oracle"
+            e2e_quant["rows"].append({"type": name, "gpu_e2e": gpu_gbs, "cpu_port": cpu_gbs, "cpu_sample_elems": sample, "ratio": gpu_gbs / cpu_gbs})
+            pq.free()
+        px.free()
+
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the whole workload ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -540,7 +571,7 @@ def ours(args, rank, world, local_rank):
                       "sharding": "by tensor, one replica of the workload per GPU, no collective", "cpu_binding_rank0": numa},
             "clocks": clocks, "e2e": e2e, "e2e_strong": e2e_strong, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "frac_of_peak_whole_step": value / world / peak, "per_kernel": per_kernel, "quant_per_kernel": quant_per_kernel,
-            "quant_roofline": quant_roofline,
+            "quant_roofline": quant_roofline, "e2e_quantize": e2e_quant,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -686,8 +686,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait_upto(int pending)
         else cp_async_wait_upto<N - 1>(pending);
     }
 }
-template <uint32_t T, class FT, int ROWS, int K>
-__global__ void __launch_bounds__(ROWS)
+template <uint32_t T, class FT, int ROWS, int K, int MINB>
+__global__ void __launch_bounds__(ROWS, MINB)
 quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t nblocks) {
     using TR = BlockTraits<T>;
     using E = Encoder<T>;
@@ -781,12 +781,12 @@ quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, s
     }
 }
 
-template <uint32_t T, class FT, int ROWS, int K>
+template <uint32_t T, class FT, int ROWS, int K, int MINB>
 static cudaError_t launch_quant_oneshot(const void *src, void *dst, size_t nblocks, cudaStream_t stream) {
     constexpr int RPB = BlockTraits<T>::ELEMS / 32, TILE_BLOCKS = ROWS / RPB;
     size_t grid = (nblocks + (size_t)TILE_BLOCKS * K - 1) / ((size_t)TILE_BLOCKS * K);
     if (grid > 0x7FFFFFFFull) grid = 0x7FFFFFFFull;
-    return launch_pdl(quant_rows_oneshot<T, FT, ROWS, K>, (unsigned)grid, ROWS, 0, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
+    return launch_pdl(quant_rows_oneshot<T, FT, ROWS, K, MINB>, (unsigned)grid, ROWS, 0, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
 }
 
 template <uint32_t T, class FT, int QS, int QL_THREADS, int MINB>
@@ -817,9 +817,11 @@ static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cuda
     constexpr bool ONESHOT_F32 = (T != T_Q8K) && std::is_same<FT, F32>::value;
     constexpr bool ONESHOT_16 = (T != T_Q8K) && !std::is_same<FT, F32>::value;
     if constexpr (ONESHOT_F32) {
-        return launch_quant_oneshot<T, FT, 128, 1>(src, dst, nblocks, stream);
+        return launch_quant_oneshot<T, FT, 128, 1, 1>(src, dst, nblocks, stream);
     } else if constexpr (ONESHOT_16) {
-        return launch_quant_oneshot<T, FT, 64, 2>(src, dst, nblocks, stream);
+        // capping the registers at 56 / 48 (launch bounds 18 / 20 CTAs per SM; no spills) changes nothing: shared memory holds
+        // residency at 17 CTAs and the time tracks the bytes, not the warps (profiles/r02_quant_legacy_minb.txt)
+        return launch_quant_oneshot<T, FT, 64, 2, 1>(src, dst, nblocks, stream);
     } else {  // Q8K: persistent ring, 64-row tiles
         // 2 input stages and 64-row tiles: 3-4 stages or 128-row tiles are 2-8 points slower (the encoder's
         // eight-lane shuffles, not bytes in flight, bound this one)
