@@ -49,12 +49,13 @@ class ConvertStats(_c.Structure):
                 ("bytes_out", _c.c_uint64), ("seconds_plan", _c.c_double), ("seconds_convert", _c.c_double),
                 ("seconds_sync", _c.c_double), ("n_devices", _c.c_int), ("n_out_files", _c.c_int), ("n_rearranged_tensors", _c.c_uint64),
                 ("n_workers", _c.c_int), ("worker_seconds_read", _c.c_double), ("worker_seconds_write", _c.c_double),
-                ("worker_seconds_gpu_wait", _c.c_double), ("h2d_bytes", _c.c_uint64), ("d2h_bytes", _c.c_uint64)]
+                ("worker_seconds_gpu_wait", _c.c_double), ("h2d_bytes", _c.c_uint64), ("d2h_bytes", _c.c_uint64),
+                ("n_direct_inputs", _c.c_int)]
 
 
 class ConvertOptions(_c.Structure):
     _fields_ = [("n_devices", _c.c_int), ("max_tensors", _c.c_uint64), ("max_bytes", _c.c_uint64), ("no_tensor_first", _c.c_int),
-                ("no_data", _c.c_int)]
+                ("no_data", _c.c_int), ("direct_io", _c.c_int)]
 
 
 class Layout(_c.Structure):

@@ -26,13 +26,13 @@ def parse_mem_size(s):
     return int(s)
 
 
-def convert(in_path, out_path, steps, n_devices=0, max_tensors=None, max_bytes=None, no_tensor_first=False, no_data=False):
+def convert(in_path, out_path, steps, n_devices=0, max_tensors=None, max_bytes=None, no_tensor_first=False, no_data=False, direct_io=False):
     """`xtask convert` for `cast:` steps.  `in_path` may be one path or a list of input shards (merged like
     `Content::new`).  Returns a dict of ggq_convert_stats.  Raises GgqError / QuantizeError like the slice API."""
     from ._lib import ConvertOptions
     paths = [in_path] if isinstance(in_path, (str, bytes)) or hasattr(in_path, "__fspath__") else list(in_path)
     arr = (ctypes.c_char_p * len(paths))(*[str(p).encode() for p in paths])
-    opts = ConvertOptions(int(n_devices), int(max_tensors or 0), parse_mem_size(max_bytes), int(bool(no_tensor_first)), int(bool(no_data)))
+    opts = ConvertOptions(int(n_devices), int(max_tensors or 0), parse_mem_size(max_bytes), int(bool(no_tensor_first)), int(bool(no_data)), int(bool(direct_io)))
     st = ConvertStats()
     rc = lib().ggq_convert_gguf_ex(arr, len(paths), str(out_path).encode(), steps.encode(), ctypes.byref(opts), ctypes.byref(st))
     if rc == 1:
@@ -53,8 +53,9 @@ def main(argv=None):
     ap.add_argument("--no-tensor-first", action="store_true")
     ap.add_argument("--no-data", action="store_true")
     ap.add_argument("--gpus", type=int, default=0)
+    ap.add_argument("--direct-io", action="store_true", help="O_DIRECT reads into the pinned staging buffers (inputs larger than RAM)")
     a = ap.parse_args(argv)
-    print(json.dumps(convert(a.file, a.out, a.steps, a.gpus, a.max_tensors, a.max_bytes, a.no_tensor_first, a.no_data)))
+    print(json.dumps(convert(a.file, a.out, a.steps, a.gpus, a.max_tensors, a.max_bytes, a.no_tensor_first, a.no_data, a.direct_io)))
 
 
 if __name__ == "__main__":

@@ -165,7 +165,7 @@ int expand_chain(const uint32_t *types, int n, std::vector<uint32_t> *out) {
 constexpr int NSLOTS = 3;
 constexpr size_t CHUNK_ELEMS = size_t(1) << 23;          // 8 Mi elements per chunk (multiple of every block size)
 constexpr size_t FIRST_CHUNK_ELEMS = size_t(1) << 20;    // ramp: 1, 2, 4, 8, 8, ... Mi elements
-constexpr size_t SLOT_BYTES = CHUNK_ELEMS * 4 + 4096;    // any representation of a chunk fits (<= 4 B/elem)
+constexpr size_t SLOT_BYTES = CHUNK_ELEMS * 4 + 16384;   // any representation of a chunk fits (<= 4 B/elem) + slack for 4 KiB-aligned direct reads
 
 struct Slot {
     void *d_a = nullptr, *d_b = nullptr, *h_in = nullptr, *h_out = nullptr;  // device ping-pong, pinned bounce
@@ -376,6 +376,10 @@ int run_jobs_io(const std::vector<ChainJob> &jobs) {
             const char *hsrc;
             if (job.io.direct_src) {
                 hsrc = static_cast<const char *>(job.io.direct_src) + in_off;
+            } else if (job.io.read_shift) {
+                const long shift = job.io.read_shift(s.h_in, SLOT_BYTES, in_off, type_nbytes(t_in, ne));
+                if (!(io_ok = shift >= 0)) break;
+                hsrc = static_cast<const char *>(s.h_in) + shift;
             } else {
                 if (!(io_ok = job.io.read(s.h_in, in_off, type_nbytes(t_in, ne)))) break;
                 hsrc = static_cast<const char *>(s.h_in);

@@ -69,8 +69,9 @@ struct InFile {
     Mapping map;
     gguf::File f;
     int fd = -1;
-    uint64_t data_off = 0;
-    ~InFile() { if (fd >= 0) close(fd); }
+    int direct_fd = -1;  // the same file opened O_DIRECT (ggq_convert_options.direct_io), or -1
+    uint64_t data_off = 0, size = 0;
+    ~InFile() { if (fd >= 0) close(fd); if (direct_fd >= 0) close(direct_fd); }
 };
 
 thread_local uint64_t t_read_ns = 0, t_write_ns = 0;  // this worker's time inside pread / pwrite (ggq_convert_stats)
@@ -164,11 +165,31 @@ class ResidentBudget {
     std::map<int, uint64_t> limit_, used_;
 };
 
+// O_DIRECT read of [off, off + n): the enclosing 4 KiB-aligned range goes straight into the (page-aligned) pinned buffer;
+// returns where `off` landed inside it, or -1.  Reads past the end of the file come back short, which is fine as long as
+// the requested bytes arrived.
+long pread_direct(int fd, void *pinned, size_t cap, size_t n, uint64_t off) {
+    ScopedNs timer(t_read_ns);
+    constexpr uint64_t A = 4096;
+    const uint64_t lo = off & ~(A - 1), hi = (off + n + A - 1) & ~(A - 1);
+    if (hi - lo > cap) return -1;
+    char *p = static_cast<char *>(pinned);
+    uint64_t got = 0;
+    while (lo + got < off + n) {
+        const ssize_t r = pread(fd, p + got, (size_t)(hi - lo - got), (off_t)(lo + got));
+        if (r <= 0) return -1;
+        got += (uint64_t)r;
+        if (got % A) break;  // short read at the end of the file: nothing more to get
+    }
+    return lo + got >= off + n ? (long)(off - lo) : -1;
+}
+
 struct IoCtx {
     const std::vector<int> *in_fds;
+    const std::vector<int> *in_direct_fds = nullptr;
     int out_fd;
     std::vector<uint8_t> *copy_buf;
-    ggq::Resident *res;  // created on first use by the worker
+    ggq::Resident *res = nullptr;  // created on first use by the worker
     std::function<ggq::Resident *()> resident;
     bool used_resident = false;  // set by emit(): the tensor went through the device-resident path
     ResidentBudget *budget = nullptr;
@@ -272,6 +293,8 @@ int emit(const Node &n, uint64_t out_off, IoCtx &io) {
         const uint64_t src_off = src.file_off;
         ggq::ChainIO cio;
         cio.read = [&](void *pinned, size_t off, size_t len) { return pread_all(ifd, pinned, len, src_off + off); };
+        const int dfd = io.in_direct_fds ? (*io.in_direct_fds)[src.file] : -1;
+        if (dfd >= 0) cio.read_shift = [=](void *pinned, size_t cap, size_t off, size_t len) { return pread_direct(dfd, pinned, cap, len, src_off + off); };
         cio.write = [&](const void *pinned, size_t off, size_t len) { return pwrite_all(ofd, pinned, len, out_off + off); };
         const int rc = ggq::cast_chain_io(n.chain.data(), (int)n.chain.size(), count(n.shape), cio);
         if (rc != GGQ_OK) t_cerr = ggq_last_error();
@@ -354,6 +377,7 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
         }
         // ---- map + parse every input shard and merge them (utils/mod.rs:42-46, read.rs:5-62) ----
         std::vector<std::unique_ptr<InFile>> files;
+        int n_direct = 0;
         uint64_t alignment = 0, bytes_in = 0;
         std::vector<const gguf::MetaKV *> kvs;
         std::set<std::string_view> kv_seen, name_seen;
@@ -365,6 +389,11 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
             struct stat st;
             if (fstat(in->fd, &st) != 0) return failc(GGQ_ERR_INVALID, std::string("cannot stat ") + in_paths[i]);
             in->map.len = (size_t)st.st_size;
+            in->size = (uint64_t)st.st_size;
+            if (o.direct_io) {
+                in->direct_fd = open(in_paths[i], O_RDONLY | O_DIRECT);  // -1 (EINVAL) where the file system has no O_DIRECT: buffered reads then
+                n_direct += in->direct_fd >= 0;
+            }
             in->map.p = (uint8_t *)mmap(nullptr, in->map.len, PROT_READ, MAP_PRIVATE, in->fd, 0);
             if (in->map.p == MAP_FAILED) { in->map.p = nullptr; return failc(GGQ_ERR_INVALID, "mmap of the input failed"); }
             in->f = gguf::File::parse(in->map.p, in->map.len);
@@ -513,14 +542,20 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
             int ok = GGQ_OK;
             if (rc_all.compare_exchange_strong(ok, rc)) first_err = m;
         };
-        std::vector<int> in_fds;
-        for (const auto &f : files) in_fds.push_back(f->fd);
+        std::vector<int> in_fds, in_direct_fds;
+        for (const auto &f : files) { in_fds.push_back(f->fd); in_direct_fds.push_back(f->direct_fd); }
         ResidentBudget budget;
         auto worker_body = [&](int dev) {
             if (need_gpu && ggq_set_device(dev) != GGQ_OK) { set_err(GGQ_ERR_CUDA, ggq_last_error()); return; }
             std::vector<uint8_t> copy_buf;
             std::unique_ptr<ggq::Resident> res;
-            IoCtx io{&in_fds, -1, &copy_buf, nullptr, nullptr, false, &budget, dev};
+            IoCtx io;
+            io.in_fds = &in_fds;
+            io.in_direct_fds = n_direct ? &in_direct_fds : nullptr;
+            io.out_fd = -1;
+            io.copy_buf = &copy_buf;
+            io.budget = &budget;
+            io.device = dev;
             io.resident = [&]() -> ggq::Resident * {
                 if (!res) {
                     res = std::make_unique<ggq::Resident>();
@@ -589,6 +624,7 @@ int ggq_convert_gguf_ex(const char *const *in_paths, size_t n_in, const char *ou
             stats->worker_seconds_gpu_wait = gpu_wait_ns.load() * 1e-9;
             stats->h2d_bytes = h2d_bytes.load();
             stats->d2h_bytes = d2h_bytes.load();
+            stats->n_direct_inputs = n_direct;
         }
         return GGQ_OK;
     } catch (const std::exception &e) {

@@ -14,6 +14,9 @@ struct ChainIO {
     void *direct_dst = nullptr;        // pinned host memory for the whole output, or null
     std::function<bool(void *pinned, size_t byte_off, size_t nbytes)> read;         // fill a pinned bounce buffer
     std::function<bool(const void *pinned, size_t byte_off, size_t nbytes)> write;  // drain one
+    // Optional replacement for `read` (O_DIRECT sources): may place the bytes anywhere in [pinned, pinned + cap) and returns
+    // the offset they start at (< 0: failure), so a 4 KiB-aligned read can cover an unaligned tensor range without a copy.
+    std::function<long(void *pinned, size_t cap, size_t byte_off, size_t nbytes)> read_shift;
 };
 
 // cast.rs:93-138 over a chain of types, streaming through the H2D -> kernels -> D2H pipeline of the

@@ -206,6 +206,7 @@ struct ggq_convert_stats {
     double worker_seconds_write;    /* pwrite of output bytes from pinned staging */
     double worker_seconds_gpu_wait; /* blocked on the GPU: H2D + kernels + D2H of a chunk not finished yet */
     uint64_t h2d_bytes, d2h_bytes;  /* bytes that crossed PCIe in each direction */
+    int n_direct_inputs;            /* input files actually opened with O_DIRECT (ggq_convert_options.direct_io) */
 };
 
 /* `OutputArgs` of xtask (xtask/src/utils/output.rs:8-53); zero means "unlimited" / "off". */
@@ -215,6 +216,11 @@ struct ggq_convert_options {
     uint64_t max_bytes;     /* -s: max bytes per output shard (the reference parses "4G", "512M", ...) */
     int no_tensor_first;    /* --no-tensor-first: shard 1 carries only the metadata */
     int no_data;            /* --no-data: write header, KVs and tensor infos only */
+    int direct_io;          /* read the tensors that stream through a cast with O_DIRECT: 4 KiB-aligned preads land
+                             * straight in the pinned staging buffers and the H2D copy starts at the tensor's offset
+                             * inside them — no page-cache copy, for inputs larger than RAM (ggus/src/file.rs:66-145
+                             * maps the file instead).  Falls back to buffered reads where the file system refuses
+                             * O_DIRECT.  Output bytes are identical either way. */
 };
 
 /* `xtask convert FILE --steps "cast:linear:q8_0 embd:q8_0 -> cast:linear:f32 ..."` —

@@ -49,6 +49,7 @@ pub struct GgqConvertStats {
     pub worker_seconds_gpu_wait: f64,
     pub h2d_bytes: u64,
     pub d2h_bytes: u64,
+    pub n_direct_inputs: c_int,
 }
 
 #[repr(C)]
@@ -59,6 +60,7 @@ pub struct GgqConvertOptions {
     pub max_bytes: u64,
     pub no_tensor_first: c_int,
     pub no_data: c_int,
+    pub direct_io: c_int,
 }
 
 extern "C" {

@@ -352,3 +352,24 @@ def test_convert_leaves_the_callers_thread_state_alone(ggq, oracle, tmp_path):
     assert torch.cuda.current_device() == cur
     y = torch.zeros(4, device="cuda")                      # the caller's own CUDA work still targets its device
     assert y.device.index == cur
+
+
+@pytest.mark.gpu
+def test_convert_direct_io_gives_the_same_bytes(ggq, oracle, tmp_path):
+    """ggq_convert_options.direct_io: tensors that stream through a cast are read with O_DIRECT, 4 KiB-aligned, straight
+    into the pinned staging buffers (tensor offsets are only 64-byte aligned; one tensor spans several pipeline chunks
+    and ends at the end of the file).  The output must equal the buffered run byte for byte and the oracle per tensor."""
+    from gguf_b200.convert import convert
+    src = tmp_path / "in.gguf"
+    ts = llama_like(big=(4096, 2400))            # 9.8 M elements: two pipeline chunks, not a multiple of 4 KiB
+    write_gguf(src, KVS, ts, alignment=64)       # KVS declares general.alignment = 64
+    a, b = tmp_path / "buffered.gguf", tmp_path / "direct.gguf"
+    st0 = convert(src, a, "cast:linear:q8_0 embd:q4k")
+    st1 = convert(src, b, "cast:linear:q8_0 embd:q4k", direct_io=True)
+    assert st0["n_direct_inputs"] == 0
+    print("inputs opened with O_DIRECT:", st1["n_direct_inputs"])     # 0 where the file system refuses it (fallback)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    _, tensors, _, _ = read_gguf(b)
+    name, shape, ty, data = ts[-1]
+    want = oracle.quantize(Q8_0, F16, np.frombuffer(data, np.uint16), threads=8)
+    assert tensors[name][1] == Q8_0 and np.array_equal(np.frombuffer(tensors[name][2], np.uint8), want)
