@@ -103,6 +103,23 @@ template <class Blk, class T> struct QuantExt {
     }
 };
 
+// ---- several slice calls as one (no counterpart in the reference: what the per-shard writer loop of
+// ggus/src/write/file_writer.rs:121-134 becomes when it hands the library all of a shard's tensors) ---------------
+template <class Blk, class T> ggq_slice_job quantize_job(Blk *dst, size_t dst_len, const T *src, size_t src_len) {
+    return ggq_slice_job{BlockInfo<Blk>::ID, FloatSide<T>::ID, 1, dst, dst_len, src, src_len};
+}
+template <class Blk, class T> ggq_slice_job dequantize_job(T *dst, size_t dst_len, const Blk *src, size_t src_len) {
+    return ggq_slice_job{BlockInfo<Blk>::ID, FloatSide<T>::ID, 0, dst, dst_len, src, src_len};
+}
+// host pointers, synchronous, one streamed pipeline (split over GPUs after ggq_set_shard_devices on this thread)
+inline Result slices(const ggq_slice_job *jobs, size_t n) { return Result(ggq_slices(jobs, n)); }
+// device pointers, enqueued on `stream`; consecutive dequantize jobs of one float side share a single grid
+inline Result slices_device(const ggq_slice_job *jobs, size_t n, void *stream) { return Result(ggq_slices_device(jobs, n, stream)); }
+// how `slices` would be split over n_devices GPUs (pure host function)
+inline size_t plan_shards(const ggq_slice_job *jobs, size_t n, int n_devices, ggq_shard_piece *out, size_t cap) {
+    return ggq_plan_shards(jobs, n, n_devices, out, cap);
+}
+
 // ---- Quantize<T, N> for Blk (lib.rs:53-90): one block at a time --------------------------------------
 template <class Blk, class T> struct Quantize {
     static constexpr size_t N = BlockInfo<Blk>::COUNT;

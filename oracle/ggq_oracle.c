@@ -6,6 +6,13 @@
  *
  * Every function cites the reference file:line it restates (paths under /root/reference/).
  * All arithmetic is IEEE binary32, one rounding per written operator, evaluated left to right.
+ *
+ * The K-quant arithmetic (make_qkx2_quants, make_qx_quants, make_q3_quants, quantize / dequantize of Q2K..Q6K) has no
+ * counterpart in the reference (`todo!()`); it restates upstream ggml's `ggml-quants.c` (llama.cpp / ggml,
+ * Copyright (c) 2023-2024 The ggml authors, MIT License: "Permission is hereby granted, free of charge, to any person
+ * obtaining a copy of this software and associated documentation files ... The above copyright notice and this permission
+ * notice shall be included in all copies or substantial portions of the Software.") so that results are bit-identical
+ * to what every GGUF consumer expects.  The loops follow upstream's order of operations by necessity.
  */
 #include "ggq_oracle.h"
 

@@ -60,9 +60,32 @@ template <class Blk> static void test_block_tolerance(std::mt19937 &rng, float t
     if (worst > tol) { std::printf("FAIL %s: max abs err %g > %g\n", name, worst, tol); failures++; }
 }
 
+// the multi-GPU split as the library reports it (pure host function): covers every element once, cuts on 2^20 elements
+static void test_plan_shards() {
+    std::vector<ggq_slice_job> jobs;
+    const size_t n0 = size_t(4096) * 14336, n1 = size_t(4096) * 4096;
+    jobs.push_back(dequantize_job<Q4_0, f16>(nullptr, n0, nullptr, n0 / 32));
+    jobs.push_back(quantize_job<Q8_0, f16>(nullptr, n1 / 32, nullptr, n1));
+    for (int ndev : {1, 2, 8}) {
+        std::vector<ggq_shard_piece> p(64);
+        const size_t n = plan_shards(jobs.data(), jobs.size(), ndev, p.data(), p.size());
+        CHECK(n >= (size_t)ndev && n <= p.size());
+        size_t covered[2] = {0, 0};
+        for (size_t i = 0; i < n; i++) {
+            CHECK(p[i].device >= 0 && p[i].device < ndev && p[i].elem_begin % (size_t(1) << 20) == 0);
+            covered[p[i].job] += p[i].elem_end - p[i].elem_begin;
+        }
+        CHECK(covered[0] == n0 && covered[1] == n1);
+    }
+    ggq_slice_job bad = quantize_job<Q8_0, float>(nullptr, 3, nullptr, 33);
+    CHECK(plan_shards(&bad, 1, 2, nullptr, 0) == 0);
+    CHECK(slices(&bad, 1).unwrap_err() == QuantizeError::Indivisible);
+}
+
 int main(int argc, char **argv) {
     const bool no_gpu = argc > 1 && std::strcmp(argv[1], "--no-gpu") == 0;
     test_error_order();
+    test_plan_shards();
     if (!no_gpu) {
         if (ggq_device_count() < 1) { std::printf("no CUDA device\n"); return 2; }
         std::mt19937 rng(1234);
