@@ -92,6 +92,58 @@ template <> struct Row<F16> {
     }
 };
 
+// ---- staging layout --------------------------------------------------------------------------------------------------
+// 32-element rows of a tile in shared memory.  Legacy blocks (one thread per row): rows padded by 16 bytes, so every
+// thread's LDS.128 of its own row is bank-conflict free.  Q8K (eight lanes per 256-element super-block, see
+// Encoder<T_Q8K>): the eight rows of a super-block stay contiguous and each SUPER-BLOCK is padded by 64 bytes (its
+// stride is 16 words mod 32), because there the eight lanes of a group read consecutive 8- / 16-byte pieces.
+template <uint32_t T, class FT> struct Stage {
+    static constexpr bool SB = (T == T_Q8K);
+    static constexpr int ROW_BYTES = 32 * FT::SIZE;
+    static constexpr int ROW_STRIDE = SB ? ROW_BYTES : ROW_BYTES + 16;
+    static constexpr int SB_PAD = SB ? 64 : 0;
+    static __host__ __device__ constexpr int bytes(int rows) { return rows * ROW_STRIDE + rows / 8 * SB_PAD; }
+    static __device__ __forceinline__ uint32_t row_off(uint32_t r) { return r * ROW_STRIDE + (r >> 3) * SB_PAD; }
+};
+
+// Q8K: lane j (0..7) of a group owns the four elements 32k + 4j .. 32k + 4j + 3 of every row k (0..7) of its super-block,
+// i.e. x[4k + i] = element 32k + 4j + i.  A group then reads 64 (f16) or 128 (f32) consecutive bytes per k, and — what
+// matters — writes its codes as consecutive words: with one row per lane the sixteen 2-byte stores of a lane went to
+// addresses 32 bytes apart across the group, an 8-way bank conflict (ncu: 58 % of all shared-memory wavefronts were
+// conflicts, mio_throttle / short_scoreboard the top stalls, 13.3 instructions per element).
+template <class FT> __device__ __forceinline__ void load_interleaved(Row<FT> &r, const uint8_t *sb, int j);
+template <> __device__ __forceinline__ void load_interleaved<F32>(Row<F32> &r, const uint8_t *sb, int j) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const float4 v = *reinterpret_cast<const float4 *>(sb + 128 * k + 16 * j);
+        r.x[4 * k] = v.x; r.x[4 * k + 1] = v.y; r.x[4 * k + 2] = v.z; r.x[4 * k + 3] = v.w;
+    }
+}
+template <> __device__ __forceinline__ void load_interleaved<F16>(Row<F16> &r, const uint8_t *sb, int j) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(sb + 64 * k + 8 * j);
+        r.raw[2 * k] = v.x; r.raw[2 * k + 1] = v.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&r.raw[k]));
+        r.x[2 * k] = f.x; r.x[2 * k + 1] = f.y;
+    }
+}
+template <> __device__ __forceinline__ void load_interleaved<BF16>(Row<BF16> &r, const uint8_t *sb, int j) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(sb + 64 * k + 8 * j);
+        r.raw[2 * k] = v.x; r.raw[2 * k + 1] = v.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        r.x[2 * k] = __uint_as_float(r.raw[k] << 16);
+        r.x[2 * k + 1] = __uint_as_float(r.raw[k] & 0xFFFF0000u);
+    }
+}
+
 // ---- folds of structs.rs:91-107 over the 32 elements of one row -----------------------------------
 // All three are max/min folds that ignore NaN; max and min are exact, so evaluating them on packed f16
 // pairs gives the same value as the reference's f32 fold.
@@ -185,7 +237,9 @@ template <> __device__ __forceinline__ void row_min_max<BF16>(const Row<BF16> &r
 // max_by_abs (structs.rs:96-100) over G lanes x 32 elements: the FIRST x with strictly greatest |x|.
 // With P = max(0, x...) and N = min(0, x...) the winner is P if P > -N, N if -N > P; only when both
 // +a and -a occur (P == -N != 0) does the order matter, and then the first of them wins.
-template <int G, class FT> __device__ __forceinline__ float max_by_abs_from(const Row<FT> &r, int j, float P, float N) {
+// `INTERLEAVED`: r.x[i] is element 32 (i / 4) + 4 j + (i % 4) of the group's 256 (Q8K), else element 32 j + i.
+template <int G, class FT, bool INTERLEAVED = false> __device__ __forceinline__ float max_by_abs_from(const Row<FT> &r, int j, float P, float N) {
+    auto index_of = [j](int i) { return INTERLEAVED ? 32 * (i >> 2) + 4 * j + (i & 3) : 32 * j + i; };
 #pragma unroll
     for (int m = 1; m < G; m <<= 1) {
         P = fmaxf(P, __shfl_xor_sync(FULL, P, m));
@@ -198,10 +252,10 @@ template <int G, class FT> __device__ __forceinline__ float max_by_abs_from(cons
     if (G == 1 ? tie : __any_sync(FULL, tie)) {  // G > 1: every lane of the warp runs the shuffles
         int first = 32 * G;
 #pragma unroll
-        for (int i = 31; i >= 0; i--) first = (fabsf(r.x[i]) == P) ? (32 * j + i) : first;
+        for (int i = 31; i >= 0; i--) first = (fabsf(r.x[i]) == P) ? index_of(i) : first;  // indices ascend with i in both layouts
         float val = 0.0f;
 #pragma unroll
-        for (int i = 31; i >= 0; i--) val = (32 * j + i == first) ? r.x[i] : val;
+        for (int i = 31; i >= 0; i--) val = (index_of(i) == first) ? r.x[i] : val;
 #pragma unroll
         for (int m = 1; m < G; m <<= 1) {
             const int of = __shfl_xor_sync(FULL, first, m);
@@ -533,15 +587,17 @@ template <> struct Encoder<T_Q8_0> : Encoder8<T_Q8_0, false> {};
 template <> struct Encoder<T_Q8_1> : Encoder8<T_Q8_1, true> {};
 
 // q8_k.rs:27-54 — reference layout {delta: f16, quants: [i8;256], sums: [i16;16]}, 290 bytes.
-// 8 consecutive lanes own one super-block; lane j holds elements 32j .. 32j+31.
+// 8 consecutive lanes own one super-block; lane j holds elements 32k + 4j .. + 3 of every row k (load_interleaved).
 template <> struct Encoder<T_Q8K> {
     static constexpr int G = 8;
     template <class FT> static __device__ __forceinline__ void run(const Row<FT> &r, int j, uint8_t *blk) {
-        const float mx = block_max_by_abs<8, FT>(r, j);
+        float P, N;
+        row_pos_neg<FT>(r, P, N);
+        const float mx = max_by_abs_from<8, FT, true>(r, j, P, N);
         uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         uint32_t d16 = 0;
-        int s0 = 0, s1 = 0;
-        if (mx != 0.0f) {
+        int v[4] = {0, 0, 0, 0};  // per-row sums of this lane's codes, two 16-bit sums per register
+        if (mx != 0.0f) {  // uniform over the group (not over the warp: no shuffles in here)
             const float d = __fdiv_rn(mx, -127.0f), rc = __fdiv_rn(1.0f, d);
             d16 = f2h(d);
             int q[32];
@@ -559,11 +615,29 @@ template <> struct Encoder<T_Q8K> {
 #pragma unroll
             for (int k = 0; k < 8; k++) w[k] = pack_sat_s8(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
 #pragma unroll
-            for (int k = 0; k < 4; k++) { s0 = __dp4a((int)w[k], 0x01010101, s0); s1 = __dp4a((int)w[k + 4], 0x01010101, s1); }
+            for (int m = 0; m < 4; m++) v[m] = __dp4a((int)w[2 * m], 0x01010101, 0) + (__dp4a((int)w[2 * m + 1], 0x01010101, 0) << 16);
         }
-        sts_words2<8>(blk + 2 + 32 * j, w);
-        sts16(blk + 258 + 4 * j, (uint32_t)s0 & 0xFFFFu);
-        sts16(blk + 258 + 4 * j + 2, (uint32_t)s1 & 0xFFFFu);
+        // sums[g] covers elements 16g .. 16g + 15 = row k = g / 2, lanes 0..3 (g even) or 4..7 (g odd): four-lane reductions
+        // of the eight per-row sums (|sum| <= 16 * 128: the halves of a register never carry into each other beyond what the
+        // unpacking below undoes)
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            v[m] += __shfl_xor_sync(FULL, v[m], 1);
+            v[m] += __shfl_xor_sync(FULL, v[m], 2);
+        }
+        const int m4 = j & 3;  // this lane stores the sums of rows 2 m4 and 2 m4 + 1 for its half of each row
+        const int vm = m4 == 0 ? v[0] : m4 == 1 ? v[1] : m4 == 2 ? v[2] : v[3];
+        const int s_lo = (int)(short)(vm & 0xFFFF);
+        const int s_hi = (vm - s_lo) >> 16;
+        // codes: word k of lane j is bytes 2 + 32k + 4j .. + 3 of the block: consecutive words across the group
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            sts16(blk + 2 + 32 * k + 4 * j, w[k] & 0xFFFFu);
+            sts16(blk + 2 + 32 * k + 4 * j + 2, w[k] >> 16);
+        }
+        const int half = j >> 2;  // sums[2 * (2 m4) + half] and sums[2 * (2 m4 + 1) + half]
+        sts16(blk + 258 + 2 * (4 * m4 + half), (uint32_t)s_lo & 0xFFFFu);
+        sts16(blk + 258 + 2 * (4 * m4 + 2 + half), (uint32_t)s_hi & 0xFFFFu);
         if (j == 0) sts16(blk, d16);
     }
 };
@@ -577,8 +651,9 @@ quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, si
     using E = Encoder<T>;
     constexpr int RPB = TR::ELEMS / 32;                 // rows per block (1, or 8 for Q8K)
     constexpr int TILE_BLOCKS = QL_THREADS / RPB;
-    constexpr int ROW_BYTES = 32 * FT::SIZE, ROW_STRIDE = ROW_BYTES + 16, CPR = ROW_BYTES / 16;
-    constexpr int IN_STAGE = QL_THREADS * ROW_STRIDE;
+    using ST = Stage<T, FT>;
+    constexpr int ROW_BYTES = 32 * FT::SIZE, CPR = ROW_BYTES / 16;
+    constexpr int IN_STAGE = ST::bytes(QL_THREADS);
     constexpr int OUT_STAGE = (TILE_BLOCKS * TR::BYTES + 15) & ~15;
     static_assert((TILE_BLOCKS * TR::BYTES) % 16 == 0, "tile must be a whole number of 16-byte chunks");
     extern __shared__ __align__(128) uint8_t smem[];
@@ -597,7 +672,9 @@ quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, si
     size_t t_issue = blockIdx.x;
     const uint8_t *g_issue = src + t_issue * TILE_IN + (size_t)tid * 16;
     const size_t g_step = (size_t)gridDim.x * TILE_IN;
-    const uint32_t s_chunk0 = (uint32_t)(tid / CPR) * ROW_STRIDE + (uint32_t)(tid % CPR) * 16;
+    const uint32_t s_chunk0 = ST::row_off((uint32_t)(tid / CPR)) + (uint32_t)(tid % CPR) * 16;
+    constexpr uint32_t PASS_STRIDE = ST::bytes(ROWS_PER_PASS);  // ROWS_PER_PASS is a multiple of 8: whole super-blocks
+    static_assert(ROWS_PER_PASS % 8 == 0, "a pass of chunks covers whole super-blocks");
     int s_issue = 0;
     auto issue = [&]() {  // all threads; 16-byte chunks, coalesced
         if (t_issue < ntiles) {
@@ -606,19 +683,19 @@ quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, si
             if (vec_in) {
                 if (rem >= (size_t)QL_THREADS) {
 #pragma unroll
-                    for (int k = 0; k < CPR; k++) cp_async16(st + s_chunk0 + k * ROWS_PER_PASS * ROW_STRIDE, g_issue + (size_t)k * QL_THREADS * 16);
+                    for (int k = 0; k < CPR; k++) cp_async16(st + s_chunk0 + k * PASS_STRIDE, g_issue + (size_t)k * QL_THREADS * 16);
                 } else {
 #pragma unroll
                     for (int k = 0; k < CPR; k++)
                         if ((size_t)(tid / CPR + k * ROWS_PER_PASS) < rem)
-                            cp_async16(st + s_chunk0 + k * ROWS_PER_PASS * ROW_STRIDE, g_issue + (size_t)k * QL_THREADS * 16);
+                            cp_async16(st + s_chunk0 + k * PASS_STRIDE, g_issue + (size_t)k * QL_THREADS * 16);
                 }
             } else {  // source not 16-byte aligned: element-granular synchronous staging
                 using RAW = typename FT::raw;
                 const RAW *ge = reinterpret_cast<const RAW *>(g_issue - (size_t)tid * 16);
                 const int rows = (int)min((size_t)QL_THREADS, rem);
                 for (int e = tid; e < rows * 32; e += QL_THREADS)
-                    *reinterpret_cast<RAW *>(st + (e / 32) * ROW_STRIDE + (e % 32) * FT::SIZE) = ge[e];
+                    *reinterpret_cast<RAW *>(st + ST::row_off(e / 32) + (e % 32) * FT::SIZE) = ge[e];
             }
         }
         cp_async_commit();
@@ -634,7 +711,8 @@ quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, si
     __syncthreads();
 
     // ---- consumer state ----
-    const uint8_t *my_row = in_st + tid * ROW_STRIDE;
+    // legacy: this thread's row; Q8K: the first row of this thread's super-block (its lane reads pieces of all eight)
+    const uint8_t *my_row = in_st + ST::row_off(ST::SB ? (uint32_t)(tid & ~7) : (uint32_t)tid);
     const int my_j = tid % RPB;
     const uint32_t my_out = (uint32_t)(tid / RPB) * TR::BYTES;
     uint8_t *o_ptr = dst + (size_t)blockIdx.x * TILE_OUT;
@@ -648,8 +726,13 @@ quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, si
         // had finished READING shared memory before the barrier of the previous iteration.
         if (RPB > 1 || tid < rows) {  // G > 1 encoders shuffle: every lane of the warp takes part
             Row<FT> r;
-            if (tid < rows) r.load(my_row + s_cons * IN_STAGE);
-            else r.zero();
+            if constexpr (ST::SB) {  // rows come in whole super-blocks: all eight lanes of a group are live or none is
+                if (tid < rows) load_interleaved<FT>(r, my_row + s_cons * IN_STAGE, my_j);
+                else r.zero();
+            } else {
+                if (tid < rows) r.load(my_row + s_cons * IN_STAGE);
+                else r.zero();
+            }
             E::template run<FT>(r, my_j, ost + my_out);
         }
         fence_proxy_async_smem();                  // generic-proxy writes -> async-proxy (bulk store) reads
@@ -692,15 +775,19 @@ quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, s
     using TR = BlockTraits<T>;
     using E = Encoder<T>;
     constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = ROWS / RPB;
-    constexpr int ROW_BYTES = 32 * FT::SIZE, ROW_STRIDE = ROW_BYTES + 16, CPR = ROW_BYTES / 16, ROWS_PER_PASS = ROWS / CPR;
-    constexpr int IN_STAGE = ROWS * ROW_STRIDE, OUT_BYTES = TILE_BLOCKS * TR::BYTES;
+    using ST = Stage<T, FT>;
+    constexpr int ROW_BYTES = 32 * FT::SIZE, CPR = ROW_BYTES / 16, ROWS_PER_PASS = ROWS / CPR;
+    constexpr int IN_STAGE = ST::bytes(ROWS), OUT_BYTES = TILE_BLOCKS * TR::BYTES;
+    constexpr uint32_t PASS_STRIDE = ST::bytes(ROWS_PER_PASS);
+    static_assert(ROWS_PER_PASS % 8 == 0, "a pass of chunks covers whole super-blocks");
     static_assert(OUT_BYTES % 16 == 0, "tile must be a whole number of 16-byte chunks");
     __shared__ __align__(128) uint8_t in_st[K * IN_STAGE];
     __shared__ __align__(16) uint8_t out_st[K * OUT_BYTES];
     const int tid = threadIdx.x;
     const size_t nrows = nblocks * RPB, ntiles = (nrows + ROWS - 1) / ROWS;
     const bool vec_in = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-    const uint32_t s_chunk0 = (uint32_t)(tid / CPR) * ROW_STRIDE + (uint32_t)(tid % CPR) * 16;
+    const uint32_t s_chunk0 = ST::row_off((uint32_t)(tid / CPR)) + (uint32_t)(tid % CPR) * 16;
+    const uint32_t my_row_off = ST::row_off(ST::SB ? (uint32_t)(tid & ~7) : (uint32_t)tid);
     pdl_launch_dependents();
     pdl_wait();
     const bool vec_out = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
@@ -714,7 +801,7 @@ quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, s
             for (int k = 0; k < K; k++) {
 #pragma unroll
                 for (int c = 0; c < CPR; c++)
-                    cp_async16(in_st + k * IN_STAGE + s_chunk0 + c * ROWS_PER_PASS * ROW_STRIDE, g + (size_t)k * ROWS * ROW_BYTES + (size_t)c * ROWS * 16);
+                    cp_async16(in_st + k * IN_STAGE + s_chunk0 + c * PASS_STRIDE, g + (size_t)k * ROWS * ROW_BYTES + (size_t)c * ROWS * 16);
                 cp_async_commit();
             }
 #pragma unroll
@@ -722,7 +809,8 @@ quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, s
                 cp_async_wait_upto<K - 1>(K - 1 - k);
                 __syncthreads();
                 Row<FT> r;
-                r.load(in_st + k * IN_STAGE + tid * ROW_STRIDE);
+                if constexpr (ST::SB) load_interleaved<FT>(r, in_st + k * IN_STAGE + my_row_off, tid % RPB);
+                else r.load(in_st + k * IN_STAGE + my_row_off);
                 E::template run<FT>(r, tid % RPB, out_st + k * OUT_BYTES + (uint32_t)(tid / RPB) * TR::BYTES);
             }
             __syncthreads();
@@ -746,12 +834,12 @@ quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, s
 #pragma unroll
                     for (int c = 0; c < CPR; c++)
                         if (rows == ROWS || tid / CPR + c * ROWS_PER_PASS < rows)
-                            cp_async16(st + s_chunk0 + c * ROWS_PER_PASS * ROW_STRIDE, g + (size_t)tid * 16 + (size_t)c * ROWS * 16);
+                            cp_async16(st + s_chunk0 + c * PASS_STRIDE, g + (size_t)tid * 16 + (size_t)c * ROWS * 16);
                 } else {  // source not 16-byte aligned: element-granular staging
                     using RAW = typename FT::raw;
                     const RAW *ge = reinterpret_cast<const RAW *>(g);
                     for (int e = tid; e < rows * 32; e += ROWS)
-                        *reinterpret_cast<RAW *>(st + (e / 32) * ROW_STRIDE + (e % 32) * FT::SIZE) = ge[e];
+                        *reinterpret_cast<RAW *>(st + ST::row_off(e / 32) + (e % 32) * FT::SIZE) = ge[e];
                 }
             }
             cp_async_commit();  // one group per tile, empty or not
@@ -767,8 +855,9 @@ quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, s
                 __syncthreads();
                 if (RPB > 1 || tid < rows) {  // G > 1 encoders shuffle: every lane of the warp takes part
                     Row<FT> r;
-                    if (tid < rows) r.load(in_st + k * IN_STAGE + tid * ROW_STRIDE);
-                    else r.zero();
+                    if (tid >= rows) r.zero();
+                    else if constexpr (ST::SB) load_interleaved<FT>(r, in_st + k * IN_STAGE + my_row_off, tid % RPB);
+                    else r.load(in_st + k * IN_STAGE + my_row_off);
                     E::template run<FT>(r, tid % RPB, out_st + k * OUT_BYTES + (uint32_t)(tid / RPB) * TR::BYTES);
                 }
                 rows_total += rows;
@@ -793,7 +882,7 @@ template <uint32_t T, class FT, int QS, int QL_THREADS, int MINB>
 static cudaError_t launch_quant_ring(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
     using TR = BlockTraits<T>;
     constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = QL_THREADS / RPB;
-    constexpr int SMEM = QS * QL_THREADS * (32 * FT::SIZE + 16) + 2 * ((TILE_BLOCKS * TR::BYTES + 15) & ~15);
+    constexpr int SMEM = QS * Stage<T, FT>::bytes(QL_THREADS) + 2 * ((TILE_BLOCKS * TR::BYTES + 15) & ~15);
     auto kern = quant_rows_kernel<T, FT, QS, QL_THREADS, MINB>;
     static std::atomic<int> occ_cache[MAX_DEVICES];
     int ctas_per_sm = 0;
@@ -813,7 +902,7 @@ static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cuda
     //   16-bit input: two 64-row tiles per CTA, both requested up front: 83-89 % (ring and one tile per CTA: 73-75 %
     //   for the 4/5-bit types, 84-87 % for Q8_0 / Q8_1 — bytes in flight, not instructions, were the limit; K = 3,
     //   96- and 128-row tiles are 1-3 points behind, 32-row tiles 10);
-    //   Q8K's eight-lane groups are slower in every one-shot form (59-64 % vs 74 %) and keep the ring's 64-row tiles.
+    //   Q8K: see below.
     constexpr bool ONESHOT_F32 = (T != T_Q8K) && std::is_same<FT, F32>::value;
     constexpr bool ONESHOT_16 = (T != T_Q8K) && !std::is_same<FT, F32>::value;
     if constexpr (ONESHOT_F32) {
@@ -822,10 +911,13 @@ static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cuda
         // capping the registers at 56 / 48 (launch bounds 18 / 20 CTAs per SM; no spills) changes nothing: shared memory holds
         // residency at 17 CTAs and the time tracks the bytes, not the warps (profiles/r02_quant_legacy_minb.txt)
         return launch_quant_oneshot<T, FT, 64, 2, 1>(src, dst, nblocks, stream);
-    } else {  // Q8K: persistent ring, 64-row tiles
-        // 2 input stages and 64-row tiles: 3-4 stages or 128-row tiles are 2-8 points slower (the encoder's
-        // eight-lane shuffles, not bytes in flight, bound this one)
-        // capped at 64 registers (14 CTAs of 64 threads per SM): +1..4 points over the 80-84 the compiler takes unasked
+    } else {  // Q8K
+        // ring: 2 input stages and 64-row tiles, capped at 72 registers (14 CTAs of 64 threads per SM)
+        // Q8K, eight interleaved lanes per super-block (Encoder<T_Q8K>; profiles/r02_quant_q8k_sweep.txt).  From f32 the
+        // short-lived two-tile CTAs of the legacy types win (102-103 % of the copy peak; ring 99 %); from 16-bit input the
+        // persistent ring does (83 / 77 % for f16 / bf16; one-shot 75 %, 128-row tiles 55-80 %).  Round 1's one-row-per-lane
+        // mapping: 73 / 72 / 90 %.
+        if constexpr (std::is_same<FT, F32>::value) return launch_quant_oneshot<T, FT, 64, 2, 1>(src, dst, nblocks, stream);
         return launch_quant_ring<T, FT, 2, 64, 14>(src, dst, nblocks, stream, dev);
     }
 }

@@ -22,6 +22,7 @@ for phase in "$@"; do
     ncu_kq)  for t in Q4K Q6K Q5K Q2K Q3K; do timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_k_kernel -c 1 -f -o gpurun_out/r02_quant_k_$t python tools/codec_sweep.py 58720256 $t:quant > gpurun_out/ncu_kq_$t.log 2>&1; tail -1 gpurun_out/ncu_kq_$t.log; done ;;
     dio)     df -h /var/tmp /tmp | cat; timeout 900 python tools/direct_io_probe.py > gpurun_out/dio.log 2>&1; tail -8 gpurun_out/dio.log ;;
     tests_conv) timeout 900 python -m pytest tests/test_convert.py -m gpu -x -q -s 2>&1 | tail -40 | cut -c1-400 ;;
+    ncu_q8k) timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_rows_kernel -c 1 -f -o gpurun_out/r02_quant_q8k_f16 python tools/codec_sweep.py 58720256 Q8K:quant > gpurun_out/ncu_q8k.log 2>&1; tail -2 gpurun_out/ncu_q8k.log ;;
     box)     bash tools/box_probe.sh > gpurun_out/box_probe.txt 2>&1 ;;
     bench2)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 800 gpurun_out/bench_n2.err; head -c 300 gpurun_out/bench_n2.json; echo ;;
     mixtral2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/mixtral_sweep.py > gpurun_out/mixtral_n2.txt 2>&1; tail -13 gpurun_out/mixtral_n2.txt ;;
