@@ -424,6 +424,9 @@ int run_chain_io(const std::vector<uint32_t> &chain, size_t n_elems, const ggq::
 // alike — the kernel's fault path, not the copy, is the bound).  Asking for transparent huge pages on the 2 MiB-
 // aligned interior turns that into one fault per 2 MiB, zeroed by whichever copy thread touches it first.  A hint
 // only: contents and mapping stay the caller's, errors are ignored, already-populated ranges are unaffected.
+// (Populating an untouched destination ahead of the copies on background threads — MADV_POPULATE_WRITE in 32 MiB
+// pieces while the first chunks are in flight — was measured and is not faster: 26.0-26.2 against 26.8-27.9 GB/s for
+// the bench step; zeroing the pages costs the same memory bandwidth whoever does it.)
 void hint_huge_pages(void *dst, size_t nbytes) {
 #ifdef MADV_HUGEPAGE
     static const bool off = getenv("GGQ_NO_THP_HINT") != nullptr;
