@@ -56,6 +56,49 @@ __device__ __forceinline__ float byte_as_float(uint32_t word, int k) {
     return __uint_as_float(__byte_perm(word, 0x4B400000u, 0x7650u + k)) - RMAGIC;
 }
 
+// ---- n / d for the 16 or 32 numerators of a sub-block that share one divisor ------------------------------------
+// Upstream requantizes with `nearest_int((x + dm) / d)`: an IEEE division per element, ~18 instructions each the way
+// the compiler expands it (reciprocal, two refinements, residual, range check).  With one divisor per sub-block the
+// reciprocal is computed once, correctly rounded (`rcp.rn`), and Markstein's sequence gives the correctly rounded
+// quotient in three operations:  q0 = RN(n r);  e = n - d q0 (exact, one FMA);  q = RN(q0 + e r)  —  the same value
+// `div.rn` returns, PROVIDED nothing under- or overflows on the way: d is taken in 2^-40 .. 2^40 and |n| <= 2^60; if
+// the exact residual is too small to be represented then |q0| < 2^-63 and the caller's nearest_int() is 0 for any
+// last-bit error.  Everything else takes `div.rn`.
+struct SharedDivisor {
+    float d, r;
+    bool ok;
+};
+__device__ __forceinline__ SharedDivisor shared_divisor(float d) {
+    SharedDivisor sd;
+    const float a = fabsf(d);
+    sd.d = d;
+    sd.ok = a >= 9.094947017729282e-13f && a <= 1.099511627776e12f;  // 2^-40 .. 2^40 (false for NaN)
+    sd.r = __frcp_rn(d);
+    return sd;
+}
+__device__ __forceinline__ float div_shared(float n, const SharedDivisor &sd) {
+    if (sd.ok && fabsf(n) <= 1.152921504606846976e18f) {  // 2^60
+        const float q0 = __fmul_rn(n, sd.r);
+        const float e = __fmaf_rn(-sd.d, q0, n);
+        return __fmaf_rn(e, sd.r, q0);
+    }
+    return __fdiv_rn(n, sd.d);
+}
+
+// The same sequence where the quotient itself is used (search scales, not just nearest_int of it): additionally
+// 2^-60 <= |n|, so the residual e (a multiple of 2^(exponent(n) - 47)) and the quotient (>= 2^-100) are ordinary numbers
+// and q is RN(n / d) without exception (host test: tests/cpp/test_shared_divisor.c, strict part).  n = 0, tiny, huge or
+// NaN numerators and out-of-range divisors take div.rn.  SD 0 disables it (A/B in tools/kq_sweep.cu).
+template <int SD> __device__ __forceinline__ float div_shared_strict(float n, const SharedDivisor &sd) {
+    const float an = fabsf(n);
+    if (SD && sd.ok && an >= 8.673617379884035e-19f && an <= 1.152921504606846976e18f) {  // 2^-60 .. 2^60
+        const float q0 = __fmul_rn(n, sd.r);
+        const float e = __fmaf_rn(-sd.d, q0, n);
+        return __fmaf_rn(e, sd.r, q0);
+    }
+    return __fdiv_rn(n, sd.d);
+}
+
 // ---- upstream make_qkx2_quants ------------------------------------------------------------------
 // Upstream keeps the codes L of the best candidate.  Every caller then REQUANTIZES the sub-block
 // with the 6-/4-bit rounded scale and min and uses the search's L only when that rounded scale is 0,
@@ -120,7 +163,7 @@ template <int RM> __device__ __forceinline__ float2 round_clamped2(float2 v, flo
 // 16-byte aligned, rows 144 bytes apart so the lanes' 128-bit accesses never share a bank) instead of N registers: two
 // 128-bit shared accesses per 4 elements and candidate, none of them on the FP32 pipe that bounds the search — and 32
 // registers fewer for the 32-element sub-blocks, which is one more resident CTA per SM.
-template <int N, bool USE_MAD, int WMODE, int LF, int AF, int RM>
+template <int N, bool USE_MAD, int WMODE, int LF, int AF, int RM, int SD>
 __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const float (&w)[N], const float av, const int nmax, float &the_min,
                                                   const float rmin, const float rdelta, const int nstep, float &isc_best, float &mn_best,
                                                   float *__restrict__ lrow, const float one) {
@@ -152,7 +195,10 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
         else return make_float2(w[2 * k], w[2 * k + 1]);
     };
     const float fmax_l = (float)nmax;
-    float iscale = fmax_l / (mx - mn);
+    // every candidate's iscale divides by (max - min), which only changes when a candidate is accepted: one correctly
+    // rounded reciprocal and three operations per quotient instead of a division each (div_shared_strict)
+    SharedDivisor range = shared_divisor(mx - mn);
+    float iscale = div_shared_strict<SD>(fmax_l, range);
     float scale = 1 / iscale;
     float best_mad = 0;
     isc_best = iscale;
@@ -172,7 +218,7 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
         }
     }
     for (int is = 0; is <= nstep; ++is) {
-        iscale = (rmin + rdelta * (float)is + fmax_l) / (mx - mn);
+        iscale = div_shared_strict<SD>(rmin + rdelta * (float)is + fmax_l, range);
         float sum_l = 0, sum_l2 = 0, sum_xl = 0;
         float2 lf[LF ? 2 : N / 2];  // LF 1: only the pair being assembled into a 128-bit store
         {
@@ -198,8 +244,9 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
         }
         const float D = sum_w * sum_l2 - sum_l * sum_l;
         if (D > 0) {
-            float this_scale = (sum_w * sum_xl - sum_x * sum_l) / D;
-            float this_min = (sum_l2 * sum_x - sum_l * sum_xl) / D;
+            const SharedDivisor sdD = shared_divisor(D);  // two quotients by D
+            float this_scale = div_shared_strict<SD>(sum_w * sum_xl - sum_x * sum_l, sdD);
+            float this_min = div_shared_strict<SD>(sum_l2 * sum_x - sum_l * sum_xl, sdD);
             if (this_min > 0) {
                 this_min = 0;
                 this_scale = sum_xl / sum_l2;
@@ -230,6 +277,7 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
                 best_mad = mad;
                 scale = this_scale;
                 mn = this_min;
+                range = shared_divisor(mx - mn);
             }
         }
     }
@@ -254,7 +302,7 @@ __device__ __forceinline__ void qx_codes16(const float (&x)[16], const float isc
 // returns the scale; `isc_best` = iscale of the kept codes; `all_zero`: upstream's early exit (L[i] = 0, raw)
 // WS 1: the per-element constants w = x*x and w*x live in the lane's shared-memory row (32 floats: w at [0, 16), w*x at
 // [16, 32)) instead of 32 registers.
-template <int WS, int RM>
+template <int WS, int RM, int SD>
 __device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const int nmax, float &isc_best, bool &all_zero, float *__restrict__ lrow) {
     float mx = 0, amax = 0;
 #pragma unroll
@@ -310,7 +358,8 @@ __device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const in
             suml2 += b.y;
         }
     };
-    float iscale = lo / mx;
+    const SharedDivisor smx = shared_divisor(mx);  // all 19 candidates divide by mx
+    float iscale = div_shared_strict<SD>(lo, smx);
     float sumlx, suml2;
     sums(iscale, sumlx, suml2);
     isc_best = iscale;
@@ -318,7 +367,7 @@ __device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const in
     float best = scale * sumlx;
     for (int is = -9; is <= 9; ++is) {
         if (is == 0) continue;
-        iscale = -(fn + 0.1f * (float)is) / mx;
+        iscale = div_shared_strict<SD>(-(fn + 0.1f * (float)is), smx);
         sums(iscale, sumlx, suml2);
         if (suml2 > 0 && sumlx * sumlx > best * suml2) {
             isc_best = iscale;
@@ -401,35 +450,6 @@ template <int G> __device__ __forceinline__ float group_max_by_abs(float v, int 
     return acc;
 }
 
-// ---- n / d for the 16 or 32 numerators of a sub-block that share one divisor ------------------------------------
-// Upstream requantizes with `nearest_int((x + dm) / d)`: an IEEE division per element, ~18 instructions each the way
-// the compiler expands it (reciprocal, two refinements, residual, range check).  With one divisor per sub-block the
-// reciprocal is computed once, correctly rounded (`rcp.rn`), and Markstein's sequence gives the correctly rounded
-// quotient in three operations:  q0 = RN(n r);  e = n - d q0 (exact, one FMA);  q = RN(q0 + e r)  —  the same value
-// `div.rn` returns, PROVIDED nothing under- or overflows on the way: d is taken in 2^-40 .. 2^40 and |n| <= 2^60; if
-// the exact residual is too small to be represented then |q0| < 2^-63 and the caller's nearest_int() is 0 for any
-// last-bit error.  Everything else takes `div.rn`.
-struct SharedDivisor {
-    float d, r;
-    bool ok;
-};
-__device__ __forceinline__ SharedDivisor shared_divisor(float d) {
-    SharedDivisor sd;
-    const float a = fabsf(d);
-    sd.d = d;
-    sd.ok = a >= 9.094947017729282e-13f && a <= 1.099511627776e12f;  // 2^-40 .. 2^40 (false for NaN)
-    sd.r = __frcp_rn(d);
-    return sd;
-}
-__device__ __forceinline__ float div_shared(float n, const SharedDivisor &sd) {
-    if (sd.ok && fabsf(n) <= 1.152921504606846976e18f) {  // 2^60
-        const float q0 = __fmul_rn(n, sd.r);
-        const float e = __fmaf_rn(-sd.d, q0, n);
-        return __fmaf_rn(e, sd.r, q0);
-    }
-    return __fdiv_rn(n, sd.d);
-}
-
 // ---- per-type quantizers ---------------------------------------------------------------------------
 // Scratch written by the lanes of one super-block, read by the bytewise assembler.
 struct KScratch {
@@ -448,7 +468,7 @@ template <int SUB> __device__ __forceinline__ void put_codes(KScratch &s, int j,
 }
 
 // Q4K and Q5K share everything but nmax / search range / final layout.
-template <int NMAX, int LF, int WM, int AF, int RM> __device__ __forceinline__ void k45_lane(const float (&x)[32], int j, KScratch &s, float rmin, int nstep, float *lrow, float one) {
+template <int NMAX, int LF, int WM, int AF, int RM, int SD> __device__ __forceinline__ void k45_lane(const float (&x)[32], int j, KScratch &s, float rmin, int nstep, float *lrow, float one) {
     float sum_x2 = 0;
 #pragma unroll
     for (int l = 0; l < 32; ++l) sum_x2 += x[l] * x[l];
@@ -463,8 +483,8 @@ template <int NMAX, int LF, int WM, int AF, int RM> __device__ __forceinline__ v
     uint32_t L[8];
     float the_min, isc_best, mn_best;
     float scale;
-    if constexpr (WM == 2) scale = make_qkx2_quants<32, false, 2, LF, AF, RM>(x, w, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best, lrow, one);
-    else scale = make_qkx2_quants<32, false, 1, LF, AF, RM>(x, x, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best, lrow, one);
+    if constexpr (WM == 2) scale = make_qkx2_quants<32, false, 2, LF, AF, RM, SD>(x, w, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best, lrow, one);
+    else scale = make_qkx2_quants<32, false, 1, LF, AF, RM, SD>(x, x, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best, lrow, one);
     const float max_scale = group_max_from_zero<8>(scale), max_min = group_max_from_zero<8>(the_min);
     const float inv_scale = max_scale > 0 ? 63.f / max_scale : 0.f;
     const float inv_min = max_min > 0 ? 63.f / max_min : 0.f;
@@ -520,7 +540,7 @@ template <> struct KQuant<T_Q4K> {
         const int t = w - 4, p = t >> 3, jj = t & 7;
         return code_word(s, 16 * p + jj) | (code_word(s, 16 * p + 8 + jj) << 4);
     }
-    template <class CFG> static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s, float *lrow, float one) { k45_lane<15, CFG::LF, CFG::WM, CFG::AF, CFG::RM>(x, j, s, -1.f, 20, lrow, one); }
+    template <class CFG> static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s, float *lrow, float one) { k45_lane<15, CFG::LF, CFG::WM, CFG::AF, CFG::RM, CFG::SD>(x, j, s, -1.f, 20, lrow, one); }
 };
 template <> struct KQuant<T_Q5K> {
     static constexpr int SUB = 32;
@@ -538,7 +558,7 @@ template <> struct KQuant<T_Q5K> {
         const int t = w - 12, p = t >> 3, jj = t & 7;
         return (code_word(s, 16 * p + jj) & 0x0F0F0F0Fu) | ((code_word(s, 16 * p + 8 + jj) & 0x0F0F0F0Fu) << 4);
     }
-    template <class CFG> static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s, float *lrow, float one) { k45_lane<31, CFG::LF, CFG::WM, CFG::AF, CFG::RM>(x, j, s, -0.5f, 15, lrow, one); }
+    template <class CFG> static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s, float *lrow, float one) { k45_lane<31, CFG::LF, CFG::WM, CFG::AF, CFG::RM, CFG::SD>(x, j, s, -0.5f, 15, lrow, one); }
 };
 
 template <> struct KQuant<T_Q6K> {
@@ -564,7 +584,7 @@ template <> struct KQuant<T_Q6K> {
         uint32_t L[4] = {0, 0, 0, 0};
         float isc_best;
         bool sub_zero;
-        const float scale = make_qx_quants16<CFG::LF, CFG::RM>(x, 32, isc_best, sub_zero, lrow);
+        const float scale = make_qx_quants16<CFG::LF, CFG::RM, CFG::SD>(x, 32, isc_best, sub_zero, lrow);
         const float max_scale = group_max_by_abs<16>(scale, lane_id);
         const bool zero = fabsf(max_scale) < GROUP_MAX_EPS;
         int sc = 0;
@@ -607,7 +627,7 @@ template <> struct KQuant<T_Q2K> {
         // weights = |x|: an operand modifier, never materialised (WMODE 0) — 7 CTAs per SM instead of 6, -4 % time
         uint32_t L[4];
         float the_min, isc_best, mn_best;
-        const float scale = make_qkx2_quants<16, true, 0, CFG::LF, CFG::AF, CFG::RM>(x, x, 0.f, 3, the_min, -0.5f, 0.1f, 15, isc_best, mn_best, lrow, one);
+        const float scale = make_qkx2_quants<16, true, 0, CFG::LF, CFG::AF, CFG::RM, CFG::SD>(x, x, 0.f, 3, the_min, -0.5f, 0.1f, 15, isc_best, mn_best, lrow, one);
         const float max_scale = group_max_from_zero<16>(scale), max_min = group_max_from_zero<16>(the_min);
         uint32_t b = 0;
         uint16_t d16 = 0, dmin16 = 0;
@@ -699,8 +719,8 @@ template <> struct KQuant<T_Q3K> {
 // which lets occupancy follow the register cap in steps of one warp rather than four), REGS (register cap per thread,
 // __maxnreg__), LF (per-lane shared-memory row: candidate codes for the qkx2 searches, w / w*x for Q6K),
 // WM (Q4K / Q5K weights: 2 registers, 1 recomputed), STAGES (input rows in flight).
-template <int WARPS_, int REGS_, int LF_, int WM_, int STAGES_, int AF_ = 0, int RM_ = 0> struct KqCfg {
-    static constexpr int WARPS = WARPS_, THREADS = WARPS_ * 32, REGS = REGS_, LF = LF_, WM = WM_, STAGES = STAGES_, AF = AF_, RM = RM_;
+template <int WARPS_, int REGS_, int LF_, int WM_, int STAGES_, int AF_ = 0, int RM_ = 0, int SD_ = 0> struct KqCfg {
+    static constexpr int WARPS = WARPS_, THREADS = WARPS_ * 32, REGS = REGS_, LF = LF_, WM = WM_, STAGES = STAGES_, AF = AF_, RM = RM_, SD = SD_;
 };
 constexpr int KQ_LROW = 36;  // floats between the lanes' rows: 144 bytes, so eight lanes' 128-bit accesses cover all 32 banks
 

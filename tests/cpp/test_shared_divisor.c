@@ -37,6 +37,20 @@ int main(void) {
             for (int en = 118; en <= 121; en += 3)
                 if (!same_or_tiny(f_from(((uint32_t)en << 23) | m), d, &checked) && bad++ < 10) printf("mismatch m=%x d=%a\n", m, d);
     }
-    printf("%ld quotients checked, %ld mismatches\n", checked, bad);
+    /* strict variant (div_shared_strict: the quotient itself is used): 2^-60 <= |n| <= 2^60, no tolerance at all; the
+     * numerators the searches really form (14 .. 33 in steps of 0.1, both signs) against random divisors, and random pairs */
+    long strict = 0;
+    for (long it = 0; it < 30000000L; it++) {
+        const int ed = 87 + (int)(rnd() % 81);
+        const float d = f_from(((uint32_t)rnd() & 0x807FFFFFu) | ((uint32_t)ed << 23));
+        float n;
+        if (it % 3 == 0) n = (float)(140 + (int)(rnd() % 191)) * 0.1f * ((rnd() & 1) ? 1.f : -1.f);
+        else n = f_from(((uint32_t)rnd() & 0x807FFFFFu) | ((uint32_t)(67 + (int)(rnd() % 121)) << 23));   /* 2^-60 .. 2^60 */
+        const float r = 1.0f / d, q0 = n * r, e = fmaf(-d, q0, n), q = fmaf(e, r, q0), t = n / d;
+        ++strict;
+        if (memcmp(&q, &t, 4) && bad++ < 10) printf("strict mismatch n=%a d=%a\n", n, d);
+    }
+    checked += strict;
+    printf("%ld quotients checked (%ld strict), %ld mismatches\n", checked, strict, bad);
     return bad != 0;
 }
