@@ -5,7 +5,6 @@ for phase in "$@"; do
   case $phase in
     tests)   timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/tests.log; tail -3 gpurun_out/tests.log ;;
     bench)   timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 600 gpurun_out/bench_n1.err; head -c 300 gpurun_out/bench_n1.json; echo ;;
-    bench_split) GGQ_BATCH_SPLIT_BIG=25165824 timeout 600 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu > gpurun_out/bench_n1_split.json 2> gpurun_out/bench_n1_split.err; head -c 300 gpurun_out/bench_n1_split.json; echo ;;
     ref)     timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2>&1 ;;
     pcie)    timeout 300 python tools/pcie_probe.py > gpurun_out/pcie_probe.txt 2>&1 ;;
     sweep)   timeout 900 python tools/codec_sweep.py > gpurun_out/codec_sweep.txt 2>&1; tail -5 gpurun_out/codec_sweep.txt ;;
@@ -23,6 +22,7 @@ for phase in "$@"; do
     dio)     df -h /var/tmp /tmp | cat; timeout 900 python tools/direct_io_probe.py > gpurun_out/dio.log 2>&1; tail -8 gpurun_out/dio.log ;;
     tests_conv) timeout 900 python -m pytest tests/test_convert.py -m gpu -x -q -s 2>&1 | tail -40 | cut -c1-400 ;;
     ncu_q8k) timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_rows_kernel -c 1 -f -o gpurun_out/r02_quant_q8k_f16 python tools/codec_sweep.py 58720256 Q8K:quant > gpurun_out/ncu_q8k.log 2>&1; tail -2 gpurun_out/ncu_q8k.log ;;
+    smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
     box)     bash tools/box_probe.sh > gpurun_out/box_probe.txt 2>&1 ;;
     bench2)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 800 gpurun_out/bench_n2.err; head -c 300 gpurun_out/bench_n2.json; echo ;;
     mixtral2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/mixtral_sweep.py > gpurun_out/mixtral_n2.txt 2>&1; tail -13 gpurun_out/mixtral_n2.txt ;;
