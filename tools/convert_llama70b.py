@@ -121,17 +121,24 @@ def stage_report(st, wall):
 
 
 runs = []
-for _ in range(2):
+for _ in range(int(os.environ.get("GGQ_70B_SINGLE_RUNS", "2"))):
     if os.path.exists(dst):
         os.unlink(dst)
     t = time.time(); st = convert(src, dst, steps, gpus); wall = time.time() - t
     runs.append(stage_report(st, wall))
     print("convert, one output file:", json.dumps(runs[-1]), flush=True)
-t = time.time(); st_sh = convert(src, os.path.join(tmp, "llama70b_sh.gguf"), steps, gpus, max_bytes="4G"); wall = time.time() - t
-sharded = stage_report(st_sh, wall)
-print("convert, -s 4G:", json.dumps(sharded), flush=True)
-for f_ in glob.glob(os.path.join(tmp, "llama70b_sh-*.gguf")):
-    os.unlink(f_)
+sharded_runs = {}
+for size in os.environ.get("GGQ_70B_SHARDS", "4G").split(","):
+    t = time.time(); st_sh = convert(src, os.path.join(tmp, "llama70b_sh.gguf"), steps, gpus, max_bytes=size); wall = time.time() - t
+    sharded_runs[size] = stage_report(st_sh, wall)
+    print(f"convert, -s {size}:", json.dumps(sharded_runs[size]), flush=True)
+    if not runs and size == os.environ.get("GGQ_70B_SHARDS", "4G").split(",")[-1]:
+        # keep the last sharded output for the parity check when no single-file run was made
+        keep = sorted(glob.glob(os.path.join(tmp, "llama70b_sh-*.gguf")))
+    else:
+        for f_ in glob.glob(os.path.join(tmp, "llama70b_sh-*.gguf")):
+            os.unlink(f_)
+sharded = sharded_runs[min(sharded_runs, key=lambda k: sharded_runs[k]["wall_seconds"])]
 one_gpu = None
 if ndev > 1 and os.environ.get("GGQ_70B_ALSO_1GPU", "1") == "1":
     t = time.time(); st1 = convert(src, os.path.join(tmp, "llama70b_1.gguf"), steps, 1, max_bytes="4G"); wall = time.time() - t
@@ -142,8 +149,16 @@ if ndev > 1 and os.environ.get("GGQ_70B_ALSO_1GPU", "1") == "1":
 
 # ---- parity: a strided sample of super-blocks of every cast tensor re-quantised by the oracle ----
 threads = os.cpu_count() or 1
-out_t, _, out_mm = index_gguf(dst)
-out_size = os.path.getsize(dst)
+if runs:
+    shard_index = [index_gguf(dst)]
+    out_size = os.path.getsize(dst)
+else:
+    shard_index = [index_gguf(f_) for f_ in keep]
+    out_size = sum(os.path.getsize(f_) for f_ in keep)
+where = {}
+for ti, (tt, _, mm) in enumerate(shard_index):
+    for name_ in tt:
+        where[name_] = ti
 bad = sampled = 0
 for name, shape in shapes:
     if len(shape) == 1:
@@ -154,6 +169,7 @@ for name, shape in shapes:
     idx = np.arange(0, nsb, 8009)
     x = pool[pool_off[name]:pool_off[name] + n].view(np.uint16).reshape(-1, 256)[idx].reshape(-1)
     want = O.quantize(ty, O.F16, np.ascontiguousarray(x), threads=threads).reshape(-1, b)
+    out_t, _, out_mm = shard_index[where[name]]
     assert out_t[name][1] == ty
     got = out_mm[out_t[name][2]:out_t[name][2] + out_t[name][3]].reshape(-1, b)[idx]
     bad += int((got != want).any(axis=1).sum()); sampled += len(idx)
@@ -163,11 +179,11 @@ t = time.time(); O.quantize(13, O.F16, xb, threads=threads); t5 = time.time() - 
 t = time.time(); O.quantize(14, O.F16, xb, threads=threads); t6 = time.time() - t
 n_q6 = 2 * H * VOCAB
 cpu_seconds = (n_lin - n_q6) / (xb.size / t5) + n_q6 / (xb.size / t6)
-best = min(runs, key=lambda r: r["wall_seconds"])
+best = min(runs + list(sharded_runs.values()), key=lambda r: r["wall_seconds"])
 res = {"config": f"Llama-3-70B-shaped synthetic F16 ({layers} of 80 layers) -> Q5_K (linear) / Q6_K (embd) whole-file convert across {ndev} B200 (BASELINE configs[4])",
        "layers": layers, "layers_requested": want_layers, "ram_disk_free_GB_at_start": free / 1e9, "tensors": len(shapes), "linear_elements": n_lin,
        "file_in_GB": os.path.getsize(src) / 1e9, "file_out_GB": out_size / 1e9, "generate_seconds": t_gen,
-       "seconds_per_file": best["wall_seconds"], "runs_one_output_file": runs, "run_sharded_4G": sharded, "run_one_gpu_sharded_4G": one_gpu,
+       "seconds_per_file": best["wall_seconds"], "runs_one_output_file": runs, "runs_sharded": sharded_runs, "run_one_gpu_sharded_4G": one_gpu,
        "speedup_N_gpus_vs_1_sharded": (one_gpu["wall_seconds"] / sharded["wall_seconds"]) if one_gpu else None,
        "sampled_super_blocks": sampled, "mismatching_super_blocks": bad,
        "cpu_baseline": {"kind": "port", "threads": threads, "q5k_Melem_per_s": xb.size / t5 / 1e6, "q6k_Melem_per_s": xb.size / t6 / 1e6,
@@ -179,5 +195,7 @@ res = {"config": f"Llama-3-70B-shaped synthetic F16 ({layers} of 80 layers) -> Q
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"convert_llama70b_{ndev}gpu.json"), "w"), indent=1)
 print(json.dumps(res))
-os.unlink(src); os.unlink(dst)
+os.unlink(src)
+for f_ in ([dst] if runs else keep):
+    os.unlink(f_)
 assert bad == 0

@@ -14,6 +14,8 @@ for phase in "$@"; do
     ncu_batch) timeout 900 ncu --set full --import-source on --clock-control none -k regex:dequant_batch -c 1 -f -o gpurun_out/r02_dequant_batch python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_batch.log 2>&1; tail -2 gpurun_out/ncu_batch.log ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launches.log 2>&1; tail -2 gpurun_out/ncu_launches.log; wc -l gpurun_out/r02_bench_launches.csv ;;
     c70_small) timeout 900 python tools/convert_llama70b.py 4 0 > gpurun_out/c70_small.log 2>&1; tail -4 gpurun_out/c70_small.log | cut -c1-1500 ;;
+    c70_small2) GGQ_70B_SINGLE_RUNS=0 GGQ_70B_SHARDS=4G,1G GGQ_70B_ALSO_1GPU=0 timeout 900 python tools/convert_llama70b.py 6 0 > gpurun_out/c70_small.log 2>&1; tail -4 gpurun_out/c70_small.log | cut -c1-900 ;;
+    c70_shards) GGQ_70B_SINGLE_RUNS=0 GGQ_70B_SHARDS=4G,2G,1G,512M GGQ_70B_ALSO_1GPU=0 timeout 1500 python tools/convert_llama70b.py 80 0 > gpurun_out/c70_shards.log 2>&1; grep "convert, -s" gpurun_out/c70_shards.log | cut -c1-400; tail -1 gpurun_out/c70_shards.log | cut -c1-600 ;;
     c70)     timeout 1700 python tools/convert_llama70b.py 80 0 > gpurun_out/c70.log 2>&1; tail -3 gpurun_out/c70.log | cut -c1-3000 ;;
     bench8)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err; tail -c 600 gpurun_out/bench_n8.err; head -c 400 gpurun_out/bench_n8.json; echo ;;
     bench4)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/bench_n4.json 2> gpurun_out/bench_n4.err; tail -c 600 gpurun_out/bench_n4.err; head -c 400 gpurun_out/bench_n4.json; echo ;;
@@ -23,6 +25,7 @@ for phase in "$@"; do
     tests_conv) timeout 900 python -m pytest tests/test_convert.py -m gpu -x -q -s 2>&1 | tail -40 | cut -c1-400 ;;
     ncu_q8k) timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_rows_kernel -c 1 -f -o gpurun_out/r02_quant_q8k_f16 python tools/codec_sweep.py 58720256 Q8K:quant > gpurun_out/ncu_q8k.log 2>&1; tail -2 gpurun_out/ncu_q8k.log ;;
     smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
+    dq6)     timeout 600 tools/dq_sweep 40 58720256 > gpurun_out/dq_sweep_mode3_exact.txt 2>&1; grep -E "Q4K|Q5K|Q3K|Q2K|Q4_K|Q5_K" gpurun_out/dq_sweep_mode3_exact.txt | head -60 ;;
     box)     bash tools/box_probe.sh > gpurun_out/box_probe.txt 2>&1 ;;
     bench2)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 800 gpurun_out/bench_n2.err; head -c 300 gpurun_out/bench_n2.json; echo ;;
     mixtral2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/mixtral_sweep.py > gpurun_out/mixtral_n2.txt 2>&1; tail -13 gpurun_out/mixtral_n2.txt ;;
