@@ -26,6 +26,7 @@ for phase in "$@"; do
     ncu_q8k) timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_rows_kernel -c 1 -f -o gpurun_out/r02_quant_q8k_f16 python tools/codec_sweep.py 58720256 Q8K:quant > gpurun_out/ncu_q8k.log 2>&1; tail -2 gpurun_out/ncu_q8k.log ;;
     smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
     dq6)     timeout 600 tools/dq_sweep 40 58720256 > gpurun_out/dq_sweep_mode3_exact.txt 2>&1; grep -E "Q4K|Q5K|Q3K|Q2K|Q4_K|Q5_K" gpurun_out/dq_sweep_mode3_exact.txt | head -60 ;;
+    small)   timeout 600 python tools/sanitize_small.py 2>&1 | tail -3 ;;
     box)     bash tools/box_probe.sh > gpurun_out/box_probe.txt 2>&1 ;;
     bench2)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 800 gpurun_out/bench_n2.err; head -c 300 gpurun_out/bench_n2.json; echo ;;
     mixtral2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/mixtral_sweep.py > gpurun_out/mixtral_n2.txt 2>&1; tail -13 gpurun_out/mixtral_n2.txt ;;

@@ -34,6 +34,19 @@ for s_, d_ in [(g.F32, g.F16), (g.F16, g.F32), (g.BF16, g.F16), (g.F32, g.BF16)]
     out = g.quantize(d_, x, s_) if d_ != g.F32 else g.dequantize(s_, x.view(np.uint8), g.F32)
     want = O.quantize(d_, s_, x) if d_ != g.F32 else O.dequantize(s_, g.F32, x.view(np.uint8))
     bad += not np.array_equal(out.view(np.uint8), want.view(np.uint8))
+# the batched descriptor-table grid with wild scale fields (exact pass for NaN / inf scales) and a ragged last tile per job
+from data import random_packed
+jobs, want, keep = [], [], []
+for ty in [g.Q4_0, g.Q4_1, g.Q5_0, g.Q5_1, g.Q8_0, g.Q8_1, g.Q8K, g.Q2K, g.Q3K, g.Q4K, g.Q5K, g.Q6K]:
+    e, b = g.block_info(ty)
+    nb = 16384 // e + 5
+    blocks = random_packed(ty, nb, b, 40 + ty, wild=True)
+    dq, dy = torch.from_numpy(blocks).cuda(), torch.zeros(nb * e, dtype=torch.float16, device="cuda")
+    jobs.append(("dequantize", ty, g.F16, dy, nb * e, dq, nb)); keep.append((dq, dy)); want.append(O.dequantize(ty, O.F16, blocks))
+g.slices_device(jobs, st)
+torch.cuda.synchronize()
+for (_, dy), w in zip(keep, want):
+    bad += not same_floats(dy.cpu().numpy().view(np.uint16), w)
 x = to_fdt(gaussian(32 * 70000, 9), g.F16)                                           # host pipeline, pageable
 bad += not np.array_equal(g.quantize(g.Q8_0, x, g.F16), O.quantize(g.Q8_0, g.F16, x))
 print("sanitize_small:", "OK" if not bad else f"{bad} MISMATCHES")
