@@ -14,6 +14,8 @@
 //     store covers full 32-byte sectors of the output (which is 64-88 % of all traffic).
 // Every multiply in every decoder is exact in f32, so `fma(q, d, m)` equals the
 // reference's separate mul + add bit for bit; the only roundings are the final add and the narrow.
+#include <cstdlib>
+
 #include "dequant_kernel.cuh"
 #include "ggq_kernels.h"
 
@@ -118,9 +120,10 @@ struct DqBatch {
     int n;
 };
 
-template <uint32_t T, class FT, int TILE_ELEMS, int THREADS>
-__device__ __forceinline__ void dequant_one_tile(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ dst, size_t nblocks, size_t t,
-                                                 uint64_t *bar, uint8_t *stage) {
+// NT consecutive tiles of one job per CTA, all bulk copies requested up front (the MANY shape above; NT = 1 is ONE)
+template <uint32_t T, class FT, int TILE_ELEMS, int THREADS, int NT>
+__device__ __forceinline__ void dequant_tiles(const uint8_t *__restrict__ src, typename FT::raw *__restrict__ dst, size_t nblocks, size_t t0,
+                                              uint64_t *bars, uint8_t *stages, int stage_bytes) {
     using TR = BlockTraits<T>;
     constexpr int TILE_BLOCKS = TILE_ELEMS / TR::ELEMS;
     constexpr int TILE_BYTES = TILE_BLOCKS * TR::BYTES;
@@ -128,55 +131,68 @@ __device__ __forceinline__ void dequant_one_tile(const uint8_t *__restrict__ src
     static_assert(TILE_BYTES % 16 == 0, "tile must be a whole number of 16-byte chunks");
     const int tid = threadIdx.x;
     const size_t full_tiles = nblocks / TILE_BLOCKS;
+    const size_t ntiles = full_tiles + (nblocks % TILE_BLOCKS ? 1 : 0);
     const bool vec = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
-    const bool bulk = t < full_tiles && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-    const int nb = t < full_tiles ? TILE_BLOCKS : (int)(nblocks % TILE_BLOCKS);
-    if (bulk) {
-        if (tid == 0) {
-            mbar_expect_tx(bar, TILE_BYTES);
-            bulk_g2s(stage, src + t * (size_t)TILE_BYTES, TILE_BYTES, bar);
+    const bool src_fast = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            if (t0 + i < full_tiles && src_fast) {
+                mbar_expect_tx(&bars[i], TILE_BYTES);
+                bulk_g2s(stages + (size_t)i * stage_bytes, src + (t0 + i) * (size_t)TILE_BYTES, TILE_BYTES, &bars[i]);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < NT; i++) {
+        const size_t t = t0 + i;
+        if (t >= ntiles) break;
+        uint8_t *stage = stages + (size_t)i * stage_bytes;
+        const int nb = t < full_tiles ? TILE_BLOCKS : (int)(nblocks % TILE_BLOCKS);
+        if (t < full_tiles && src_fast) {
+            mbar_wait(&bars[i], 0);
+        } else {
+            cta_copy_g2s(stage, src + t * (size_t)TILE_BYTES, (uint32_t)nb * TR::BYTES, tid, THREADS);
+            __syncthreads();
         }
-        mbar_wait(bar, 0);
-    } else {
-        cta_copy_g2s(stage, src + t * (size_t)TILE_BYTES, (uint32_t)nb * TR::BYTES, tid, THREADS);
-        __syncthreads();
-    }
-    typename FT::raw *out = dst + t * (size_t)TILE_ELEMS;
-    bool bad = false;  // see dequant_kernel
-    if (nb == TILE_BLOCKS) {
+        typename FT::raw *out = dst + t * (size_t)TILE_ELEMS;
+        bool bad = false;  // see dequant_kernel
+        if (nb == TILE_BLOCKS) {
 #pragma unroll 2
-        for (int u = tid; u < TILE_BLOCKS * UNITS; u += THREADS)
-            bad |= Decoder<T>::template run<FT, 0>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
-    } else {
-        for (int u = tid; u < nb * UNITS; u += THREADS)
-            bad |= Decoder<T>::template run<FT, 0>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
-    }
+            for (int u = tid; u < TILE_BLOCKS * UNITS; u += THREADS)
+                bad |= Decoder<T>::template run<FT, 0>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
+        } else {
+            for (int u = tid; u < nb * UNITS; u += THREADS)
+                bad |= Decoder<T>::template run<FT, 0>(stage + (u / UNITS) * TR::BYTES, u % UNITS, out + (size_t)(u / UNITS) * TR::ELEMS, vec);
+        }
 #ifndef GGQ_AB_NO_EXACT_PASS
-    if (bad) fix_units_exact<T, FT, THREADS>(stage, out, nb * UNITS, tid);
+        if (bad) fix_units_exact<T, FT, THREADS>(stage, out, nb * UNITS, tid);
 #endif
+    }
 }
 
-template <class FT, int TILE_ELEMS, int THREADS, int MINB>
+template <class FT, int TILE_ELEMS, int THREADS, int MINB, int NT>
 __global__ void __launch_bounds__(THREADS, MINB) dequant_batch_kernel(const __grid_constant__ DqBatch batch) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    uint8_t *stage = smem + 128;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *stages = smem + 128;
+    constexpr int STAGE_BYTES = (TILE_ELEMS / 256 * 290 + 15) & ~15;  // the widest tile: Q8K
     if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
+#pragma unroll
+        for (int i = 0; i < NT; i++) mbar_init(&bars[i], 1);
         fence_barrier_init();
     }
     pdl_launch_dependents();
     __syncthreads();
     pdl_wait();
-    int j = 0;  // the job this CTA's tile belongs to (CTA-uniform)
+    int j = 0;  // the job this CTA's tiles belong to (CTA-uniform)
 #pragma unroll
     for (int k = 1; k < DQ_BATCH_MAX; k++)
         if (k < batch.n && blockIdx.x >= batch.job[k].tile0) j = k;
     const DqBatchJob &jb = batch.job[j];
-    const size_t t = blockIdx.x - jb.tile0;
+    const size_t t0 = (size_t)(blockIdx.x - jb.tile0) * NT;
     typename FT::raw *dst = static_cast<typename FT::raw *>(jb.dst);
 #define GGQ_DQ_CASE(T) \
-    case T: dequant_one_tile<T, FT, TILE_ELEMS, THREADS>(jb.src, dst, (size_t)jb.nblocks, t, bar, stage); break;
+    case T: dequant_tiles<T, FT, TILE_ELEMS, THREADS, NT>(jb.src, dst, (size_t)jb.nblocks, t0, bars, stages, STAGE_BYTES); break;
     switch (jb.type) {
         GGQ_DQ_CASE(T_Q4_0) GGQ_DQ_CASE(T_Q4_1) GGQ_DQ_CASE(T_Q5_0) GGQ_DQ_CASE(T_Q5_1) GGQ_DQ_CASE(T_Q8_0) GGQ_DQ_CASE(T_Q8_1)
         GGQ_DQ_CASE(T_Q2K) GGQ_DQ_CASE(T_Q3K) GGQ_DQ_CASE(T_Q4K) GGQ_DQ_CASE(T_Q5K) GGQ_DQ_CASE(T_Q6K) GGQ_DQ_CASE(T_Q8K)
@@ -193,11 +209,10 @@ static int block_bytes_of(uint32_t t) {
     return 0;
 }
 
-template <class FT, int TILE>
+template <class FT, int TILE, int THREADS, int MINB, int NT>
 static cudaError_t launch_dequant_batch(const DequantJob *jobs, size_t n, cudaStream_t stream, DevInfo dev, uint64_t *launches) {
-    constexpr int THREADS = 128, MINB = 8;
-    constexpr int SMEM = 128 + TILE / 256 * 290 + 16;  // the widest tile: Q8K
-    auto kern = dequant_batch_kernel<FT, TILE, THREADS, MINB>;
+    constexpr int SMEM = 128 + NT * ((TILE / 256 * 290 + 15) & ~15) + 16;
+    auto kern = dequant_batch_kernel<FT, TILE, THREADS, MINB, NT>;
     static std::atomic<int> occ_cache[MAX_DEVICES];
     int ctas_per_sm = 0;
     cudaError_t e = cached_occupancy(kern, THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);  // also raises the smem limit
@@ -205,21 +220,21 @@ static cudaError_t launch_dequant_batch(const DequantJob *jobs, size_t n, cudaSt
     size_t i = 0;
     while (i < n) {
         DqBatch b{};
-        unsigned long long tiles = 0;
+        unsigned long long ctas = 0;
         for (; i < n && b.n < DQ_BATCH_MAX; i++) {
             if (jobs[i].nblocks == 0) continue;
             if (!block_bytes_of(jobs[i].type)) return cudaErrorInvalidValue;
             const unsigned long long tb = TILE / block_elems_of(jobs[i].type);
-            const unsigned long long nt = (jobs[i].nblocks + tb - 1) / tb;
-            if (tiles + nt > 0x7FFFFFFFull) {  // grid.x limit: close this batch (a single job beyond it is split by the caller)
+            const unsigned long long nt = ((jobs[i].nblocks + tb - 1) / tb + NT - 1) / NT;  // CTAs of this job
+            if (ctas + nt > 0x7FFFFFFFull) {  // grid.x limit: close this batch (a single job beyond it is split by the caller)
                 if (b.n == 0) return cudaErrorInvalidValue;
                 break;
             }
-            b.job[b.n++] = {static_cast<const uint8_t *>(jobs[i].src), jobs[i].dst, (unsigned long long)jobs[i].nblocks, (unsigned int)tiles, jobs[i].type};
-            tiles += nt;
+            b.job[b.n++] = {static_cast<const uint8_t *>(jobs[i].src), jobs[i].dst, (unsigned long long)jobs[i].nblocks, (unsigned int)ctas, jobs[i].type};
+            ctas += nt;
         }
         if (b.n == 0) continue;
-        e = launch_pdl(kern, (unsigned)tiles, THREADS, SMEM, stream, b);
+        e = launch_pdl(kern, (unsigned)ctas, THREADS, SMEM, stream, b);
         if (e != cudaSuccess) return e;
         if (launches) ++*launches;
     }
@@ -228,9 +243,25 @@ static cudaError_t launch_dequant_batch(const DequantJob *jobs, size_t n, cudaSt
 
 cudaError_t dequant_blocks_batch(uint32_t fdt, const DequantJob *jobs, size_t n, cudaStream_t stream, DevInfo dev, uint64_t *launches) {
     switch (fdt) {
-        case T_F32: return launch_dequant_batch<F32, 8192>(jobs, n, stream, dev, launches);
-        case T_F16: return launch_dequant_batch<F16, 16384>(jobs, n, stream, dev, launches);
-        case T_BF16: return launch_dequant_batch<BF16, 16384>(jobs, n, stream, dev, launches);
+        case T_F32: return launch_dequant_batch<F32, 8192, 128, 8, 1>(jobs, n, stream, dev, launches);
+#ifdef GGQ_BATCH_EXPERIMENT  /* tools/gpu_round.sh batch_cfg: other launch shapes of the same kernel, f16 only */
+        case T_F16: {
+            static const int cfg = getenv("GGQ_BATCH_CFG") ? atoi(getenv("GGQ_BATCH_CFG")) : 0;
+            switch (cfg) {
+                case 1: return launch_dequant_batch<F16, 8192, 128, 8, 1>(jobs, n, stream, dev, launches);
+                case 2: return launch_dequant_batch<F16, 8192, 128, 8, 2>(jobs, n, stream, dev, launches);
+                case 3: return launch_dequant_batch<F16, 8192, 128, 10, 2>(jobs, n, stream, dev, launches);
+                case 4: return launch_dequant_batch<F16, 4096, 128, 8, 4>(jobs, n, stream, dev, launches);
+                case 5: return launch_dequant_batch<F16, 16384, 256, 4, 1>(jobs, n, stream, dev, launches);
+                case 6: return launch_dequant_batch<F16, 16384, 128, 6, 2>(jobs, n, stream, dev, launches);
+                case 7: return launch_dequant_batch<F16, 32768, 256, 3, 1>(jobs, n, stream, dev, launches);
+                default: return launch_dequant_batch<F16, 16384, 128, 8, 1>(jobs, n, stream, dev, launches);
+            }
+        }
+#else
+        case T_F16: return launch_dequant_batch<F16, 16384, 128, 8, 1>(jobs, n, stream, dev, launches);
+#endif
+        case T_BF16: return launch_dequant_batch<BF16, 16384, 128, 8, 1>(jobs, n, stream, dev, launches);
     }
     return cudaErrorInvalidValue;
 }

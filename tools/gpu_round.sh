@@ -27,6 +27,7 @@ for phase in "$@"; do
     smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
     dq6)     timeout 600 tools/dq_sweep 40 58720256 > gpurun_out/dq_sweep_mode3_exact.txt 2>&1; grep -E "Q4K|Q5K|Q3K|Q2K|Q4_K|Q5_K" gpurun_out/dq_sweep_mode3_exact.txt | head -60 ;;
     small)   timeout 600 python tools/sanitize_small.py 2>&1 | tail -3 ;;
+    batch_cfg) for r in 1 2; do for c in 0 1 2 3 4 5 6 7; do GGQ_SO=$PWD/gguf_b200/libggq_ab_batch.so GGQ_BATCH_CFG=$c timeout 300 python bench.py --steps 40 --warmup 5 --no-e2e --no-cpu 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('cfg', $c, 'value %.1f GB/s  %.2f us/step' % (d['value'], d['ms_per_step']*1e3))"; done; done ;;
     box)     bash tools/box_probe.sh > gpurun_out/box_probe.txt 2>&1 ;;
     bench2)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 800 gpurun_out/bench_n2.err; head -c 300 gpurun_out/bench_n2.json; echo ;;
     mixtral2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/mixtral_sweep.py > gpurun_out/mixtral_n2.txt 2>&1; tail -13 gpurun_out/mixtral_n2.txt ;;
