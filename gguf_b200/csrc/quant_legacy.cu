@@ -9,16 +9,17 @@
 // instructions per element on shuffles / redundant divides and was issue-bound at 38 % of HBM peak):
 //   * ONE THREAD PER 32-ELEMENT ROW (a legacy block, or 1/8 of a Q8K super-block): the folds of
 //     structs.rs:91-107 are register-local, delta/recip cost two divides per 32 elements;
-//   * rows are staged global -> shared with 16-byte cp.async (coalesced, no registers), into rows
-//     padded by 16 bytes so that every thread's LDS.128 of its own row is bank-conflict free;
+//   * rows are staged global -> shared with 16-byte cp.async (coalesced, no registers): 128-byte f32 rows padded by
+//     16 bytes, 64-byte f16 / bf16 rows unpadded with their 16-byte chunks permuted (Stage::SWZ), Q8K super-blocks
+//     contiguous — in every layout both the cp.async writes of a quarter warp and each thread's LDS.128 of its own row
+//     are bank-conflict free;
 //   * f16 input folds with packed HMNMX2; codes are produced with full-rate float ops (clamp, then a
 //     round-toward-zero add of 2^23 leaves floor(v) in the mantissa) instead of F2I on the XU pipe;
-//   * launch shape (launch_quant): short-lived CTAs that request their tile(s) up front — one 128-row tile
-//     from f32 input, two 64-row tiles from 16-bit input (rows are half as long there, and the bytes in
-//     flight per SM, not the instruction count, bounded the encoders) — encode and write the packed blocks
-//     with cooperative 16-byte stores (quant_rows_oneshot); Q8K keeps the persistent ring
-//     (quant_rows_kernel: 2 cp.async stages, packed tile leaves as ONE 1-D bulk async store,
-//     `cp.async.bulk.global.shared::cta`, SASS UBLKCP, double buffered).
+//   * launch shape (launch_quant, quant_rows_oneshot): short-lived CTAs that request their tile(s) up front — one
+//     128-row tile from f32 input, two 64-row tiles from 16-bit input (rows are half as long there, and the bytes in
+//     flight per SM, not the instruction count, bound the encoders) — encode tile k while tile k+1 arrives, stage the
+//     packed tiles in shared memory (tiles 1.. on top of input stages already consumed) and write them with cooperative
+//     16-byte stores, or, for Q8K, as ONE 1-D bulk async store (`cp.async.bulk.global.shared::cta`, SASS UBLKCP).
 #include <cstdlib>
 #include <type_traits>
 
@@ -39,7 +40,7 @@ template <> struct Row<F32> {
 #pragma unroll
         for (int k = 0; k < 32; k++) x[k] = 0.0f;
     }
-    __device__ __forceinline__ void load(const uint8_t *s) {
+    __device__ __forceinline__ void load(const uint8_t *s, uint32_t = 0) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const float4 v = *reinterpret_cast<const float4 *>(s + 16 * i);
@@ -56,10 +57,10 @@ template <> struct Row<BF16> {
 #pragma unroll
         for (int k = 0; k < 16; k++) raw[k] = 0u;
     }
-    __device__ __forceinline__ void load(const uint8_t *s) {
+    __device__ __forceinline__ void load(const uint8_t *s, uint32_t xm = 0) {  // xm: Stage::xmask of this row
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(s + 16 * i);
+            const uint4 v = *reinterpret_cast<const uint4 *>(s + ((16 * i) ^ xm));
             raw[4 * i] = v.x; raw[4 * i + 1] = v.y; raw[4 * i + 2] = v.z; raw[4 * i + 3] = v.w;
         }
 #pragma unroll
@@ -78,10 +79,10 @@ template <> struct Row<F16> {
 #pragma unroll
         for (int k = 0; k < 16; k++) raw[k] = 0u;
     }
-    __device__ __forceinline__ void load(const uint8_t *s) {
+    __device__ __forceinline__ void load(const uint8_t *s, uint32_t xm = 0) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(s + 16 * i);
+            const uint4 v = *reinterpret_cast<const uint4 *>(s + ((16 * i) ^ xm));
             raw[4 * i] = v.x; raw[4 * i + 1] = v.y; raw[4 * i + 2] = v.z; raw[4 * i + 3] = v.w;
         }
 #pragma unroll
@@ -97,13 +98,20 @@ template <> struct Row<F16> {
 // thread's LDS.128 of its own row is bank-conflict free.  Q8K (eight lanes per 256-element super-block, see
 // Encoder<T_Q8K>): the eight rows of a super-block stay contiguous and each SUPER-BLOCK is padded by 64 bytes (its
 // stride is 16 words mod 32), because there the eight lanes of a group read consecutive 8- / 16-byte pieces.
-template <uint32_t T, class FT> struct Stage {
+template <uint32_t T, class FT, bool ALLOW_SWZ = false> struct Stage {
     static constexpr bool SB = (T == T_Q8K);
+    // 64-byte rows (16-bit input) of the short-lived CTAs are stored UNPADDED with their four 16-byte chunks permuted:
+    // chunk c of row r sits at chunk c ^ ((r >> 1) & 3).  A quarter warp's LDS.128 (eight consecutive rows, the same
+    // logical chunk) then touches eight different 16-byte bank groups, like the padded layout, in 4/5 of the space —
+    // which is what bounds how many of these CTAs an SM holds (see launch_quant).
+    static constexpr bool SWZ = ALLOW_SWZ && !SB && FT::SIZE == 2;
     static constexpr int ROW_BYTES = 32 * FT::SIZE;
-    static constexpr int ROW_STRIDE = SB ? ROW_BYTES : ROW_BYTES + 16;
+    static constexpr int ROW_STRIDE = (SB || SWZ) ? ROW_BYTES : ROW_BYTES + 16;
     static constexpr int SB_PAD = SB ? 64 : 0;
     static __host__ __device__ constexpr int bytes(int rows) { return rows * ROW_STRIDE + rows / 8 * SB_PAD; }
     static __device__ __forceinline__ uint32_t row_off(uint32_t r) { return r * ROW_STRIDE + (r >> 3) * SB_PAD; }
+    // XOR mask for a byte offset inside row r (0 when the layout is not permuted)
+    static __device__ __forceinline__ uint32_t xmask(uint32_t r) { return SWZ ? ((r >> 1) & 3u) << 4 : 0u; }
 };
 
 // Q8K: lane j (0..7) of a group owns the four elements 32k + 4j .. 32k + 4j + 3 of every row k (0..7) of its super-block,
@@ -250,12 +258,17 @@ template <int G, class FT, bool INTERLEAVED = false> __device__ __forceinline__ 
     // tie between +P and -P somewhere in the block: the first |x| == P in index order decides the sign
     const bool tie = (P == a) && (P != 0.0f);
     if (G == 1 ? tie : __any_sync(FULL, tie)) {  // G > 1: every lane of the warp runs the shuffles
+        // one descending pass: the last assignment comes from the lowest matching index (indices ascend with i in both
+        // layouts).  With 16-bit input — bf16 above all, 8 significant bits — a row holding both +max and -max is common
+        // (several per cent of random rows, i.e. most warps), so this path is not a cold one.
         int first = 32 * G;
-#pragma unroll
-        for (int i = 31; i >= 0; i--) first = (fabsf(r.x[i]) == P) ? index_of(i) : first;  // indices ascend with i in both layouts
         float val = 0.0f;
 #pragma unroll
-        for (int i = 31; i >= 0; i--) val = (index_of(i) == first) ? r.x[i] : val;
+        for (int i = 31; i >= 0; i--) {
+            const bool hit = fabsf(r.x[i]) == P;
+            if (G > 1) first = hit ? index_of(i) : first;
+            val = hit ? r.x[i] : val;
+        }
 #pragma unroll
         for (int m = 1; m < G; m <<= 1) {
             const int of = __shfl_xor_sync(FULL, first, m);
@@ -643,124 +656,14 @@ template <> struct Encoder<T_Q8K> {
 };
 
 // ---------------------------------------------------------------------------------------------
-// QL_THREADS = rows per tile (one thread per row); chosen per type in launch_quant
-template <uint32_t T, class FT, int QS, int QL_THREADS, int MINB>
-__global__ void __launch_bounds__(QL_THREADS, MINB)
-quant_rows_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t nblocks) {
-    using TR = BlockTraits<T>;
-    using E = Encoder<T>;
-    constexpr int RPB = TR::ELEMS / 32;                 // rows per block (1, or 8 for Q8K)
-    constexpr int TILE_BLOCKS = QL_THREADS / RPB;
-    using ST = Stage<T, FT>;
-    constexpr int ROW_BYTES = 32 * FT::SIZE, CPR = ROW_BYTES / 16;
-    constexpr int IN_STAGE = ST::bytes(QL_THREADS);
-    constexpr int OUT_STAGE = (TILE_BLOCKS * TR::BYTES + 15) & ~15;
-    static_assert((TILE_BLOCKS * TR::BYTES) % 16 == 0, "tile must be a whole number of 16-byte chunks");
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *in_st = smem;
-    uint8_t *out_st = smem + QS * IN_STAGE;
-
-    const int tid = threadIdx.x;
-    const size_t nrows = nblocks * RPB;
-    const size_t ntiles = (nrows + QL_THREADS - 1) / QL_THREADS;
-    const bool vec_in = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-    const bool bulk_out = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
-    constexpr size_t TILE_IN = (size_t)QL_THREADS * ROW_BYTES, TILE_OUT = (size_t)TILE_BLOCKS * TR::BYTES;
-    constexpr int ROWS_PER_PASS = QL_THREADS / CPR;  // chunk k of thread tid lands in row tid/CPR + k*ROWS_PER_PASS
-
-    // ---- producer state: tile i of this CTA goes to stage i % QS (running pointers, no div/mod) ----
-    size_t t_issue = blockIdx.x;
-    const uint8_t *g_issue = src + t_issue * TILE_IN + (size_t)tid * 16;
-    const size_t g_step = (size_t)gridDim.x * TILE_IN;
-    const uint32_t s_chunk0 = ST::row_off((uint32_t)(tid / CPR)) + (uint32_t)(tid % CPR) * 16;
-    constexpr uint32_t PASS_STRIDE = ST::bytes(ROWS_PER_PASS);  // ROWS_PER_PASS is a multiple of 8: whole super-blocks
-    static_assert(ROWS_PER_PASS % 8 == 0, "a pass of chunks covers whole super-blocks");
-    int s_issue = 0;
-    auto issue = [&]() {  // all threads; 16-byte chunks, coalesced
-        if (t_issue < ntiles) {
-            uint8_t *st = in_st + s_issue * IN_STAGE;
-            const size_t rem = nrows - t_issue * QL_THREADS;
-            if (vec_in) {
-                if (rem >= (size_t)QL_THREADS) {
-#pragma unroll
-                    for (int k = 0; k < CPR; k++) cp_async16(st + s_chunk0 + k * PASS_STRIDE, g_issue + (size_t)k * QL_THREADS * 16);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < CPR; k++)
-                        if ((size_t)(tid / CPR + k * ROWS_PER_PASS) < rem)
-                            cp_async16(st + s_chunk0 + k * PASS_STRIDE, g_issue + (size_t)k * QL_THREADS * 16);
-                }
-            } else {  // source not 16-byte aligned: element-granular synchronous staging
-                using RAW = typename FT::raw;
-                const RAW *ge = reinterpret_cast<const RAW *>(g_issue - (size_t)tid * 16);
-                const int rows = (int)min((size_t)QL_THREADS, rem);
-                for (int e = tid; e < rows * 32; e += QL_THREADS)
-                    *reinterpret_cast<RAW *>(st + ST::row_off(e / 32) + (e % 32) * FT::SIZE) = ge[e];
-            }
-        }
-        cp_async_commit();
-        t_issue += gridDim.x;
-        g_issue += g_step;
-        s_issue = (s_issue + 1 == QS) ? 0 : s_issue + 1;
-    };
-    pdl_launch_dependents();
-    pdl_wait();  // previous kernel in the stream complete before the first global access
-#pragma unroll
-    for (int i = 0; i < QS; i++) issue();
-    cp_async_wait<QS - 1>();
-    __syncthreads();
-
-    // ---- consumer state ----
-    // legacy: this thread's row; Q8K: the first row of this thread's super-block (its lane reads pieces of all eight)
-    const uint8_t *my_row = in_st + ST::row_off(ST::SB ? (uint32_t)(tid & ~7) : (uint32_t)tid);
-    const int my_j = tid % RPB;
-    const uint32_t my_out = (uint32_t)(tid / RPB) * TR::BYTES;
-    uint8_t *o_ptr = dst + (size_t)blockIdx.x * TILE_OUT;
-    const size_t o_step = (size_t)gridDim.x * TILE_OUT;
-    int s_cons = 0, o_cons = 0;
-    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const size_t rem = nrows - t * QL_THREADS;
-        const int rows = (int)min((size_t)QL_THREADS, rem);
-        uint8_t *ost = out_st + o_cons * OUT_STAGE;
-        // out_st[o_cons] was handed to the bulk store two iterations ago; thread 0 confirmed that store
-        // had finished READING shared memory before the barrier of the previous iteration.
-        if (RPB > 1 || tid < rows) {  // G > 1 encoders shuffle: every lane of the warp takes part
-            Row<FT> r;
-            if constexpr (ST::SB) {  // rows come in whole super-blocks: all eight lanes of a group are live or none is
-                if (tid < rows) load_interleaved<FT>(r, my_row + s_cons * IN_STAGE, my_j);
-                else r.zero();
-            } else {
-                if (tid < rows) r.load(my_row + s_cons * IN_STAGE);
-                else r.zero();
-            }
-            E::template run<FT>(r, my_j, ost + my_out);
-        }
-        fence_proxy_async_smem();                  // generic-proxy writes -> async-proxy (bulk store) reads
-        cp_async_wait<(QS >= 2) ? QS - 2 : 0>();   // this thread's copies of the next tile have landed
-        if (tid == 0) bulk_wait_read<0>();         // every earlier bulk store has released its stage
-        __syncthreads();                           // out tile complete, next in tile visible, this in stage free
-        if (bulk_out && rows == QL_THREADS) {
-            if (tid == 0) { bulk_s2g(o_ptr, ost, (uint32_t)TILE_OUT); bulk_commit(); }
-        } else {
-            cta_copy_s2g(o_ptr, ost, (uint32_t)(rows / RPB) * TR::BYTES, tid, QL_THREADS);
-        }
-        issue();
-        o_ptr += o_step;
-        s_cons = (s_cons + 1 == QS) ? 0 : s_cons + 1;
-        o_cons ^= 1;
-    }
-    if (tid == 0) bulk_wait_all<0>();
-}
-
 // Short-lived CTAs: stage K tiles of ROWS rows up front, encode them one after the other, write the packed
 // blocks — no ring, no running pointers.  The overlap of loads, math and stores comes from the hardware
 // scheduling several resident CTAs per SM, the structure that took the cast kernel from 85 % to 98 % of the copy
-// peak; per row it also sheds the bookkeeping of the persistent pipeline above.  K > 1 exists for 16-bit input:
-// a thread's row is then only 64 bytes, and one row per resident thread (registers allow ~1 150 threads per SM)
-// is ~70 KB in flight per SM in the best case — too little to cover HBM latency at full bandwidth, which is why
-// every 16-bit-input encoder stopped at ~31 us per 58.7 M elements whatever its instruction count.  With K
-// tiles requested before the first is encoded the bytes in flight per thread multiply and tile k+1 keeps
-// arriving while tile k is encoded.  launch_quant picks (ROWS, K) per (type, float side).
+// peak; per row it also sheds the bookkeeping of a persistent pipeline (the ring this replaced: 73-92 %).  K > 1
+// exists for 16-bit input: a thread's row is then only 64 bytes, and one row per resident thread (registers allow
+// ~1 000 threads per SM) is ~64 KB in flight per SM in the best case — too little to cover HBM latency at full
+// bandwidth.  With K tiles requested before the first is encoded the bytes in flight per thread multiply and tile
+// k+1 keeps arriving while tile k is encoded.  launch_quant picks (ROWS, K, register cap) per (type, float side).
 template <int N> __device__ __forceinline__ void cp_async_wait_upto(int pending) {  // wait until <= pending groups are outstanding
     if constexpr (N == 0) {
         cp_async_wait<0>();
@@ -775,19 +678,26 @@ quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, s
     using TR = BlockTraits<T>;
     using E = Encoder<T>;
     constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = ROWS / RPB;
-    using ST = Stage<T, FT>;
+    using ST = Stage<T, FT, true>;
     constexpr int ROW_BYTES = 32 * FT::SIZE, CPR = ROW_BYTES / 16, ROWS_PER_PASS = ROWS / CPR;
     constexpr int IN_STAGE = ST::bytes(ROWS), OUT_BYTES = TILE_BLOCKS * TR::BYTES;
     constexpr uint32_t PASS_STRIDE = ST::bytes(ROWS_PER_PASS);
-    static_assert(ROWS_PER_PASS % 8 == 0, "a pass of chunks covers whole super-blocks");
+    static_assert(ROWS_PER_PASS % 8 == 0, "a pass of chunks covers whole super-blocks (and leaves the row permutation unchanged)");
     static_assert(OUT_BYTES % 16 == 0, "tile must be a whole number of 16-byte chunks");
-    __shared__ __align__(128) uint8_t in_st[K * IN_STAGE];
-    __shared__ __align__(16) uint8_t out_st[K * OUT_BYTES];
+    // One buffer: [packed tile 0][input stage 0][input stage 1]...  Packed tile k lives at k * OUT_BYTES, i.e. tiles
+    // 1.. overwrite input stages 0..k-1 — every thread has taken its rows of those stages before anyone passes the
+    // barrier that precedes tile k's encode — so the K packed tiles are contiguous for the final copy and cost the
+    // space of one.  (k + 1) * OUT_BYTES <= IN_OFF + k * IN_STAGE because a packed tile is smaller than its input.
+    constexpr int IN_OFF = (OUT_BYTES + 127) & ~127;
+    static_assert(OUT_BYTES <= IN_STAGE, "packed tiles must fit into consumed input stages");
+    __shared__ __align__(128) uint8_t smem[IN_OFF + K * IN_STAGE];
+    uint8_t *const out_st = smem, *const in_st = smem + IN_OFF;
     const int tid = threadIdx.x;
     const size_t nrows = nblocks * RPB, ntiles = (nrows + ROWS - 1) / ROWS;
     const bool vec_in = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-    const uint32_t s_chunk0 = ST::row_off((uint32_t)(tid / CPR)) + (uint32_t)(tid % CPR) * 16;
+    const uint32_t s_chunk0 = ST::row_off((uint32_t)(tid / CPR)) + (((uint32_t)(tid % CPR) * 16) ^ ST::xmask((uint32_t)(tid / CPR)));
     const uint32_t my_row_off = ST::row_off(ST::SB ? (uint32_t)(tid & ~7) : (uint32_t)tid);
+    const uint32_t my_xm = ST::xmask((uint32_t)tid);
     pdl_launch_dependents();
     pdl_wait();
     const bool vec_out = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
@@ -810,14 +720,31 @@ quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, s
                 __syncthreads();
                 Row<FT> r;
                 if constexpr (ST::SB) load_interleaved<FT>(r, in_st + k * IN_STAGE + my_row_off, tid % RPB);
-                else r.load(in_st + k * IN_STAGE + my_row_off);
+                else r.load(in_st + k * IN_STAGE + my_row_off, my_xm);
                 E::template run<FT>(r, tid % RPB, out_st + k * OUT_BYTES + (uint32_t)(tid / RPB) * TR::BYTES);
             }
-            __syncthreads();
-            constexpr int NV = K * OUT_BYTES / 16;
-            uint4 *gd = reinterpret_cast<uint4 *>(dst + t0 * (size_t)OUT_BYTES);
+            // Q8K (2.3 KB per packed tile): the K tiles leave as ONE bulk async store issued by thread 0
+            // (`cp.async.bulk.global.shared::cta`, SASS UBLKCP) — +3 points over cooperative 16-byte stores; for the
+            // 1.1-2.3 KB tiles of the 32-element types the cooperative stores are 0.3-0.8 points ahead
+            // (profiles/r02_quant_legacy16_sweep.txt)
+#ifndef GGQ_ONESHOT_BULK_OUT
+#define GGQ_ONESHOT_BULK_OUT (T == T_Q8K)
+#endif
+            if constexpr (GGQ_ONESHOT_BULK_OUT) {
+                fence_proxy_async_smem();  // generic-proxy writes -> async-proxy reads
+                __syncthreads();
+                if (tid == 0) {
+                    bulk_s2g(dst + t0 * (size_t)OUT_BYTES, out_st, (uint32_t)(K * OUT_BYTES));
+                    bulk_commit();
+                    bulk_wait_read<0>();  // shared memory must outlive the read
+                }
+            } else {
+                __syncthreads();
+                constexpr int NV = K * OUT_BYTES / 16;
+                uint4 *gd = reinterpret_cast<uint4 *>(dst + t0 * (size_t)OUT_BYTES);
 #pragma unroll
-            for (int i = tid; i < NV; i += ROWS) gd[i] = reinterpret_cast<const uint4 *>(out_st)[i];
+                for (int i = tid; i < NV; i += ROWS) gd[i] = reinterpret_cast<const uint4 *>(out_st)[i];
+            }
             __syncthreads();  // only matters when the loop runs again
             continue;
         }
@@ -839,7 +766,7 @@ quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, s
                     using RAW = typename FT::raw;
                     const RAW *ge = reinterpret_cast<const RAW *>(g);
                     for (int e = tid; e < rows * 32; e += ROWS)
-                        *reinterpret_cast<RAW *>(st + ST::row_off(e / 32) + (e % 32) * FT::SIZE) = ge[e];
+                        *reinterpret_cast<RAW *>(st + ST::row_off(e / 32) + (((uint32_t)(e % 32) * FT::SIZE) ^ ST::xmask(e / 32))) = ge[e];
                 }
             }
             cp_async_commit();  // one group per tile, empty or not
@@ -857,7 +784,7 @@ quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, s
                     Row<FT> r;
                     if (tid >= rows) r.zero();
                     else if constexpr (ST::SB) load_interleaved<FT>(r, in_st + k * IN_STAGE + my_row_off, tid % RPB);
-                    else r.load(in_st + k * IN_STAGE + my_row_off);
+                    else r.load(in_st + k * IN_STAGE + my_row_off, my_xm);
                     E::template run<FT>(r, tid % RPB, out_st + k * OUT_BYTES + (uint32_t)(tid / RPB) * TR::BYTES);
                 }
                 rows_total += rows;
@@ -878,47 +805,42 @@ static cudaError_t launch_quant_oneshot(const void *src, void *dst, size_t nbloc
     return launch_pdl(quant_rows_oneshot<T, FT, ROWS, K, MINB>, (unsigned)grid, ROWS, 0, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
 }
 
-template <uint32_t T, class FT, int QS, int QL_THREADS, int MINB>
-static cudaError_t launch_quant_ring(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
-    using TR = BlockTraits<T>;
-    constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = QL_THREADS / RPB;
-    constexpr int SMEM = QS * Stage<T, FT>::bytes(QL_THREADS) + 2 * ((TILE_BLOCKS * TR::BYTES + 15) & ~15);
-    auto kern = quant_rows_kernel<T, FT, QS, QL_THREADS, MINB>;
-    static std::atomic<int> occ_cache[MAX_DEVICES];
-    int ctas_per_sm = 0;
-    cudaError_t e = cached_occupancy(kern, QL_THREADS, SMEM, dev.device, occ_cache, &ctas_per_sm);
-    if (e != cudaSuccess) return e;
-    const size_t ntiles = (nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
-    size_t grid = (size_t)dev.sm_count * ctas_per_sm;
-    if (grid > ntiles) grid = ntiles;
-    return launch_pdl(kern, (unsigned)grid, QL_THREADS, SMEM, stream, static_cast<const uint8_t *>(src), static_cast<uint8_t *>(dst), nblocks);
-}
-
 template <uint32_t T, class FT>
 static cudaError_t launch_quant(const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev) {
     using TR = BlockTraits<T>;
-    // measured (tools/codec_sweep.py, 58.7 M elements, profiles/r01_quant_oneshot_sweep.txt):
-    //   f32 input: one 128-row tile per CTA runs at 99-101 % of the copy peak (persistent ring: 89-92 %);
-    //   16-bit input: two 64-row tiles per CTA, both requested up front: 83-89 % (ring and one tile per CTA: 73-75 %
-    //   for the 4/5-bit types, 84-87 % for Q8_0 / Q8_1 — bytes in flight, not instructions, were the limit; K = 3,
-    //   96- and 128-row tiles are 1-3 points behind, 32-row tiles 10);
-    //   Q8K: see below.
+    // measured (tools/codec_sweep.py, 58.7 M elements; profiles/r01_quant_oneshot_sweep.txt, r02_quant_legacy16_sweep.txt):
+    //   f32 input: one 128-row tile per CTA runs at 100-102 % of the copy peak (a persistent ring: 89-92 %);
+    //   16-bit input: two 64-row tiles per CTA, both requested up front (K = 3, 96- / 128-row tiles 1-3 points behind,
+    //   32-row tiles 10; one tile per CTA or a ring 10-15).
     constexpr bool ONESHOT_F32 = (T != T_Q8K) && std::is_same<FT, F32>::value;
     constexpr bool ONESHOT_16 = (T != T_Q8K) && !std::is_same<FT, F32>::value;
     if constexpr (ONESHOT_F32) {
         return launch_quant_oneshot<T, FT, 128, 1, 1>(src, dst, nblocks, stream);
     } else if constexpr (ONESHOT_16) {
-        // capping the registers at 56 / 48 (launch bounds 18 / 20 CTAs per SM; no spills) changes nothing: shared memory holds
-        // residency at 17 CTAs and the time tracks the bytes, not the warps (profiles/r02_quant_legacy_minb.txt)
-        return launch_quant_oneshot<T, FT, 64, 2, 1>(src, dst, nblocks, stream);
+        // 64-byte rows unpadded and chunk-permuted (Stage::SWZ), packed tiles aliased onto consumed input stages: 9.3-10.5 KB
+        // per CTA instead of 12.5, and every quarter-warp cp.async lands in 128 contiguous bytes (the 80-byte padded rows made
+        // each of them a two-way bank conflict): 85-90 % -> 93-99.5 % of the measured copy peak.  The register cap is per type
+        // (profiles/r02_quant_legacy16_sweep.txt): none for Q4_0 / Q4_1 / Q8_0 / Q8_1 (70-72 registers, 14 CTAs per SM), 64 /
+        // 56 / 48 where more resident CTAs beat the compiler's freer schedule.
+#ifdef GGQ_QL16_K
+        return launch_quant_oneshot<T, FT, 64, GGQ_QL16_K, GGQ_QL16_MINB>(src, dst, nblocks, stream);
+#else
+        constexpr bool BF = std::is_same<FT, BF16>::value;
+        constexpr int MINB = T == T_Q5_0 ? (BF ? 20 : 16) : T == T_Q5_1 ? 20 : (T == T_Q4_0 && BF) ? 18 : 1;
+        return launch_quant_oneshot<T, FT, 64, 2, MINB>(src, dst, nblocks, stream);
+#endif
     } else {  // Q8K
-        // ring: 2 input stages and 64-row tiles, capped at 72 registers (14 CTAs of 64 threads per SM)
-        // Q8K, eight interleaved lanes per super-block (Encoder<T_Q8K>; profiles/r02_quant_q8k_sweep.txt).  From f32 the
-        // short-lived two-tile CTAs of the legacy types win (102-103 % of the copy peak; ring 99 %); from 16-bit input the
-        // persistent ring does (83 / 77 % for f16 / bf16; one-shot 75 %, 128-row tiles 55-80 %).  Round 1's one-row-per-lane
-        // mapping: 73 / 72 / 90 %.
+        // Eight interleaved lanes per super-block (Encoder<T_Q8K>).  Short-lived two-tile CTAs for every float side: from f32
+        // 102-103 % of the copy peak (a persistent ring: 99 %); from 16-bit input 97-99 % with the registers capped (56, no
+        // spills; left alone the compiler takes 118: 8 CTAs per SM and 74 %), the packed tiles on top of consumed input stages
+        // (11.6 KB per CTA) and the bulk store — the ring that shipped before reached 83 / 77 % for f16 / bf16
+        // (profiles/r02_quant_q8k_sweep.txt, r02_quant_legacy16_sweep.txt).  Round 1's one-row-per-lane mapping: 73 / 72 / 90 %.
         if constexpr (std::is_same<FT, F32>::value) return launch_quant_oneshot<T, FT, 64, 2, 1>(src, dst, nblocks, stream);
-        return launch_quant_ring<T, FT, 2, 64, 14>(src, dst, nblocks, stream, dev);
+#ifdef GGQ_Q8K16_ONESHOT_K
+        return launch_quant_oneshot<T, FT, 64, GGQ_Q8K16_ONESHOT_K, GGQ_Q8K16_MINB>(src, dst, nblocks, stream);
+#else
+        return launch_quant_oneshot<T, FT, 64, 2, 16>(src, dst, nblocks, stream);
+#endif
     }
 }
 

@@ -23,16 +23,20 @@ for phase in "$@"; do
     ncu_kq)  for t in Q4K Q6K Q5K Q2K Q3K; do timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_k_kernel -c 1 -f -o gpurun_out/r02_quant_k_$t python tools/codec_sweep.py 58720256 $t:quant > gpurun_out/ncu_kq_$t.log 2>&1; tail -1 gpurun_out/ncu_kq_$t.log; done ;;
     dio)     df -h /var/tmp /tmp | cat; timeout 900 python tools/direct_io_probe.py > gpurun_out/dio.log 2>&1; tail -8 gpurun_out/dio.log ;;
     tests_conv) timeout 900 python -m pytest tests/test_convert.py -m gpu -x -q -s 2>&1 | tail -40 | cut -c1-400 ;;
-    ncu_q8k) timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_rows_kernel -c 1 -f -o gpurun_out/r02_quant_q8k_f16 python tools/codec_sweep.py 58720256 Q8K:quant > gpurun_out/ncu_q8k.log 2>&1; tail -2 gpurun_out/ncu_q8k.log ;;
+    ncu_q8k) timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_rows_oneshot -c 1 -f -o gpurun_out/r02_quant_q8k_f16 python tools/codec_sweep.py 58720256 Q8K:quant > gpurun_out/ncu_q8k.log 2>&1; tail -2 gpurun_out/ncu_q8k.log ;;
     smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
     dq6)     timeout 600 tools/dq_sweep 40 58720256 > gpurun_out/dq_sweep_mode3_exact.txt 2>&1; grep -E "Q4K|Q5K|Q3K|Q2K|Q4_K|Q5_K" gpurun_out/dq_sweep_mode3_exact.txt | head -60 ;;
     small)   timeout 600 python tools/sanitize_small.py 2>&1 | tail -3 ;;
-    batch_cfg) for r in 1 2; do for c in 0 1 2 3 4 5 6 7; do GGQ_SO=$PWD/gguf_b200/libggq_ab_batch.so GGQ_BATCH_CFG=$c timeout 300 python bench.py --steps 40 --warmup 5 --no-e2e --no-cpu 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('cfg', $c, 'value %.1f GB/s  %.2f us/step' % (d['value'], d['ms_per_step']*1e3))"; done; done ;;
+    absweep) # A/B libraries built by tools/build_ab.sh: AB_VARIANTS="default name1 name2", AB_ONLY=codec_sweep filter, AB_OUT=file
+             timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "quantize or ragged or big_tensor_legacy or kat or fuzz or alignment" 2>&1 | tail -3
+             for r in 1 2; do for v in $AB_VARIANTS; do
+               so=$PWD/gguf_b200/libggq_ab_$v.so; [ $v = default ] && so=$PWD/gguf_b200/libggq.so
+               GGQ_SO=$so timeout 300 python tools/codec_sweep.py 58720256 $AB_ONLY 2>&1 | grep -v " F32 " | sed "s/^/$v /"; done; done > gpurun_out/${AB_OUT:-absweep.txt}
+             cat gpurun_out/${AB_OUT:-absweep.txt} ;;
     box)     bash tools/box_probe.sh > gpurun_out/box_probe.txt 2>&1 ;;
     bench2)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 800 gpurun_out/bench_n2.err; head -c 300 gpurun_out/bench_n2.json; echo ;;
     mixtral2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/mixtral_sweep.py > gpurun_out/mixtral_n2.txt 2>&1; tail -13 gpurun_out/mixtral_n2.txt ;;
     tests_dq) timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "dequantize or slices or kat or nan_rule or alignment or big" 2>&1 | tail -4 ;;
-    ab_exact) for i in 1 2; do GGQ_SO=$PWD/gguf_b200/libggq_ab_noexact.so timeout 600 python tools/codec_sweep.py 58720256 dequant > gpurun_out/ab_noexact_$i.txt 2>&1; timeout 600 python tools/codec_sweep.py 58720256 dequant > gpurun_out/ab_exact_$i.txt 2>&1; done; tail -2 gpurun_out/ab_exact_2.txt ;;
     tests2)  timeout 1500 python -m pytest tests -m gpu -x -q -k "shard or slices or convert" 2>&1 | tail -5 ;;
     *) echo "unknown phase $phase" ;;
   esac
