@@ -32,6 +32,12 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr float F32_MAX = 3.40282347e+38f;
 
 
+// bf16 pair -> two f32: shift / mask (ALU pipe).  Blackwell's mixed-precision FMA (`fma.rn.f32.bf16`, SASS FHFMA.BF16:
+// x * 1 + (-0) widens either half of the register exactly, on the FP32 pipe) was measured as a replacement: bit-identical
+// output, no gain (Q5_0 -0.7 point, Q8K -1.2, Q5_1 +0.4; profiles/r02_quant_bf16_widen_ab.txt) — the ALU pipe is not
+// what holds the bf16 encoders back.
+__device__ __forceinline__ float2 widen_bf16_pair(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)); }
+
 // ---- a row of 32 elements, widened to f32 (lib.rs:66-69, 82-84); `raw` keeps the f16 pairs --------
 template <class FT> struct Row;
 template <> struct Row<F32> {
@@ -65,8 +71,8 @@ template <> struct Row<BF16> {
         }
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            x[2 * k] = __uint_as_float(raw[k] << 16);
-            x[2 * k + 1] = __uint_as_float(raw[k] & 0xFFFF0000u);
+            const float2 f = widen_bf16_pair(raw[k]);
+            x[2 * k] = f.x; x[2 * k + 1] = f.y;
         }
     }
 };
@@ -147,8 +153,8 @@ template <> __device__ __forceinline__ void load_interleaved<BF16>(Row<BF16> &r,
     }
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        r.x[2 * k] = __uint_as_float(r.raw[k] << 16);
-        r.x[2 * k + 1] = __uint_as_float(r.raw[k] & 0xFFFF0000u);
+        const float2 f = widen_bf16_pair(r.raw[k]);
+        r.x[2 * k] = f.x; r.x[2 * k + 1] = f.y;
     }
 }
 
