@@ -100,17 +100,19 @@ template <> struct Row<F16> {
 };
 
 // ---- staging layout --------------------------------------------------------------------------------------------------
-// 32-element rows of a tile in shared memory.  Legacy blocks (one thread per row): rows padded by 16 bytes, so every
-// thread's LDS.128 of its own row is bank-conflict free.  Q8K (eight lanes per 256-element super-block, see
+// 32-element rows of a tile in shared memory.  Legacy blocks (one thread per row): 128-byte f32 rows padded by 16 bytes,
+// 64-byte f16 / bf16 rows unpadded and chunk-permuted (SWZ below) — either way every thread's LDS.128 of its own row and
+// every quarter warp's cp.async write is bank-conflict free.  Q8K (eight lanes per 256-element super-block, see
 // Encoder<T_Q8K>): the eight rows of a super-block stay contiguous and each SUPER-BLOCK is padded by 64 bytes (its
 // stride is 16 words mod 32), because there the eight lanes of a group read consecutive 8- / 16-byte pieces.
-template <uint32_t T, class FT, bool ALLOW_SWZ = false> struct Stage {
+template <uint32_t T, class FT> struct Stage {
     static constexpr bool SB = (T == T_Q8K);
-    // 64-byte rows (16-bit input) of the short-lived CTAs are stored UNPADDED with their four 16-byte chunks permuted:
-    // chunk c of row r sits at chunk c ^ ((r >> 1) & 3).  A quarter warp's LDS.128 (eight consecutive rows, the same
-    // logical chunk) then touches eight different 16-byte bank groups, like the padded layout, in 4/5 of the space —
-    // which is what bounds how many of these CTAs an SM holds (see launch_quant).
-    static constexpr bool SWZ = ALLOW_SWZ && !SB && FT::SIZE == 2;
+    // 64-byte rows (16-bit input) are stored UNPADDED with their four 16-byte chunks permuted: chunk c of row r sits at
+    // chunk c ^ ((r >> 1) & 3).  A quarter warp's LDS.128 (eight consecutive rows, the same logical chunk) then touches
+    // eight different 16-byte bank groups, and its eight cp.async writes (two rows x four chunks) 128 contiguous bytes —
+    // with rows padded to 80 bytes the first and the last of those eight shared a bank group: a two-way conflict on
+    // every asynchronous write, which, with the 25 % larger stage, held these kernels at 85-90 % of the copy peak.
+    static constexpr bool SWZ = !SB && FT::SIZE == 2;
     static constexpr int ROW_BYTES = 32 * FT::SIZE;
     static constexpr int ROW_STRIDE = (SB || SWZ) ? ROW_BYTES : ROW_BYTES + 16;
     static constexpr int SB_PAD = SB ? 64 : 0;
@@ -684,7 +686,7 @@ quant_rows_oneshot(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, s
     using TR = BlockTraits<T>;
     using E = Encoder<T>;
     constexpr int RPB = TR::ELEMS / 32, TILE_BLOCKS = ROWS / RPB;
-    using ST = Stage<T, FT, true>;
+    using ST = Stage<T, FT>;
     constexpr int ROW_BYTES = 32 * FT::SIZE, CPR = ROW_BYTES / 16, ROWS_PER_PASS = ROWS / CPR;
     constexpr int IN_STAGE = ST::bytes(ROWS), OUT_BYTES = TILE_BLOCKS * TR::BYTES;
     constexpr uint32_t PASS_STRIDE = ST::bytes(ROWS_PER_PASS);
