@@ -480,6 +480,9 @@ def ours(args, rank, world, local_rank):
                "per_call_value": step_bytes * e2e_steps * world / dt_per_call / 1e9,
                "per_call_api": "8 separate ggq_dequantize_slice calls per step (pipeline drains between tensors)",
                "pcie_floor": floor, "frac_of_pcie_floor": e2e_value / floor["value"],
+               # where the host side is not full duplex (this pool's 4- and 8-GPU boxes: H2D and D2H share a limit), the pair of
+               # raw copies issued together is what a pipeline can reach at best
+               "frac_of_concurrent_copy_pair": e2e_value / floor["concurrent_pair_measured"],
                "pageable": {"value": step_bytes * pg_steps * world / dt_warm / 1e9, "cold_value": step_bytes * pg_steps * world / dt_cold / 1e9,
                             "unit": UNIT, "steps": pg_steps, "frac_of_pcie_floor": step_bytes * pg_steps * world / dt_warm / 1e9 / floor["value"],
                             "what": "same call, pageable caller buffers (numpy) bounced through the library's pinned staging; cold = output in a fresh "
