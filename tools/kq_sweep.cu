@@ -88,18 +88,19 @@ int main(int argc, char **argv) {
     if (!f32) {
         RUN(T_Q4K, F16, 4, 128, 0, 2, 2, true);
         RUNA(T_Q4K, F16, 4, 128, 0, 2, 2, 1);
-        RUNS(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 0, 1);
+        RUNA(T_Q4K, F16, 4, 168, 0, 2, 2, 1);   // more registers, fewer warps: 3 per scheduler
+        RUNA(T_Q4K, F16, 4, 255, 0, 2, 2, 1);   // 2 per scheduler
         RUN(T_Q5K, F16, 4, 128, 0, 2, 2, true);
         RUNA(T_Q5K, F16, 4, 128, 0, 2, 2, 1);
-        RUNS(T_Q5K, F16, 4, 128, 0, 2, 2, 1, 0, 1);
+        RUNA(T_Q5K, F16, 4, 168, 0, 2, 2, 1);
         RUN(T_Q2K, F16, 4, 72, 0, 2, 2, true);
         RUNA(T_Q2K, F16, 1, 64, 0, 2, 2, 1);
-        RUNS(T_Q2K, F16, 1, 64, 0, 2, 2, 1, 0, 1);
+        RUNA(T_Q2K, F16, 4, 96, 0, 2, 2, 1);
         RUN(T_Q6K, F16, 4, 96, 0, 2, 2, true);
         RUNR(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 2);
-        RUNS(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 2, 1);
-        RUNS(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 0, 1);
+        RUNR(T_Q6K, F16, 4, 128, 0, 2, 2, 0, 2);
         RUN(T_Q3K, F16, 4, 96, 0, 2, 2, true);
+        RUN(T_Q3K, F16, 4, 128, 0, 2, 2, false);
     } else {
         RUN(T_Q4K, F32, 4, 128, 0, 2, 2, true);
         RUNS(T_Q4K, F32, 4, 128, 0, 2, 2, 1, 0, 1);
