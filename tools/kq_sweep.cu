@@ -89,10 +89,13 @@ int main(int argc, char **argv) {
         RUN(T_Q4K, F16, 4, 128, 0, 2, 2, true);
         RUNA(T_Q4K, F16, 4, 128, 0, 2, 2, 1);
         RUNA(T_Q4K, F16, 4, 168, 0, 2, 2, 1);   // more registers, fewer warps: 3 per scheduler
-        RUNA(T_Q4K, F16, 4, 255, 0, 2, 2, 1);   // 2 per scheduler
+        RUNS(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 0, 1);  // shared division with room for its reciprocals
+        RUNS(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 1, 0);  // all rounding on the FP32 pipe
+        RUNS(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 2, 0);  // alternate pairs
         RUN(T_Q5K, F16, 4, 128, 0, 2, 2, true);
         RUNA(T_Q5K, F16, 4, 128, 0, 2, 2, 1);
         RUNA(T_Q5K, F16, 4, 168, 0, 2, 2, 1);
+        RUNS(T_Q5K, F16, 4, 168, 0, 2, 2, 1, 0, 1);
         RUN(T_Q2K, F16, 4, 72, 0, 2, 2, true);
         RUNA(T_Q2K, F16, 1, 64, 0, 2, 2, 1);
         RUNA(T_Q2K, F16, 4, 96, 0, 2, 2, 1);
