@@ -33,6 +33,12 @@ __device__ __forceinline__ int nearest_int(float v) {
     const float t = v + 12582912.f;
     return (__float_as_int(t) & 0x007fffff) - 0x00400000;
 }
+// The same for an argument that can be inf * 0: super-blocks of subnormal weights overflow `63 / max_scale`, and a
+// sub-block whose scale or min is exactly 0 then feeds a NaN to upstream's nearest_int().  On the reference platform that
+// NaN is the default one (0xFFC00000: mantissa 0x400000), which the magic-number arithmetic turns into 0; the GPU's
+// arithmetic NaN (0x7FFFFFFF) would come out as 4194303.  Infinities and huge values take the ordinary route (same bits
+// on both machines).
+__device__ __forceinline__ int nearest_int_of_product(float v) { return v != v ? 0 : nearest_int(v); }
 // exact (float)l for a small integer l in [-64, 2^22)
 __device__ __forceinline__ float i2f_small(int l) { return u2f_biased((uint32_t)(l + 64), 64.0f); }
 
@@ -197,9 +203,16 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
     const float fmax_l = (float)nmax;
     // every candidate's iscale divides by (max - min), which only changes when a candidate is accepted: one correctly
     // rounded reciprocal and three operations per quotient instead of a division each (div_shared_strict)
+    // A sub-block whose range is below nmax / FLT_MAX (subnormal weights) overflows iscale to +inf.  Upstream's
+    // nearest_int() then sees +-inf or NaN (inf * 0) for every element, and its magic-number add turns all three into a
+    // value that the following clamp maps to 0 (release builds; the debug assert is the only other behaviour): the
+    // candidate's codes are all zero.  Here the clamp comes first and would map +inf to nmax, so an infinite iscale
+    // is replaced by 0 where it multiplies (0 * finite = 0 -> code 0); `scale = 1 / iscale` keeps the true value.
+    auto usable = [](float isc) { return isc == __int_as_float(0x7f800000) ? 0.f : isc; };
     SharedDivisor range = shared_divisor(mx - mn);
     float iscale = div_shared_strict<SD>(fmax_l, range);
     float scale = 1 / iscale;
+    iscale = usable(iscale);
     float best_mad = 0;
     isc_best = iscale;
     mn_best = mn;
@@ -218,7 +231,7 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
         }
     }
     for (int is = 0; is <= nstep; ++is) {
-        iscale = div_shared_strict<SD>(rmin + rdelta * (float)is + fmax_l, range);
+        iscale = usable(div_shared_strict<SD>(rmin + rdelta * (float)is + fmax_l, range));
         float sum_l = 0, sum_l2 = 0, sum_xl = 0;
         float2 lf[LF ? 2 : N / 2];  // LF 1: only the pair being assembled into a 128-bit store
         {
@@ -488,8 +501,8 @@ template <int NMAX, int LF, int WM, int AF, int RM, int SD> __device__ __forcein
     const float max_scale = group_max_from_zero<8>(scale), max_min = group_max_from_zero<8>(the_min);
     const float inv_scale = max_scale > 0 ? 63.f / max_scale : 0.f;
     const float inv_min = max_min > 0 ? 63.f / max_min : 0.f;
-    uint32_t ls = (uint32_t)nearest_int(inv_scale * scale) & 0xFFu;
-    uint32_t lm = (uint32_t)nearest_int(inv_min * the_min) & 0xFFu;
+    uint32_t ls = (uint32_t)nearest_int_of_product(inv_scale * scale) & 0xFFu;
+    uint32_t lm = (uint32_t)nearest_int_of_product(inv_min * the_min) & 0xFFu;
     ls = min(ls, 63u);
     lm = min(lm, 63u);
     const uint16_t d16 = f2h(max_scale / 63.f), dmin16 = f2h(max_min / 63.f);
@@ -633,12 +646,12 @@ template <> struct KQuant<T_Q2K> {
         uint16_t d16 = 0, dmin16 = 0;
         if (max_scale > 0) {
             const float iscale = 15.f / max_scale;
-            b = (uint32_t)nearest_int(iscale * scale) & 0xFFu;
+            b = (uint32_t)nearest_int_of_product(iscale * scale) & 0xFFu;
             d16 = f2h(max_scale / 15.f);
         }
         if (max_min > 0) {
             const float iscale = 15.f / max_min;
-            b |= ((uint32_t)nearest_int(iscale * the_min) << 4) & 0xFFu;
+            b |= ((uint32_t)nearest_int_of_product(iscale * the_min) << 4) & 0xFFu;
             dmin16 = f2h(max_min / 15.f);
         }
         const float d = h2f(d16) * (float)(b & 0xFu);

@@ -670,3 +670,43 @@ def test_q4_k_m_llama3_8b_mix_sampled_vs_oracle(ggq, oracle):
             assert bad.size == 0, f"{variant} type {ty}: {bad.size} of {got.size // b} sampled super-blocks differ"
             sampled += got.size // b
     assert sampled == 2 * 31204
+
+
+def test_adversarial_input_families(ggq, oracle):
+    """tools/soak.py, fixed case count: every type x float side on inputs built to sit on rounding boundaries (values a few
+    ulps either side of each code boundary of the block's own scale), rows holding +max and -max, constant rows, signed
+    zeros, subnormal weights (for the K-quants: sub-block ranges below nmax / FLT_MAX, where upstream's iscale overflows and
+    its nearest_int() sees inf and inf * 0), heavy tails, NaN / inf sprinkles for the legacy types.  Quantize and dequantize
+    must equal the oracle bit for bit in every case."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SOAK_CASES="2500")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "soak.py"), "0", "11"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("fdt", FDTS)
+@pytest.mark.parametrize("ty", KQ)
+def test_kquant_subnormal_weights(ggq, oracle, ty, fdt):
+    """Super-blocks of subnormal and near-subnormal weights: the sub-block range sweeps across nmax / FLT_MAX (4e-38 for
+    Q4_K), so `iscale = nmax / (max - min)` overflows for some candidates of the search and not for others, `63 / max_scale`
+    overflows, sub-blocks with a positive minimum (min code 0) and all-equal sub-blocks are mixed in."""
+    import torch
+    n, b = oracle.block_info(ty)
+    rng = np.random.default_rng(7000 + ty)
+    rows = []
+    for sigma in (1e-41, 3e-40, 1e-39, 8e-39, 2e-38, 4.4e-38, 9e-38, 3e-37):
+        x = (rng.standard_normal((6, n)) * sigma).astype(np.float32)
+        x[1] = np.abs(x[1])                       # positive minimum: the_min = 0
+        x[2, :n // 2] = np.float32(sigma)         # all-equal sub-blocks
+        x[3, ::2] = 0.0
+        rows.append(x)
+    x = to_fdt(np.concatenate(rows).reshape(-1), fdt)
+    nb = x.size // n
+    want = oracle.quantize(ty, fdt, x)
+    st = torch.cuda.current_stream().cuda_stream
+    src = torch.from_numpy(x.view(np.uint8)).cuda()
+    q = torch.zeros(nb * b, dtype=torch.uint8, device="cuda")
+    ggq.quantize_slice_device(ty, fdt, q.data_ptr(), nb, src.data_ptr(), n * nb, st)
+    torch.cuda.synchronize()
+    assert same_blocks(q.cpu().numpy(), want, ty, b)

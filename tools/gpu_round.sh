@@ -34,6 +34,7 @@ for phase in "$@"; do
                GGQ_SO=$so timeout 300 python tools/codec_sweep.py 58720256 $AB_ONLY 2>&1 | grep -v " F32 " | sed "s/^/$v /"; done; done > gpurun_out/${AB_OUT:-absweep.txt}
              cat gpurun_out/${AB_OUT:-absweep.txt} ;;
     cpuprobe) timeout 900 python tools/cpu_port_probe.py > gpurun_out/cpu_port_probe.txt 2>&1; cat gpurun_out/cpu_port_probe.txt ;;
+    soak)    timeout 900 python tools/soak.py ${SOAK_SECONDS:-300} ${SOAK_SEED:-1} > gpurun_out/soak.txt 2>&1; tail -14 gpurun_out/soak.txt ;;
     box)     bash tools/box_probe.sh > gpurun_out/box_probe.txt 2>&1 ;;
     bench2)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 800 gpurun_out/bench_n2.err; head -c 300 gpurun_out/bench_n2.json; echo ;;
     mixtral2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/mixtral_sweep.py > gpurun_out/mixtral_n2.txt 2>&1; tail -13 gpurun_out/mixtral_n2.txt ;;
