@@ -12,9 +12,10 @@ namespace ggq {
 // buys).  What ships beyond round 1: the packed affine (AF 1: -1..-1.6 %), and for Q2K one-warp CTAs at 64 registers
 // (8 warps per scheduler instead of 7, and no 4-warp granularity in the tail: -5 %).
 template <uint32_t T> struct KqShipped { using type = KqCfg<4, KQuant<T>::REGS, 0, 2, 2>; };
-template <> struct KqShipped<T_Q4K> { using type = KqCfg<4, 128, 0, 2, 2, 1>; };
-template <> struct KqShipped<T_Q5K> { using type = KqCfg<4, 128, 0, 2, 2, 1>; };
-template <> struct KqShipped<T_Q2K> { using type = KqCfg<1, 64, 0, 2, 2, 1>; };
+// CL 1: the search's clamp to [0, nmax] is one VIMNMX.RELU per element instead of two FMNMX (quant_k_kernel.cuh, clamp0_relu).
+template <> struct KqShipped<T_Q4K> { using type = KqCfg<4, 128, 0, 2, 2, 1, 0, 0, 1>; };
+template <> struct KqShipped<T_Q5K> { using type = KqCfg<4, 128, 0, 2, 2, 1, 0, 0, 1>; };
+template <> struct KqShipped<T_Q2K> { using type = KqCfg<1, 64, 0, 2, 2, 1, 0, 0, 1>; };
 // Q6K's hottest pipe is the XU (FRND: 62 % busy against 49 % for the FP32 pipe): rounding every other pair with the two
 // magic-number adds instead balances the two (-1 %); all pairs on the FP32 pipe is +3 %.
 template <> struct KqShipped<T_Q6K> { using type = KqCfg<4, 96, 0, 2, 2, 0, 2>; };

@@ -133,6 +133,16 @@ __device__ __forceinline__ void qkx2_codes(const float (&x)[N], const float isc,
 __device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
 __device__ __forceinline__ float2 clamp2(float2 v, float lo, float hi) { return make_float2(fminf(fmaxf(v.x, lo), hi), fminf(fmaxf(v.y, lo), hi)); }
 __device__ __forceinline__ float2 abs2(float2 v) { return make_float2(fabsf(v.x), fabsf(v.y)); }
+// clamp(v, 0, hi) in ONE instruction (VIMNMX.RELU, `min.relu.s32` on the float's bits) instead of two FMNMX: non-negative
+// floats order like their bit patterns, so the signed minimum with hi's bits is min(v, hi) for v >= 0, and every negative
+// float (sign bit set: a negative integer, -0 included) falls to the relu's 0 = +0.0f.  Same value as
+// fminf(fmaxf(v, 0), hi) for every v that is not a NaN (+inf -> hi, -inf -> 0); a NaN, which only non-finite input could
+// produce here (outside upstream's domain: its nearest_int asserts), gives hi or 0 by its sign instead of 0.
+__device__ __forceinline__ float clamp0_relu(float v, float hi) {
+    int r;
+    asm("min.relu.s32 %0, %1, %2;" : "=r"(r) : "r"(__float_as_int(v)), "r"(__float_as_int(hi)));
+    return __int_as_float(r);
+}
 // (ns*l + nm) per lane with its two roundings.  Scalar on purpose: ptxas 12.9 contracts a mul.rn.f32x2 feeding an
 // add.rn.f32x2 into one single-rounding FFMA2 even with --fmad=false (the explicit .rn protects only scalar
 // code), which changes results.  No other packed multiply in this file feeds a packed add; the Makefile
@@ -155,8 +165,9 @@ template <int AF> __device__ __forceinline__ float2 affine2(float2 l, float ns, 
 // RM selects where the rounding runs: 0 = FRND for every element (XU pipe, 8 cycles per warp instruction), 1 = the
 // magic-number adds for every pair (two packed FP32-pipe instructions per pair), 2 = alternating pairs, which splits the
 // rounding work between the two pipes.
-template <int RM> __device__ __forceinline__ float2 round_clamped2(float2 v, float lo, float hi, int k) {
-    const float2 c = clamp2(v, lo, hi);
+// CL 1 (only where lo == 0): the clamp is one VIMNMX.RELU per element (clamp0_relu) instead of two FMNMX.
+template <int RM, int CL = 0> __device__ __forceinline__ float2 round_clamped2(float2 v, float lo, float hi, int k) {
+    const float2 c = CL ? make_float2(clamp0_relu(v.x, hi), clamp0_relu(v.y, hi)) : clamp2(v, lo, hi);
     if (RM == 1 || (RM == 2 && (k & 1))) return __fadd2_rn(__fadd2_rn(c, bcast2(RMAGIC)), bcast2(-RMAGIC));
     return make_float2(rintf(c.x), rintf(c.y));
 }
@@ -169,7 +180,7 @@ template <int RM> __device__ __forceinline__ float2 round_clamped2(float2 v, flo
 // 16-byte aligned, rows 144 bytes apart so the lanes' 128-bit accesses never share a bank) instead of N registers: two
 // 128-bit shared accesses per 4 elements and candidate, none of them on the FP32 pipe that bounds the search — and 32
 // registers fewer for the 32-element sub-blocks, which is one more resident CTA per SM.
-template <int N, bool USE_MAD, int WMODE, int LF, int AF, int RM, int SD>
+template <int N, bool USE_MAD, int WMODE, int LF, int AF, int RM, int SD, int CL>
 __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const float (&w)[N], const float av, const int nmax, float &the_min,
                                                   const float rmin, const float rdelta, const int nstep, float &isc_best, float &mn_best,
                                                   float *__restrict__ lrow, const float one) {
@@ -222,7 +233,7 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
         const float2 nmn = bcast2(-mn), isc2 = bcast2(iscale);
 #pragma unroll
         for (int k = 0; k < N / 2; ++k) {
-            const float2 l = round_clamped2<RM>(__fmul2_rn(__fadd2_rn(x2[k], nmn), isc2), 0.f, fmax_l, k);
+            const float2 l = round_clamped2<RM, CL>(__fmul2_rn(__fadd2_rn(x2[k], nmn), isc2), 0.f, fmax_l, k);
             float2 d = __fadd2_rn(x2[k], affine2<AF>(l, -scale, -mn, one));
             d = USE_MAD ? abs2(d) : __fmul2_rn(d, d);
             const float2 e = __fmul2_rn(w2(k), d);
@@ -238,7 +249,7 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
             const float2 nmn = bcast2(-mn), isc2 = bcast2(iscale);
 #pragma unroll
             for (int k = 0; k < N / 2; ++k) {
-                const float2 l = round_clamped2<RM>(__fmul2_rn(__fadd2_rn(x2[k], nmn), isc2), 0.f, fmax_l, k);
+                const float2 l = round_clamped2<RM, CL>(__fmul2_rn(__fadd2_rn(x2[k], nmn), isc2), 0.f, fmax_l, k);
                 if constexpr (LF) {
                     lf[k & 1] = l;
                     if (k & 1) *reinterpret_cast<float4 *>(lrow + 2 * (k - 1)) = make_float4(lf[0].x, lf[0].y, lf[1].x, lf[1].y);
@@ -481,7 +492,7 @@ template <int SUB> __device__ __forceinline__ void put_codes(KScratch &s, int j,
 }
 
 // Q4K and Q5K share everything but nmax / search range / final layout.
-template <int NMAX, int LF, int WM, int AF, int RM, int SD> __device__ __forceinline__ void k45_lane(const float (&x)[32], int j, KScratch &s, float rmin, int nstep, float *lrow, float one) {
+template <int NMAX, int LF, int WM, int AF, int RM, int SD, int CL> __device__ __forceinline__ void k45_lane(const float (&x)[32], int j, KScratch &s, float rmin, int nstep, float *lrow, float one) {
     float sum_x2 = 0;
 #pragma unroll
     for (int l = 0; l < 32; ++l) sum_x2 += x[l] * x[l];
@@ -496,8 +507,8 @@ template <int NMAX, int LF, int WM, int AF, int RM, int SD> __device__ __forcein
     uint32_t L[8];
     float the_min, isc_best, mn_best;
     float scale;
-    if constexpr (WM == 2) scale = make_qkx2_quants<32, false, 2, LF, AF, RM, SD>(x, w, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best, lrow, one);
-    else scale = make_qkx2_quants<32, false, 1, LF, AF, RM, SD>(x, x, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best, lrow, one);
+    if constexpr (WM == 2) scale = make_qkx2_quants<32, false, 2, LF, AF, RM, SD, CL>(x, w, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best, lrow, one);
+    else scale = make_qkx2_quants<32, false, 1, LF, AF, RM, SD, CL>(x, x, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best, lrow, one);
     const float max_scale = group_max_from_zero<8>(scale), max_min = group_max_from_zero<8>(the_min);
     const float inv_scale = max_scale > 0 ? 63.f / max_scale : 0.f;
     const float inv_min = max_min > 0 ? 63.f / max_min : 0.f;
@@ -553,7 +564,7 @@ template <> struct KQuant<T_Q4K> {
         const int t = w - 4, p = t >> 3, jj = t & 7;
         return code_word(s, 16 * p + jj) | (code_word(s, 16 * p + 8 + jj) << 4);
     }
-    template <class CFG> static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s, float *lrow, float one) { k45_lane<15, CFG::LF, CFG::WM, CFG::AF, CFG::RM, CFG::SD>(x, j, s, -1.f, 20, lrow, one); }
+    template <class CFG> static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s, float *lrow, float one) { k45_lane<15, CFG::LF, CFG::WM, CFG::AF, CFG::RM, CFG::SD, CFG::CL>(x, j, s, -1.f, 20, lrow, one); }
 };
 template <> struct KQuant<T_Q5K> {
     static constexpr int SUB = 32;
@@ -571,7 +582,7 @@ template <> struct KQuant<T_Q5K> {
         const int t = w - 12, p = t >> 3, jj = t & 7;
         return (code_word(s, 16 * p + jj) & 0x0F0F0F0Fu) | ((code_word(s, 16 * p + 8 + jj) & 0x0F0F0F0Fu) << 4);
     }
-    template <class CFG> static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s, float *lrow, float one) { k45_lane<31, CFG::LF, CFG::WM, CFG::AF, CFG::RM, CFG::SD>(x, j, s, -0.5f, 15, lrow, one); }
+    template <class CFG> static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s, float *lrow, float one) { k45_lane<31, CFG::LF, CFG::WM, CFG::AF, CFG::RM, CFG::SD, CFG::CL>(x, j, s, -0.5f, 15, lrow, one); }
 };
 
 template <> struct KQuant<T_Q6K> {
@@ -640,7 +651,7 @@ template <> struct KQuant<T_Q2K> {
         // weights = |x|: an operand modifier, never materialised (WMODE 0) — 7 CTAs per SM instead of 6, -4 % time
         uint32_t L[4];
         float the_min, isc_best, mn_best;
-        const float scale = make_qkx2_quants<16, true, 0, CFG::LF, CFG::AF, CFG::RM, CFG::SD>(x, x, 0.f, 3, the_min, -0.5f, 0.1f, 15, isc_best, mn_best, lrow, one);
+        const float scale = make_qkx2_quants<16, true, 0, CFG::LF, CFG::AF, CFG::RM, CFG::SD, CFG::CL>(x, x, 0.f, 3, the_min, -0.5f, 0.1f, 15, isc_best, mn_best, lrow, one);
         const float max_scale = group_max_from_zero<16>(scale), max_min = group_max_from_zero<16>(the_min);
         uint32_t b = 0;
         uint16_t d16 = 0, dmin16 = 0;
@@ -732,8 +743,8 @@ template <> struct KQuant<T_Q3K> {
 // which lets occupancy follow the register cap in steps of one warp rather than four), REGS (register cap per thread,
 // __maxnreg__), LF (per-lane shared-memory row: candidate codes for the qkx2 searches, w / w*x for Q6K),
 // WM (Q4K / Q5K weights: 2 registers, 1 recomputed), STAGES (input rows in flight).
-template <int WARPS_, int REGS_, int LF_, int WM_, int STAGES_, int AF_ = 0, int RM_ = 0, int SD_ = 0> struct KqCfg {
-    static constexpr int WARPS = WARPS_, THREADS = WARPS_ * 32, REGS = REGS_, LF = LF_, WM = WM_, STAGES = STAGES_, AF = AF_, RM = RM_, SD = SD_;
+template <int WARPS_, int REGS_, int LF_, int WM_, int STAGES_, int AF_ = 0, int RM_ = 0, int SD_ = 0, int CL_ = 0> struct KqCfg {
+    static constexpr int WARPS = WARPS_, THREADS = WARPS_ * 32, REGS = REGS_, LF = LF_, WM = WM_, STAGES = STAGES_, AF = AF_, RM = RM_, SD = SD_, CL = CL_;
 };
 constexpr int KQ_LROW = 36;  // floats between the lanes' rows: 144 bytes, so eight lanes' 128-bit accesses cover all 32 banks
 

@@ -9,6 +9,7 @@ for phase in "$@"; do
     pcie)    timeout 300 python tools/pcie_probe.py > gpurun_out/pcie_probe.txt 2>&1 ;;
     sweep)   timeout 900 python tools/codec_sweep.py > gpurun_out/codec_sweep.txt 2>&1; tail -5 gpurun_out/codec_sweep.txt ;;
     sweep_dq) timeout 900 python tools/codec_sweep.py 58720256 dequant > gpurun_out/codec_sweep_dq.txt 2>&1; timeout 900 python tools/codec_sweep.py 16777216 dequant > gpurun_out/codec_sweep_dq_16m.txt 2>&1; timeout 900 python tools/codec_sweep.py 4194304 dequant > gpurun_out/codec_sweep_dq_4m.txt 2>&1; tail -3 gpurun_out/codec_sweep_dq_4m.txt ;;
+    iprobe)  timeout 120 tools/issue_probe > gpurun_out/issue_probe.txt 2>&1; cat gpurun_out/issue_probe.txt ;;
     kq)      timeout 600 tools/kq_sweep f16 > gpurun_out/kq_sweep_f16.txt 2>&1; timeout 300 tools/kq_sweep f32 > gpurun_out/kq_sweep_f32.txt 2>&1; cat gpurun_out/kq_sweep_f16.txt gpurun_out/kq_sweep_f32.txt ;;
     kq_ncu)  for t in T_Q4K T_Q6K; do timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_k_kernel -c 1 -f -o gpurun_out/kq_${t} tools/kq_sweep f16 $t first > gpurun_out/kq_ncu_${t}.log 2>&1; tail -2 gpurun_out/kq_ncu_${t}.log; done ;;
     ncu_batch) timeout 900 ncu --set full --import-source on --clock-control none -k regex:dequant_batch -c 1 -f -o gpurun_out/r02_dequant_batch python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_batch.log 2>&1; tail -2 gpurun_out/ncu_batch.log ;;

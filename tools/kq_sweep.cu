@@ -58,6 +58,7 @@ void run(const char *name, const void *d_x, uint8_t *d_out, size_t nblocks, bool
 #define RUN(T, FT, W, REGS, LF, WM, ST, ref) run<T, FT, KqCfg<W, REGS, LF, WM, ST>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST ">", d_x, d_out, nblocks, ref)
 #define RUNA(T, FT, W, REGS, LF, WM, ST, AF) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF ">", d_x, d_out, nblocks, false)
 #define RUNS(T, FT, W, REGS, LF, WM, ST, AF, RM, SD) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM, SD>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM "," #SD ">", d_x, d_out, nblocks, false)
+#define RUNC(T, FT, W, REGS, LF, WM, ST, AF, RM, SD, CL) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM, SD, CL>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM "," #SD "," #CL ">", d_x, d_out, nblocks, false)
 #define RUNR(T, FT, W, REGS, LF, WM, ST, AF, RM) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM ">", d_x, d_out, nblocks, false)
 
 int main(int argc, char **argv) {
@@ -88,16 +89,24 @@ int main(int argc, char **argv) {
     if (!f32) {
         RUN(T_Q4K, F16, 4, 128, 0, 2, 2, true);
         RUNA(T_Q4K, F16, 4, 128, 0, 2, 2, 1);
+        RUNC(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1);   // clamp as one VIMNMX.RELU
+        RUNC(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 0, 0, 1);
+        RUNC(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 2, 0, 1);   // + alternate pairs round on the FP32 pipe
+        RUNC(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 0, 1, 1);   // + shared division
         RUNA(T_Q4K, F16, 4, 168, 0, 2, 2, 1);   // more registers, fewer warps: 3 per scheduler
         RUNS(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 0, 1);  // shared division with room for its reciprocals
         RUNS(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 1, 0);  // all rounding on the FP32 pipe
         RUNS(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 2, 0);  // alternate pairs
         RUN(T_Q5K, F16, 4, 128, 0, 2, 2, true);
         RUNA(T_Q5K, F16, 4, 128, 0, 2, 2, 1);
+        RUNC(T_Q5K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1);
+        RUNC(T_Q5K, F16, 4, 128, 0, 2, 2, 1, 0, 1, 1);
         RUNA(T_Q5K, F16, 4, 168, 0, 2, 2, 1);
         RUNS(T_Q5K, F16, 4, 168, 0, 2, 2, 1, 0, 1);
         RUN(T_Q2K, F16, 4, 72, 0, 2, 2, true);
         RUNA(T_Q2K, F16, 1, 64, 0, 2, 2, 1);
+        RUNC(T_Q2K, F16, 1, 64, 0, 2, 2, 1, 0, 0, 1);
+        RUNC(T_Q2K, F16, 4, 72, 0, 2, 2, 1, 0, 0, 1);
         RUNA(T_Q2K, F16, 4, 96, 0, 2, 2, 1);
         RUN(T_Q6K, F16, 4, 96, 0, 2, 2, true);
         RUNR(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 2);
@@ -107,6 +116,7 @@ int main(int argc, char **argv) {
     } else {
         RUN(T_Q4K, F32, 4, 128, 0, 2, 2, true);
         RUNS(T_Q4K, F32, 4, 128, 0, 2, 2, 1, 0, 1);
+        RUNC(T_Q4K, F32, 4, 128, 0, 2, 2, 1, 0, 0, 1);
         RUN(T_Q6K, F32, 4, 96, 0, 2, 2, true);
         RUNS(T_Q6K, F32, 4, 96, 0, 2, 2, 0, 2, 1);
     }
