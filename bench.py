@@ -20,7 +20,7 @@ Workload (N=1): BASELINE.json configs[1] — Llama-3-8B-shaped synthetic tensors
             bytes asserted equal to the single-device result.
   roofline  the dominant kernel (the batched dequantize grid: 100 % of the step's launches): algorithmic bytes per
             launch / average launch duration from the CUDA events of the timed region.
-  quant_roofline  the K-quant quantize kernels against the instruction-issue roofline they are bound by.
+  quant_roofline  the K-quant quantize kernels against the FP32-pipe and instruction-issue rooflines that bound them.
   cpu_baseline  the CPU oracle port (oracle/, the reference's algorithm restated in C; the Rust
             reference cannot be built in this image) on the host cores, the whole workload.
 
@@ -366,11 +366,13 @@ def ours(args, rank, world, local_rank):
                                      "bound": "fp32 issue (bit-faithful scale search)" if w["ty"] in (g.Q4K, g.Q6K) else "hbm"})
             del outs
         del xs
-        # K-quant quantize is instruction-issue bound: roofline = warp instructions / (schedulers x clock).
-        # instr_per_elem comes from the committed ncu summary of the shipped kernels (tools/quant_roofline.py writes it).
+        # K-quant quantize is bound by the SM's arithmetic, not by HBM.  Two rooflines, both from the committed
+        # ncu capture of the shipped kernels (tools/quant_roofline.py writes the JSON): issue = warp instructions /
+        # (schedulers x clock); fp32 pipe = the time the FP32 pipe alone needs (a packed FADD2 / FMUL2 / FFMA2 holds it two
+        # cycles, so this counts lane operations).  `frac` is against the tighter (larger) of the two.
         qr = load_profile_json("r02_quant_k_roofline.json")
         if qr:
-            quant_roofline = {"bound": "issue", "source": "profiles/r02_quant_k_roofline.json (smsp__inst_executed from ncu, shipped kernels)", "kernels": []}
+            quant_roofline = {"bound": "fp32 pipe / issue", "source": "profiles/r02_quant_k_roofline.json (smsp__inst_executed and sm__pipe_fma_cycles_active from ncu, shipped kernels)", "kernels": []}
             sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
             for row in quant_per_kernel:
                 key = {"quantize<Q4_K,f16>": "Q4K", "quantize<Q6_K,f16>": "Q6K"}.get(row["kernel"])
@@ -378,8 +380,13 @@ def ours(args, rank, world, local_rank):
                     ipe = qr["instr_per_elem"][key]   # thread-level instructions per element
                     n_el = ffn[0]["n"]
                     issue_us = ipe * n_el / 32.0 / (sm_count * 4 * qr.get("sm_clock_mhz", 1965.0) * 1e6) * 1e6
+                    fp32_us = qr.get("kernels", {}).get(key, {}).get("fp32_pipe_limit_us")
+                    limit = max(issue_us, fp32_us or 0.0)
                     quant_roofline["kernels"].append({"kernel": row["kernel"], "instr_per_elem": ipe, "issue_limit_us": issue_us,
-                                                      "achieved_us": row["us"], "frac": issue_us / row["us"]})
+                                                      "fp32_pipe_limit_us": fp32_us, "achieved_us": row["us"],
+                                                      "frac_issue": issue_us / row["us"],
+                                                      "frac_fp32_pipe": (fp32_us / row["us"]) if fp32_us else None,
+                                                      "frac": limit / row["us"]})
     clocks = sampler.stop()
     peak, peak_src = measured_peak()
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture

@@ -1009,6 +1009,7 @@ void ggq_shutdown(void) {
         cudaSetDevice(p->device);
         destroy_pipeline(p);
     }
+    quant_k_release_work();
     const int ndev = ggq_device_count();
     for (int d = 0; d < ndev && d < MAX_DEVICES; d++) {  // give cached stream-ordered allocations back
         cudaMemPool_t pool;

@@ -29,6 +29,8 @@ cudaError_t dequant_blocks_batch(uint32_t fdt, const DequantJob *jobs, size_t n,
 cudaError_t quant_blocks_legacy(uint32_t type, uint32_t fdt, const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev);
 // float side -> packed blocks, K-quants (Q2K..Q6K).
 cudaError_t quant_blocks_k(uint32_t type, uint32_t fdt, const void *src, void *dst, size_t nblocks, cudaStream_t stream, DevInfo dev);
+// frees the ticket counters quant_blocks_k keeps per (thread, device, stream); called by ggq_shutdown()
+void quant_k_release_work();
 // element casts between f32 / f16 / bf16 (the 1-element "blocks" of structs/half.rs).
 cudaError_t cast_elems(uint32_t src_dt, uint32_t dst_dt, const void *src, void *dst, size_t n, cudaStream_t stream, DevInfo dev);
 

@@ -180,7 +180,7 @@ template <int RM, int CL = 0> __device__ __forceinline__ float2 round_clamped2(f
 // 16-byte aligned, rows 144 bytes apart so the lanes' 128-bit accesses never share a bank) instead of N registers: two
 // 128-bit shared accesses per 4 elements and candidate, none of them on the FP32 pipe that bounds the search — and 32
 // registers fewer for the 32-element sub-blocks, which is one more resident CTA per SM.
-template <int N, bool USE_MAD, int WMODE, int LF, int AF, int RM, int SD, int CL>
+template <int N, bool USE_MAD, int WMODE, int LF, int AF, int RM, int SD, int CL, int SP>
 __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const float (&w)[N], const float av, const int nmax, float &the_min,
                                                   const float rmin, const float rdelta, const int nstep, float &isc_best, float &mn_best,
                                                   float *__restrict__ lrow, const float one) {
@@ -241,8 +241,20 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
             best_mad += e.y;
         }
     }
+    // SP 1: the NEXT candidate's iscale is divided out while this candidate is still being evaluated, from the range as
+    // it stands (a candidate is rarely accepted); an accepted candidate changes the range and the quotient is taken
+    // again — the same operands either way, so the same bits, but the division's latency (reciprocal, four dependent
+    // FMAs, range check: ~50 cycles in which the warp can issue nothing else) leaves the path between two candidates.
+    // Measured and left off: bit-identical, but the quotient carried across the candidate costs registers the 128-register
+    // kernels do not have (spill 16 -> 24 bytes): Q4K 839 -> 858 us, Q5K 682 -> 700, Q2K 670 -> 690.
+    float iscale_next = SP ? div_shared_strict<SD>(rmin + rdelta * 0.f + fmax_l, range) : 0.f;
     for (int is = 0; is <= nstep; ++is) {
-        iscale = usable(div_shared_strict<SD>(rmin + rdelta * (float)is + fmax_l, range));
+        if constexpr (SP) {
+            iscale = usable(iscale_next);
+            iscale_next = div_shared_strict<SD>(rmin + rdelta * (float)(is + 1) + fmax_l, range);
+        } else {
+            iscale = usable(div_shared_strict<SD>(rmin + rdelta * (float)is + fmax_l, range));
+        }
         float sum_l = 0, sum_l2 = 0, sum_xl = 0;
         float2 lf[LF ? 2 : N / 2];  // LF 1: only the pair being assembled into a 128-bit store
         {
@@ -302,6 +314,7 @@ __device__ __forceinline__ float make_qkx2_quants(const float (&x)[N], const flo
                 scale = this_scale;
                 mn = this_min;
                 range = shared_divisor(mx - mn);
+                if constexpr (SP) iscale_next = div_shared_strict<SD>(rmin + rdelta * (float)(is + 1) + fmax_l, range);
             }
         }
     }
@@ -492,7 +505,7 @@ template <int SUB> __device__ __forceinline__ void put_codes(KScratch &s, int j,
 }
 
 // Q4K and Q5K share everything but nmax / search range / final layout.
-template <int NMAX, int LF, int WM, int AF, int RM, int SD, int CL> __device__ __forceinline__ void k45_lane(const float (&x)[32], int j, KScratch &s, float rmin, int nstep, float *lrow, float one) {
+template <int NMAX, int LF, int WM, int AF, int RM, int SD, int CL, int SP> __device__ __forceinline__ void k45_lane(const float (&x)[32], int j, KScratch &s, float rmin, int nstep, float *lrow, float one) {
     float sum_x2 = 0;
 #pragma unroll
     for (int l = 0; l < 32; ++l) sum_x2 += x[l] * x[l];
@@ -507,8 +520,8 @@ template <int NMAX, int LF, int WM, int AF, int RM, int SD, int CL> __device__ _
     uint32_t L[8];
     float the_min, isc_best, mn_best;
     float scale;
-    if constexpr (WM == 2) scale = make_qkx2_quants<32, false, 2, LF, AF, RM, SD, CL>(x, w, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best, lrow, one);
-    else scale = make_qkx2_quants<32, false, 1, LF, AF, RM, SD, CL>(x, x, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best, lrow, one);
+    if constexpr (WM == 2) scale = make_qkx2_quants<32, false, 2, LF, AF, RM, SD, CL, SP>(x, w, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best, lrow, one);
+    else scale = make_qkx2_quants<32, false, 1, LF, AF, RM, SD, CL, SP>(x, x, av_x, NMAX, the_min, rmin, 0.1f, nstep, isc_best, mn_best, lrow, one);
     const float max_scale = group_max_from_zero<8>(scale), max_min = group_max_from_zero<8>(the_min);
     const float inv_scale = max_scale > 0 ? 63.f / max_scale : 0.f;
     const float inv_min = max_min > 0 ? 63.f / max_min : 0.f;
@@ -564,7 +577,7 @@ template <> struct KQuant<T_Q4K> {
         const int t = w - 4, p = t >> 3, jj = t & 7;
         return code_word(s, 16 * p + jj) | (code_word(s, 16 * p + 8 + jj) << 4);
     }
-    template <class CFG> static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s, float *lrow, float one) { k45_lane<15, CFG::LF, CFG::WM, CFG::AF, CFG::RM, CFG::SD, CFG::CL>(x, j, s, -1.f, 20, lrow, one); }
+    template <class CFG> static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s, float *lrow, float one) { k45_lane<15, CFG::LF, CFG::WM, CFG::AF, CFG::RM, CFG::SD, CFG::CL, CFG::SP>(x, j, s, -1.f, 20, lrow, one); }
 };
 template <> struct KQuant<T_Q5K> {
     static constexpr int SUB = 32;
@@ -582,7 +595,7 @@ template <> struct KQuant<T_Q5K> {
         const int t = w - 12, p = t >> 3, jj = t & 7;
         return (code_word(s, 16 * p + jj) & 0x0F0F0F0Fu) | ((code_word(s, 16 * p + 8 + jj) & 0x0F0F0F0Fu) << 4);
     }
-    template <class CFG> static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s, float *lrow, float one) { k45_lane<31, CFG::LF, CFG::WM, CFG::AF, CFG::RM, CFG::SD, CFG::CL>(x, j, s, -0.5f, 15, lrow, one); }
+    template <class CFG> static __device__ __forceinline__ void lane(const float (&x)[32], int j, int, KScratch &s, float *lrow, float one) { k45_lane<31, CFG::LF, CFG::WM, CFG::AF, CFG::RM, CFG::SD, CFG::CL, CFG::SP>(x, j, s, -0.5f, 15, lrow, one); }
 };
 
 template <> struct KQuant<T_Q6K> {
@@ -651,7 +664,7 @@ template <> struct KQuant<T_Q2K> {
         // weights = |x|: an operand modifier, never materialised (WMODE 0) — 7 CTAs per SM instead of 6, -4 % time
         uint32_t L[4];
         float the_min, isc_best, mn_best;
-        const float scale = make_qkx2_quants<16, true, 0, CFG::LF, CFG::AF, CFG::RM, CFG::SD, CFG::CL>(x, x, 0.f, 3, the_min, -0.5f, 0.1f, 15, isc_best, mn_best, lrow, one);
+        const float scale = make_qkx2_quants<16, true, 0, CFG::LF, CFG::AF, CFG::RM, CFG::SD, CFG::CL, CFG::SP>(x, x, 0.f, 3, the_min, -0.5f, 0.1f, 15, isc_best, mn_best, lrow, one);
         const float max_scale = group_max_from_zero<16>(scale), max_min = group_max_from_zero<16>(the_min);
         uint32_t b = 0;
         uint16_t d16 = 0, dmin16 = 0;
@@ -743,14 +756,14 @@ template <> struct KQuant<T_Q3K> {
 // which lets occupancy follow the register cap in steps of one warp rather than four), REGS (register cap per thread,
 // __maxnreg__), LF (per-lane shared-memory row: candidate codes for the qkx2 searches, w / w*x for Q6K),
 // WM (Q4K / Q5K weights: 2 registers, 1 recomputed), STAGES (input rows in flight).
-template <int WARPS_, int REGS_, int LF_, int WM_, int STAGES_, int AF_ = 0, int RM_ = 0, int SD_ = 0, int CL_ = 0> struct KqCfg {
-    static constexpr int WARPS = WARPS_, THREADS = WARPS_ * 32, REGS = REGS_, LF = LF_, WM = WM_, STAGES = STAGES_, AF = AF_, RM = RM_, SD = SD_, CL = CL_;
+template <int WARPS_, int REGS_, int LF_, int WM_, int STAGES_, int AF_ = 0, int RM_ = 0, int SD_ = 0, int CL_ = 0, int SP_ = 0> struct KqCfg {
+    static constexpr int WARPS = WARPS_, THREADS = WARPS_ * 32, REGS = REGS_, LF = LF_, WM = WM_, STAGES = STAGES_, AF = AF_, RM = RM_, SD = SD_, CL = CL_, SP = SP_;
 };
 constexpr int KQ_LROW = 36;  // floats between the lanes' rows: 144 bytes, so eight lanes' 128-bit accesses cover all 32 banks
 
 template <uint32_t T, class FT, class CFG>
 __global__ void __launch_bounds__(CFG::THREADS) __maxnreg__(CFG::REGS)
-quant_k_kernel(const typename FT::raw *__restrict__ src, uint8_t *__restrict__ dst, size_t nblocks, const float one) {
+quant_k_kernel(const typename FT::raw *__restrict__ src, uint8_t *__restrict__ dst, size_t nblocks, const float one, unsigned long long *__restrict__ work) {
     using KQ = KQuant<T>;
     constexpr int NSTG = CFG::STAGES, KQ_WARPS = CFG::WARPS, KQ_THREADS = CFG::THREADS;
     constexpr int SUB = KQ::SUB, NSUB = 256 / SUB, SBW = 32 / NSUB;  // super-blocks per warp pass
@@ -803,14 +816,29 @@ quant_k_kernel(const typename FT::raw *__restrict__ src, uint8_t *__restrict__ d
         cp_async_commit();
     };
 
-    size_t g = (size_t)blockIdx.x * KQ_WARPS + warp;
+    // The pass after `cur`.  `work` (a launch-wide counter, zero at launch) hands the passes out as tickets: the first
+    // pass of every warp is its own index, tickets start behind those.  A pass takes tens of microseconds and a
+    // data-dependent time (Q3K's refinement loops most of all); with a fixed stride the warps of an SM also stay in the
+    // same phase of the search and queue for the same pipe.  Measured against the fixed stride on 58.7 M elements:
+    // Q4K 836 -> 769 us, Q5K 678 -> 632, Q2K 664 -> 621, Q6K 481 -> 449, Q3K 449 -> 428.  `work == nullptr` (small
+    // inputs: at most one pass per warp) keeps the fixed stride.
+    auto next_of = [&](size_t cur) -> size_t {
+        if (work != nullptr) {
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(work, 1ull);
+            return gstep + (size_t)__shfl_sync(KFULL, t, 0);
+        }
+        return cur + gstep;
+    };
+    size_t g = (size_t)blockIdx.x * KQ_WARPS + warp, gnext = 0;
     int stage = 0;
     if constexpr (NSTG == 2) issue(g, 0);
-    for (; g < ngroups; g += gstep, stage ^= (NSTG - 1)) {
+    for (; g < ngroups; g = gnext, stage ^= (NSTG - 1)) {
         const size_t sb0 = g * SBW;
         const int nsb = (int)min((size_t)SBW, nblocks - sb0);
+        gnext = next_of(g);
         if constexpr (NSTG == 2) {
-            issue(g + gstep, stage ^ 1);  // the other stage was consumed before the __syncwarp that ended the previous pass
+            issue(gnext, stage ^ 1);  // the other stage was consumed before the __syncwarp that ended the previous pass
             cp_async_wait<1>();           // this lane's chunks of pass g have landed ...
         } else {
             issue(g, 0);                  // single stage: the rows were consumed into registers before the previous pass searched

@@ -22,6 +22,7 @@ for phase in "$@"; do
     bench4)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/bench_n4.json 2> gpurun_out/bench_n4.err; tail -c 600 gpurun_out/bench_n4.err; head -c 400 gpurun_out/bench_n4.json; echo ;;
     ncu_q40) timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_rows_oneshot -c 1 -f -o gpurun_out/r02_quant_q40_f16 python tools/codec_sweep.py 58720256 Q4_0:quant > gpurun_out/ncu_q40.log 2>&1; tail -2 gpurun_out/ncu_q40.log ;;
     ncu_kq)  for t in Q4K Q6K Q5K Q2K Q3K; do timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_k_kernel -c 1 -f -o gpurun_out/r02_quant_k_$t python tools/codec_sweep.py 58720256 $t:quant > gpurun_out/ncu_kq_$t.log 2>&1; tail -1 gpurun_out/ncu_kq_$t.log; done ;;
+    ncu_kq2) for t in ${KQ_TYPES:-Q4K Q6K Q5K Q2K}; do timeout 400 ncu --set full --import-source on --clock-control none -k regex:quant_k_kernel -c 1 -f -o gpurun_out/r02b_quant_k_$t python tools/codec_sweep.py 58720256 $t:quant > gpurun_out/ncu_kq_$t.log 2>&1; tail -1 gpurun_out/ncu_kq_$t.log; done ;;
     dio)     df -h /var/tmp /tmp | cat; timeout 900 python tools/direct_io_probe.py > gpurun_out/dio.log 2>&1; tail -8 gpurun_out/dio.log ;;
     tests_conv) timeout 900 python -m pytest tests/test_convert.py -m gpu -x -q -s 2>&1 | tail -40 | cut -c1-400 ;;
     ncu_q8k) timeout 600 ncu --set full --import-source on --clock-control none -k regex:quant_rows_oneshot -c 1 -f -o gpurun_out/r02_quant_q8k_f16 python tools/codec_sweep.py 58720256 Q8K:quant > gpurun_out/ncu_q8k.log 2>&1; tail -2 gpurun_out/ncu_q8k.log ;;

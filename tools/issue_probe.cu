@@ -14,11 +14,14 @@
 #define P_ALU(k) asm volatile("min.relu.s32 %0, %0, %1;" : "+r"(n[k]) : "r"(m))
 #define P_FMNMX(k) asm volatile("min.f32 %0, %0, %1;" : "+f"(g[k]) : "f"(a))
 #define P_FRND(k) asm volatile("cvt.rni.f32.f32 %0, %0;" : "+f"(g[k]))
+#define P_FADD2(k) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[k]) : "l"(a2))
 #define P_LOP(k) asm volatile("xor.b32 %0, %0, %1;" : "+r"(n[k]) : "r"(m))
 
 // MODE: 0 FMUL2 only | 1 FMUL2 + VIMNMX 1:1 | 2 FMUL2 + FMNMX 1:1 | 3 FMUL2 + scalar FADD 1:1 | 4 scalar FMUL + VIMNMX 1:1
 //       5 scalar FMUL only | 6 FMUL2 + FRND 4:1 | 7 VIMNMX only | 8 FMUL2 + LOP3 1:1 | 9 FMUL2 + 2 VIMNMX | 10 FRND only
-//       11 scalar FADD + FRND 4:1
+//       11 scalar FADD + FRND 4:1 | 12 FMUL2 x8 then FADD x8 (grouped) | 13 (FMUL2, FMUL2, FADD, FADD) x4
+//       14 FADD2 + scalar FADD 1:1 | 15 scalar FMUL + scalar FADD 1:1 | 16 the search's candidate-pass mix per pair:
+//       FADD2 FMUL2 VIMNMX VIMNMX FRND FRND FMUL2 FMUL2 FMUL2 + 6 FADD on three chains
 template <int MODE> __global__ void __launch_bounds__(256) probe(float *out, int iters, float a, int m) {
     unsigned long long p[8];
     float f[8], g[8];
@@ -46,6 +49,20 @@ template <int MODE> __global__ void __launch_bounds__(256) probe(float *out, int
             if (MODE == 9) { P_FMUL2(k); P_ALU(k); P_LOP((k + 4) & 7); }
             if (MODE == 10) { P_FRND(k); }
             if (MODE == 11) { P_FADD(k); if ((k & 3) == 0) P_FRND(k); }
+            if (MODE == 13) { if ((k & 1) == 0) { P_FMUL2(k); P_FMUL2(k + 1); P_FADD(k); P_FADD(k + 1); } }
+            if (MODE == 14) { P_FADD2(k); P_FADD(k); }
+            if (MODE == 15) { P_FMUL(k); P_FADD((k + 4) & 7); }
+            if (MODE == 16) {
+                P_FADD2(k); P_FMUL2((k + 3) & 7); P_ALU(k); P_ALU((k + 1) & 7); P_FRND(k); P_FRND((k + 5) & 7);
+                P_FMUL2((k + 1) & 7); P_FMUL2((k + 2) & 7); P_FMUL2((k + 4) & 7);
+                P_FADD(k); P_FADD((k + 1) & 7); P_FADD((k + 2) & 7); P_FADD((k + 3) & 7); P_FADD((k + 4) & 7); P_FADD((k + 5) & 7);
+            }
+        }
+        if (MODE == 12) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) P_FMUL2(k);
+#pragma unroll
+            for (int k = 0; k < 8; k++) P_FADD(k);
         }
     }
     float s = 0;
@@ -58,21 +75,23 @@ template <int MODE> __global__ void __launch_bounds__(256) probe(float *out, int
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+static int g_ctas = 4;   // CTAs of 8 warps per SM: 4 -> 8 warps per scheduler, 2 -> 4
 template <int MODE> void run(const char *name, int instr_per_body, float *out, int sms, double ghz) {
     const int iters = 4000;
     for (int rep = 0; rep < 2; rep++) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        probe<MODE><<<sms * 4, 256>>>(out, iters, 0.9999f, 0x7fffffff);   // 4 CTAs x 8 warps per SM = 8 warps per scheduler
+        probe<MODE><<<sms * g_ctas, 256>>>(out, iters, 0.9999f, 0x7fffffff);   // g_ctas CTAs x 8 warps per SM
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms;
         cudaEventElapsedTime(&ms, e0, e1);
         if (rep == 0) continue;
         // per scheduler: 8 warps x iters x instr_per_body instructions in ms * ghz * 1e6 cycles
-        const double cycles = ms * 1e-3 * ghz * 1e9, instr = 8.0 * iters * instr_per_body;
-        printf("%-34s %8.3f ms  %5.2f warp-instr / cycle / scheduler   %6.2f cycles per body of %d\n", name, ms, instr / cycles, cycles / (8.0 * iters), instr_per_body);
+        const double wps = 2.0 * g_ctas;   // warps per scheduler
+        const double cycles = ms * 1e-3 * ghz * 1e9, instr = wps * iters * instr_per_body;
+        printf("%-34s %8.3f ms  %5.2f warp-instr / cycle / scheduler   %6.2f cycles per body of %d\n", name, ms, instr / cycles, cycles / (wps * iters), instr_per_body);
     }
 }
 
@@ -86,6 +105,9 @@ int main() {
     cudaMalloc(&out, (size_t)prop.multiProcessorCount * 4 * 256 * sizeof(float));
     printf("%s, %d SMs, %.3f GHz (attribute; cycles assume the SM runs at it)\n", prop.name, prop.multiProcessorCount, ghz);
     const int s = prop.multiProcessorCount;
+  for (int pass = 0; pass < 2; pass++) {
+    g_ctas = pass == 0 ? 4 : 2;
+    printf("---- %d warps per scheduler ----\n", 2 * g_ctas);
     run<5>("scalar FMUL x8", 8, out, s, ghz);
     run<0>("FMUL2 x8", 8, out, s, ghz);
     run<7>("VIMNMX.RELU x8", 8, out, s, ghz);
@@ -98,5 +120,11 @@ int main() {
     run<3>("FMUL2 + scalar FADD (8+8)", 16, out, s, ghz);
     run<6>("FMUL2 + FRND (8+2)", 10, out, s, ghz);
     run<11>("scalar FADD + FRND (8+2)", 10, out, s, ghz);
+    run<15>("scalar FMUL + scalar FADD (8+8)", 16, out, s, ghz);
+    run<14>("FADD2 + scalar FADD (8+8)", 16, out, s, ghz);
+    run<12>("FMUL2 x8 then FADD x8", 16, out, s, ghz);
+    run<13>("(FMUL2 FMUL2 FADD FADD) x4", 16, out, s, ghz);
+    run<16>("candidate-pass mix x8 (15 each)", 120, out, s, ghz);
+  }
     return 0;
 }

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <random>
+#include <map>
 #include <vector>
 
 #include "quant_k_kernel.cuh"
@@ -15,12 +16,17 @@ using namespace ggq;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 static int g_sms = 148;
-static std::vector<uint8_t> g_ref;
+static std::map<uint32_t, std::vector<uint8_t>> g_refs;   // bytes of the first configuration, per block type
 static const char *g_only = nullptr;   // argv[2]: run only configurations whose name contains this (e.g. T_Q6K)
 static bool g_first_only = false;      // argv[3] == "first": only the reference configuration of each type (for ncu)
 
+static bool g_dyn = false;             // hand the warp passes out by the ticket counter
+static int g_passes = 0;               // > 0: not persistent — a grid of ngroups / (WARPS * g_passes) CTAs, the hardware hands them out
 template <uint32_t T, class FT, class CFG>
-void run(const char *name, const void *d_x, uint8_t *d_out, size_t nblocks, bool is_ref) {
+void run(const char *name_, const void *d_x, uint8_t *d_out, size_t nblocks, bool is_ref) {
+    char name[96];
+    if (g_passes) snprintf(name, sizeof name, "%s grid/%d", name_, g_passes);
+    else snprintf(name, sizeof name, "%s%s", name_, g_dyn ? " tickets" : "");
     if (g_only && !strstr(name, g_only)) return;
     if (g_first_only && !is_ref) return;
     constexpr int SBW = 32 / (256 / KQuant<T>::SUB);
@@ -33,14 +39,21 @@ void run(const char *name, const void *d_x, uint8_t *d_out, size_t nblocks, bool
     const size_t ngroups = (nblocks + SBW - 1) / SBW;
     size_t grid = (size_t)g_sms * occ;
     if (grid > (ngroups + CFG::WARPS - 1) / CFG::WARPS) grid = (ngroups + CFG::WARPS - 1) / CFG::WARPS;
+    if (g_passes) grid = (ngroups + (size_t)CFG::WARPS * g_passes - 1) / ((size_t)CFG::WARPS * g_passes);
     CK(cudaMemset(d_out, 0xEE, nblocks * BYTES));
-    kern<<<(unsigned)grid, CFG::THREADS>>>(static_cast<const typename FT::raw *>(d_x), d_out, nblocks, 1.0f);
+    static unsigned long long *d_work = nullptr;
+    if (!d_work) CK(cudaMalloc(&d_work, 8));
+    CK(cudaMemsetAsync(d_work, 0, 8));
+    kern<<<(unsigned)grid, CFG::THREADS>>>(static_cast<const typename FT::raw *>(d_x), d_out, nblocks, 1.0f, g_dyn ? d_work : nullptr);
     CK(cudaDeviceSynchronize());
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const int reps = 3;
     CK(cudaEventRecord(e0));
-    for (int r = 0; r < reps; r++) kern<<<(unsigned)grid, CFG::THREADS>>>(static_cast<const typename FT::raw *>(d_x), d_out, nblocks, 1.0f);
+    for (int r = 0; r < reps; r++) {
+        if (g_dyn) CK(cudaMemsetAsync(d_work, 0, 8));   // inside the timed region: the shipped launcher pays it too
+        kern<<<(unsigned)grid, CFG::THREADS>>>(static_cast<const typename FT::raw *>(d_x), d_out, nblocks, 1.0f, g_dyn ? d_work : nullptr);
+    }
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms = 0;
@@ -48,9 +61,10 @@ void run(const char *name, const void *d_x, uint8_t *d_out, size_t nblocks, bool
     std::vector<uint8_t> out(nblocks * BYTES);
     CK(cudaMemcpy(out.data(), d_out, out.size(), cudaMemcpyDeviceToHost));
     const char *same = "ref";
+    std::vector<uint8_t> &g_ref = g_refs[T];
     if (is_ref) g_ref = out;
     else same = (out.size() == g_ref.size() && memcmp(out.data(), g_ref.data(), out.size()) == 0) ? "same bytes" : "BYTES DIFFER";
-    printf("%-26s regs %3d  spill %3zu  smem %6zu  warps/SM %2d  %9.1f us   %s\n", name, fa.numRegs, (size_t)fa.localSizeBytes, (size_t)fa.sharedSizeBytes, occ * CFG::WARPS,
+    printf("%-42s regs %3d  spill %3zu  smem %6zu  warps/SM %2d  %9.1f us   %s\n", name, fa.numRegs, (size_t)fa.localSizeBytes, (size_t)fa.sharedSizeBytes, occ * CFG::WARPS,
            ms * 1000.f / reps, same);
     fflush(stdout);
 }
@@ -59,6 +73,7 @@ void run(const char *name, const void *d_x, uint8_t *d_out, size_t nblocks, bool
 #define RUNA(T, FT, W, REGS, LF, WM, ST, AF) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF ">", d_x, d_out, nblocks, false)
 #define RUNS(T, FT, W, REGS, LF, WM, ST, AF, RM, SD) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM, SD>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM "," #SD ">", d_x, d_out, nblocks, false)
 #define RUNC(T, FT, W, REGS, LF, WM, ST, AF, RM, SD, CL) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM, SD, CL>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM "," #SD "," #CL ">", d_x, d_out, nblocks, false)
+#define RUNP(T, FT, W, REGS, LF, WM, ST, AF, RM, SD, CL, SP) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM, SD, CL, SP>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM "," #SD "," #CL "," #SP ">", d_x, d_out, nblocks, false)
 #define RUNR(T, FT, W, REGS, LF, WM, ST, AF, RM) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM ">", d_x, d_out, nblocks, false)
 
 int main(int argc, char **argv) {
@@ -86,39 +101,36 @@ int main(int argc, char **argv) {
         CK(cudaMemcpy(d_x, h.data(), n * 2, cudaMemcpyHostToDevice));
     }
     printf("%s input, %zu elements, %d SMs; config <WARPS, REGS, LF, WM, STAGES>\n", f32 ? "f32" : "f16", n, g_sms);
-    if (!f32) {
-        RUN(T_Q4K, F16, 4, 128, 0, 2, 2, true);
-        RUNA(T_Q4K, F16, 4, 128, 0, 2, 2, 1);
-        RUNC(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1);   // clamp as one VIMNMX.RELU
-        RUNC(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 0, 0, 1);
-        RUNC(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 2, 0, 1);   // + alternate pairs round on the FP32 pipe
-        RUNC(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 0, 1, 1);   // + shared division
-        RUNA(T_Q4K, F16, 4, 168, 0, 2, 2, 1);   // more registers, fewer warps: 3 per scheduler
-        RUNS(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 0, 1);  // shared division with room for its reciprocals
-        RUNS(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 1, 0);  // all rounding on the FP32 pipe
-        RUNS(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 2, 0);  // alternate pairs
-        RUN(T_Q5K, F16, 4, 128, 0, 2, 2, true);
-        RUNA(T_Q5K, F16, 4, 128, 0, 2, 2, 1);
-        RUNC(T_Q5K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1);
-        RUNC(T_Q5K, F16, 4, 128, 0, 2, 2, 1, 0, 1, 1);
-        RUNA(T_Q5K, F16, 4, 168, 0, 2, 2, 1);
-        RUNS(T_Q5K, F16, 4, 168, 0, 2, 2, 1, 0, 1);
-        RUN(T_Q2K, F16, 4, 72, 0, 2, 2, true);
-        RUNA(T_Q2K, F16, 1, 64, 0, 2, 2, 1);
-        RUNC(T_Q2K, F16, 1, 64, 0, 2, 2, 1, 0, 0, 1);
-        RUNC(T_Q2K, F16, 4, 72, 0, 2, 2, 1, 0, 0, 1);
-        RUNA(T_Q2K, F16, 4, 96, 0, 2, 2, 1);
-        RUN(T_Q6K, F16, 4, 96, 0, 2, 2, true);
-        RUNR(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 2);
-        RUNR(T_Q6K, F16, 4, 128, 0, 2, 2, 0, 2);
-        RUN(T_Q3K, F16, 4, 96, 0, 2, 2, true);
-        RUN(T_Q3K, F16, 4, 128, 0, 2, 2, false);
-    } else {
-        RUN(T_Q4K, F32, 4, 128, 0, 2, 2, true);
-        RUNS(T_Q4K, F32, 4, 128, 0, 2, 2, 1, 0, 1);
-        RUNC(T_Q4K, F32, 4, 128, 0, 2, 2, 1, 0, 0, 1);
-        RUN(T_Q6K, F32, 4, 96, 0, 2, 2, true);
-        RUNS(T_Q6K, F32, 4, 96, 0, 2, 2, 0, 2, 1);
+    for (int dyn = 0; dyn < 6; dyn++) {
+        g_dyn = dyn == 1;
+        g_passes = dyn >= 2 ? (dyn == 5 ? 6 : dyn - 1) : 0;   // 1, 2, 3, 6 passes per warp
+        if (!f32) {
+            RUN(T_Q4K, F16, 4, 128, 0, 2, 2, dyn == 0);
+            RUNC(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1);   // shipped: packed affine, clamp as one VIMNMX.RELU
+            RUNP(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1, 1);   // + the next candidate's iscale divided out early
+            RUNP(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 0, 0, 1, 1);
+            RUNC(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 0, 0, 1);   // 140 registers, three warps per scheduler
+            RUNC(T_Q4K, F16, 1, 128, 0, 2, 2, 1, 0, 0, 1);   // one-warp CTAs
+            RUN(T_Q5K, F16, 4, 128, 0, 2, 2, dyn == 0);
+            RUNC(T_Q5K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1);
+            RUNP(T_Q5K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1, 1);
+            RUN(T_Q2K, F16, 4, 72, 0, 2, 2, dyn == 0);
+            RUNC(T_Q2K, F16, 1, 64, 0, 2, 2, 1, 0, 0, 1);
+            RUNP(T_Q2K, F16, 1, 64, 0, 2, 2, 1, 0, 0, 1, 1);
+            RUNC(T_Q2K, F16, 4, 64, 0, 2, 2, 1, 0, 0, 1);
+            RUN(T_Q6K, F16, 4, 96, 0, 2, 2, dyn == 0);
+            RUNR(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 2);
+            RUNR(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 0);
+            RUNR(T_Q6K, F16, 1, 96, 0, 2, 2, 0, 2);
+            RUN(T_Q3K, F16, 4, 96, 0, 2, 2, dyn == 0);
+            RUN(T_Q3K, F16, 1, 96, 0, 2, 2, false);
+        } else {
+            RUN(T_Q4K, F32, 4, 128, 0, 2, 2, dyn == 0);
+            RUNC(T_Q4K, F32, 4, 128, 0, 2, 2, 1, 0, 0, 1);
+            RUN(T_Q6K, F32, 4, 96, 0, 2, 2, dyn == 0);
+            RUNR(T_Q6K, F32, 4, 96, 0, 2, 2, 0, 2);
+            RUN(T_Q3K, F32, 4, 96, 0, 2, 2, dyn == 0);
+        }
     }
     return 0;
 }

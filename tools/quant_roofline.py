@@ -18,11 +18,22 @@ WANT = {"smsp__inst_executed.sum": "warp_instructions", "gpu__time_duration.sum"
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active": "alu_pipe_pct",
         "launch__registers_per_thread": "registers", "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct"}
 out = {"n_elems": n, "sm_clock_mhz": 1965.0, "instr_per_elem": {}, "kernels": {},
+       "note_fp32": "fp32_pipe_limit_us = ncu_us x sm__pipe_fma_cycles_active: what the launch would take with the FP32 pipe busy every cycle",
        "note": "instr_per_elem = smsp__inst_executed.sum * 32 / n_elems (thread-instruction equivalents); issue roofline = warp "
                "instructions / (148 SMs x 4 schedulers x 1.965 GHz)"}
+try:
+    PREV = json.load(open(os.path.join(ROOT, "profiles", "r02_quant_k_roofline.json")))
+except (OSError, ValueError):
+    PREV = {}
 for ty in ("Q4K", "Q6K", "Q5K", "Q2K", "Q3K"):
-    rep = os.path.join(ROOT, "gpurun_out", f"r02_quant_k_{ty}.ncu-rep")
-    if not os.path.exists(rep):
+    # r02b_*: captures made after the VIMNMX.RELU clamp (Q4K / Q5K / Q2K changed; tools/gpu_round.sh ncu_kq2)
+    reps = [os.path.join(ROOT, "gpurun_out", f"{pre}_quant_k_{ty}.ncu-rep") for pre in ("r02b", "r02")]
+    rep = next((r for r in reps if os.path.exists(r)), None)
+    if rep is None:
+        prev = PREV.get("kernels", {}).get(ty)   # keep the committed record of a kernel that was not re-captured
+        if prev:
+            out["instr_per_elem"][ty] = prev["instr_per_elem"]
+            out["kernels"][ty] = prev
         continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -38,6 +49,10 @@ for ty in ("Q4K", "Q6K", "Q5K", "Q2K", "Q3K"):
     ipe = rec["warp_instructions"] * 32 / n
     rec["instr_per_elem"] = ipe
     rec["issue_limit_us"] = rec["warp_instructions"] / (148 * 4 * 1965e6) * 1e6
+    # the time the FP32 pipe alone would need: ncu's busy fraction of it x the launch under ncu (a packed FADD2 / FMUL2 /
+    # FFMA2 holds the pipe two cycles, so this counts lane operations, not instructions)
+    if "fp32_pipe_cycles_active_pct" in rec:
+        rec["fp32_pipe_limit_us"] = rec["ncu_us"] * rec["fp32_pipe_cycles_active_pct"] / 100.0
     out["instr_per_elem"][ty] = ipe
     out["kernels"][ty] = rec
 json.dump(out, open(os.path.join(ROOT, "profiles", "r02_quant_k_roofline.json"), "w"), indent=1)
