@@ -10,14 +10,16 @@ namespace ggq {
 // Shipped configuration per type (tools/kq_sweep.cu; profiles/r02_kq_sweep*.txt).  The register file is split per SM
 // sub-partition (4 x 16 K registers), so occupancy moves in steps of one warp per scheduler: 4 at <= 128 registers, 5 at
 // <= 96, 6 at <= 80, 7 at <= 72, 8 at <= 64.  Q4K / Q5K need 128 (x, weights and candidate codes of a 32-element
-// sub-block: moving the codes or the weights to shared memory, recomputing the weights, or one-warp CTAs at 96-120
-// registers were all 4-60 % slower: the loop itself keeps ~112 registers live and spills cost more than the fifth warp
-// buys).  What ships beyond round 1: the packed affine (AF 1: -1..-1.6 %), and for Q2K one-warp CTAs at 64 registers
-// (8 warps per scheduler instead of 7, and no 4-warp granularity in the tail: -5 %).
+// sub-block: moving the codes or the weights to shared memory, recomputing the weights, or 96-120 registers were all
+// 4-60 % slower: the loop itself keeps ~112 registers live and spills cost more than the fifth warp buys).
+//   AF 1  the search's scale * l + min as FMUL2 + FFMA2 by an opaque 1.0 (-1..-1.6 %)
+//   CL 1  the search's clamp to [0, nmax] as one VIMNMX.RELU per element instead of two FMNMX (-3.5..-4 %)
+//   WARPS 1 (Q2K, Q4K, Q5K): warps are independent (own staging, own scratch, __syncwarp only), and with one pass per warp
+//         (below) a one-warp CTA frees its slot the moment its pass ends; also compiles without the 16-byte spill
+//         (Q4K 761 -> 754 us, Q5K 610 -> 603; Q2K: 8 warps per scheduler at 64 registers instead of 7)
 template <uint32_t T> struct KqShipped { using type = KqCfg<4, KQuant<T>::REGS, 0, 2, 2>; };
-// CL 1: the search's clamp to [0, nmax] is one VIMNMX.RELU per element instead of two FMNMX (quant_k_kernel.cuh, clamp0_relu).
-template <> struct KqShipped<T_Q4K> { using type = KqCfg<4, 128, 0, 2, 2, 1, 0, 0, 1>; };
-template <> struct KqShipped<T_Q5K> { using type = KqCfg<4, 128, 0, 2, 2, 1, 0, 0, 1>; };
+template <> struct KqShipped<T_Q4K> { using type = KqCfg<1, 128, 0, 2, 2, 1, 0, 0, 1>; };
+template <> struct KqShipped<T_Q5K> { using type = KqCfg<1, 128, 0, 2, 2, 1, 0, 0, 1>; };
 template <> struct KqShipped<T_Q2K> { using type = KqCfg<1, 64, 0, 2, 2, 1, 0, 0, 1>; };
 // Q6K's hottest pipe is the XU (FRND: 62 % busy against 49 % for the FP32 pipe): rounding every other pair with the two
 // magic-number adds instead balances the two (-1 %); all pairs on the FP32 pipe is +3 %.

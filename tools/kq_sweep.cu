@@ -101,29 +101,33 @@ int main(int argc, char **argv) {
         CK(cudaMemcpy(d_x, h.data(), n * 2, cudaMemcpyHostToDevice));
     }
     printf("%s input, %zu elements, %d SMs; config <WARPS, REGS, LF, WM, STAGES>\n", f32 ? "f32" : "f16", n, g_sms);
-    for (int dyn = 0; dyn < 6; dyn++) {
+    // rounds: 0 persistent grid, fixed stride (what shipped until round 2's last step) | 1 persistent, passes by ticket
+    // (ships for Q3K) | 2.. not persistent: 1 / 2 / 3 / 6 passes per warp (1 ships for Q2K / Q4K / Q5K / Q6K)
+    const int nrounds = getenv("KQ_ROUNDS") ? atoi(getenv("KQ_ROUNDS")) : 6;
+    for (int dyn = 0; dyn < nrounds; dyn++) {
         g_dyn = dyn == 1;
-        g_passes = dyn >= 2 ? (dyn == 5 ? 6 : dyn - 1) : 0;   // 1, 2, 3, 6 passes per warp
+        g_passes = dyn >= 2 ? (dyn == 5 ? 6 : dyn - 1) : 0;
         if (!f32) {
             RUN(T_Q4K, F16, 4, 128, 0, 2, 2, dyn == 0);
             RUNC(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1);   // shipped: packed affine, clamp as one VIMNMX.RELU
-            RUNP(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1, 1);   // + the next candidate's iscale divided out early
-            RUNP(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 0, 0, 1, 1);
-            RUNC(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 0, 0, 1);   // 140 registers, three warps per scheduler
+            RUNC(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 0, 0, 1);   // 140 registers, three warps per scheduler, no spill
+            RUNC(T_Q4K, F16, 2, 128, 0, 2, 2, 1, 0, 0, 1);   // two-warp CTAs
             RUNC(T_Q4K, F16, 1, 128, 0, 2, 2, 1, 0, 0, 1);   // one-warp CTAs
+            RUNC(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 2, 0, 1);   // alternate pairs round on the FP32 pipe
+            RUNC(T_Q4K, F16, 4, 128, 0, 2, 1, 1, 0, 0, 1);   // one input stage (a one-shot CTA has no next pass to prefetch)
             RUN(T_Q5K, F16, 4, 128, 0, 2, 2, dyn == 0);
             RUNC(T_Q5K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1);
-            RUNP(T_Q5K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1, 1);
+            RUNC(T_Q5K, F16, 1, 128, 0, 2, 2, 1, 0, 0, 1);
             RUN(T_Q2K, F16, 4, 72, 0, 2, 2, dyn == 0);
             RUNC(T_Q2K, F16, 1, 64, 0, 2, 2, 1, 0, 0, 1);
-            RUNP(T_Q2K, F16, 1, 64, 0, 2, 2, 1, 0, 0, 1, 1);
             RUNC(T_Q2K, F16, 4, 64, 0, 2, 2, 1, 0, 0, 1);
+            RUNC(T_Q2K, F16, 2, 64, 0, 2, 2, 1, 0, 0, 1);
             RUN(T_Q6K, F16, 4, 96, 0, 2, 2, dyn == 0);
             RUNR(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 2);
-            RUNR(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 0);
-            RUNR(T_Q6K, F16, 1, 96, 0, 2, 2, 0, 2);
+            RUNR(T_Q6K, F16, 2, 96, 0, 2, 2, 0, 2);
+            RUNR(T_Q6K, F16, 4, 96, 0, 2, 1, 0, 2);
             RUN(T_Q3K, F16, 4, 96, 0, 2, 2, dyn == 0);
-            RUN(T_Q3K, F16, 1, 96, 0, 2, 2, false);
+            RUN(T_Q3K, F16, 2, 96, 0, 2, 2, false);
         } else {
             RUN(T_Q4K, F32, 4, 128, 0, 2, 2, dyn == 0);
             RUNC(T_Q4K, F32, 4, 128, 0, 2, 2, 1, 0, 0, 1);
