@@ -23,7 +23,8 @@ template <> struct KqShipped<T_Q5K> { using type = KqCfg<1, 128, 0, 2, 2, 1, 0, 
 template <> struct KqShipped<T_Q2K> { using type = KqCfg<1, 64, 0, 2, 2, 1, 0, 0, 1>; };
 // Q6K's hottest pipe is the XU (FRND: 62 % busy against 49 % for the FP32 pipe): rounding every other pair with the two
 // magic-number adds instead balances the two (-1 %); all pairs on the FP32 pipe is +3 %.
-template <> struct KqShipped<T_Q6K> { using type = KqCfg<4, 96, 0, 2, 2, 0, 2>; };
+// CS 1: the clamp to [-32, 31] only for the candidates that can reach a bound (make_qx_quants16): 444 -> 424 us.
+template <> struct KqShipped<T_Q6K> { using type = KqCfg<4, 96, 0, 2, 2, 0, 2, 0, 0, 0, 1>; };
 
 // ---- how the warp passes reach the warps (tools/kq_sweep.cu, profiles/r02_kq_sweep_grid_f16.txt) ---------------------
 // A warp pass (32 sub-block searches) takes 8-35 us.  A persistent grid with a fixed stride was the slowest way to hand

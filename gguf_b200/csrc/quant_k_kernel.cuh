@@ -166,9 +166,15 @@ template <int AF> __device__ __forceinline__ float2 affine2(float2 l, float ns, 
 // magic-number adds for every pair (two packed FP32-pipe instructions per pair), 2 = alternating pairs, which splits the
 // rounding work between the two pipes.
 // CL 1 (only where lo == 0): the clamp is one VIMNMX.RELU per element (clamp0_relu) instead of two FMNMX.
+// CL 2: only the upper bound is applied, CL 3: none (make_qx_quants16 proves which candidates can reach which bound).
 template <int RM, int CL = 0> __device__ __forceinline__ float2 round_clamped2(float2 v, float lo, float hi, int k) {
-    const float2 c = CL ? make_float2(clamp0_relu(v.x, hi), clamp0_relu(v.y, hi)) : clamp2(v, lo, hi);
-    if (RM == 1 || (RM == 2 && (k & 1))) return __fadd2_rn(__fadd2_rn(c, bcast2(RMAGIC)), bcast2(-RMAGIC));
+    const float2 c = CL == 1   ? make_float2(clamp0_relu(v.x, hi), clamp0_relu(v.y, hi))
+                     : CL == 2 ? make_float2(fminf(v.x, hi), fminf(v.y, hi))
+                     : CL == 3 ? v
+                               : clamp2(v, lo, hi);
+    // (not with CL 3: there `c` is the packed product itself, and ptxas contracts a packed multiply feeding a packed add
+    // into one single-rounding FFMA2 — the unclamped candidates always round with FRND)
+    if (CL != 3 && (RM == 1 || (RM == 2 && (k & 1)))) return __fadd2_rn(__fadd2_rn(c, bcast2(RMAGIC)), bcast2(-RMAGIC));
     return make_float2(rintf(c.x), rintf(c.y));
 }
 
@@ -339,7 +345,16 @@ __device__ __forceinline__ void qx_codes16(const float (&x)[16], const float isc
 // returns the scale; `isc_best` = iscale of the kept codes; `all_zero`: upstream's early exit (L[i] = 0, raw)
 // WS 1: the per-element constants w = x*x and w*x live in the lane's shared-memory row (32 floats: w at [0, 16), w*x at
 // [16, 32)) instead of 32 registers.
-template <int WS, int RM, int SD>
+// CS 1: the clamp to [-nmax, nmax - 1] is applied only where a candidate can reach it.  Every |x| <= |mx|, and candidate
+// `is` multiplies by iscale = RN(-(nmax + RN(0.1f is)) / mx), so |iscale x| <= (nmax + 0.1 is) (1 + 2^-23) (1 + 2^-24)^2:
+//   is <= -6:  |v| <= 31.40001 < 31.5   -> rint(v) in [-31, 31]: neither bound can be reached (4 candidates)
+//   is <=  4:  |v| <= 32.40001 < 32.5   -> rint(v) in [-32, 32]: only the upper bound nmax - 1 = 31 (9 candidates and
+//              the first evaluation, whose iscale is -nmax / mx: |v| <= 32.00001)
+//   is >=  5:  both (RN(-32.5 / mx) mx may land beyond the tie at -32.5)                       (5 candidates)
+// (nmax = 32; the bounds use nmax only through these constants, hence the static_assert on the caller's side.)
+// The values are the same floats whether a bound that cannot bind is applied or not: 32 + 16 fewer instructions per 16
+// elements in the first two groups, on a kernel that is issue-bound.
+template <int WS, int RM, int SD, int CS = 0>
 __device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const int nmax, float &isc_best, bool &all_zero, float *__restrict__ lrow) {
     float mx = 0, amax = 0;
 #pragma unroll
@@ -369,12 +384,13 @@ __device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const in
         }
     }
     // sumlx, suml2 for `isc`, accumulated in element order
-    auto sums = [&](float isc, float &sumlx, float &suml2) {
+    auto sums = [&](float isc, float &sumlx, float &suml2, auto clamp_mode) {
+        constexpr int CLM = decltype(clamp_mode)::value;   // 0 both bounds, 2 upper only, 3 none (round_clamped2)
         const float2 isc2 = bcast2(isc);
         sumlx = suml2 = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float2 l = round_clamped2<RM>(__fmul2_rn(isc2, x2[k]), lo, hi, k);
+            const float2 l = round_clamped2<RM, CLM>(__fmul2_rn(isc2, x2[k]), lo, hi, k);
             float2 wk, wxk;
             if constexpr (WS) {
                 if ((k & 1) == 0) {
@@ -397,20 +413,31 @@ __device__ __forceinline__ float make_qx_quants16(const float (&x)[16], const in
     };
     const SharedDivisor smx = shared_divisor(mx);  // all 19 candidates divide by mx
     float iscale = div_shared_strict<SD>(lo, smx);
+    using Both = std::integral_constant<int, 0>;
+    using Upper = std::integral_constant<int, CS ? 2 : 0>;
+    using None = std::integral_constant<int, CS ? 3 : 0>;
     float sumlx, suml2;
-    sums(iscale, sumlx, suml2);
+    sums(iscale, sumlx, suml2, Upper{});
     isc_best = iscale;
     float scale = suml2 ? sumlx / suml2 : 0.0f;
     float best = scale * sumlx;
-    for (int is = -9; is <= 9; ++is) {
-        if (is == 0) continue;
+    auto candidate = [&](int is, auto clamp_mode) {
         iscale = div_shared_strict<SD>(-(fn + 0.1f * (float)is), smx);
-        sums(iscale, sumlx, suml2);
+        sums(iscale, sumlx, suml2, clamp_mode);
         if (suml2 > 0 && sumlx * sumlx > best * suml2) {
             isc_best = iscale;
             scale = sumlx / suml2;
             best = scale * sumlx;
         }
+    };
+    if constexpr (CS) {
+        for (int is = -9; is <= -6; ++is) candidate(is, None{});
+        for (int is = -5; is <= 4; ++is)
+            if (is != 0) candidate(is, Upper{});
+        for (int is = 5; is <= 9; ++is) candidate(is, Both{});
+    } else {
+        for (int is = -9; is <= 9; ++is)
+            if (is != 0) candidate(is, Both{});
     }
     return scale;
 }
@@ -621,7 +648,7 @@ template <> struct KQuant<T_Q6K> {
         uint32_t L[4] = {0, 0, 0, 0};
         float isc_best;
         bool sub_zero;
-        const float scale = make_qx_quants16<CFG::LF, CFG::RM, CFG::SD>(x, 32, isc_best, sub_zero, lrow);
+        const float scale = make_qx_quants16<CFG::LF, CFG::RM, CFG::SD, CFG::CS>(x, 32, isc_best, sub_zero, lrow);   // nmax = 32: see CS
         const float max_scale = group_max_by_abs<16>(scale, lane_id);
         const bool zero = fabsf(max_scale) < GROUP_MAX_EPS;
         int sc = 0;
@@ -756,8 +783,8 @@ template <> struct KQuant<T_Q3K> {
 // which lets occupancy follow the register cap in steps of one warp rather than four), REGS (register cap per thread,
 // __maxnreg__), LF (per-lane shared-memory row: candidate codes for the qkx2 searches, w / w*x for Q6K),
 // WM (Q4K / Q5K weights: 2 registers, 1 recomputed), STAGES (input rows in flight).
-template <int WARPS_, int REGS_, int LF_, int WM_, int STAGES_, int AF_ = 0, int RM_ = 0, int SD_ = 0, int CL_ = 0, int SP_ = 0> struct KqCfg {
-    static constexpr int WARPS = WARPS_, THREADS = WARPS_ * 32, REGS = REGS_, LF = LF_, WM = WM_, STAGES = STAGES_, AF = AF_, RM = RM_, SD = SD_, CL = CL_, SP = SP_;
+template <int WARPS_, int REGS_, int LF_, int WM_, int STAGES_, int AF_ = 0, int RM_ = 0, int SD_ = 0, int CL_ = 0, int SP_ = 0, int CS_ = 0> struct KqCfg {
+    static constexpr int WARPS = WARPS_, THREADS = WARPS_ * 32, REGS = REGS_, LF = LF_, WM = WM_, STAGES = STAGES_, AF = AF_, RM = RM_, SD = SD_, CL = CL_, SP = SP_, CS = CS_;
 };
 constexpr int KQ_LROW = 36;  // floats between the lanes' rows: 144 bytes, so eight lanes' 128-bit accesses cover all 32 banks
 

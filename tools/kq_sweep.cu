@@ -74,6 +74,7 @@ void run(const char *name_, const void *d_x, uint8_t *d_out, size_t nblocks, boo
 #define RUNS(T, FT, W, REGS, LF, WM, ST, AF, RM, SD) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM, SD>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM "," #SD ">", d_x, d_out, nblocks, false)
 #define RUNC(T, FT, W, REGS, LF, WM, ST, AF, RM, SD, CL) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM, SD, CL>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM "," #SD "," #CL ">", d_x, d_out, nblocks, false)
 #define RUNP(T, FT, W, REGS, LF, WM, ST, AF, RM, SD, CL, SP) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM, SD, CL, SP>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM "," #SD "," #CL "," #SP ">", d_x, d_out, nblocks, false)
+#define RUNQ(T, FT, W, REGS, LF, WM, ST, AF, RM, SD, CL, SP, CS) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM, SD, CL, SP, CS>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM "," #SD "," #CL "," #SP "," #CS ">", d_x, d_out, nblocks, false)
 #define RUNR(T, FT, W, REGS, LF, WM, ST, AF, RM) run<T, FT, KqCfg<W, REGS, LF, WM, ST, AF, RM>>(#T " " #FT " <" #W "," #REGS "," #LF "," #WM "," #ST "," #AF "," #RM ">", d_x, d_out, nblocks, false)
 
 int main(int argc, char **argv) {
@@ -124,7 +125,11 @@ int main(int argc, char **argv) {
             RUNC(T_Q2K, F16, 2, 64, 0, 2, 2, 1, 0, 0, 1);
             RUN(T_Q6K, F16, 4, 96, 0, 2, 2, dyn == 0);
             RUNR(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 2);
-            RUNR(T_Q6K, F16, 2, 96, 0, 2, 2, 0, 2);
+            RUNQ(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 2, 0, 0, 0, 1);   // clamp only where a candidate can reach the bound
+            RUNQ(T_Q6K, F16, 4, 96, 0, 2, 2, 0, 0, 0, 0, 0, 1);
+            RUNQ(T_Q6K, F16, 1, 96, 0, 2, 2, 0, 2, 0, 0, 0, 1);
+            RUNC(T_Q2K, F16, 1, 64, 0, 2, 2, 1, 2, 0, 1);          // Q2K / Q5K with alternate pairs rounded on the FP32 pipe
+            RUNC(T_Q5K, F16, 1, 128, 0, 2, 2, 1, 2, 0, 1);
             RUNR(T_Q6K, F16, 4, 96, 0, 2, 1, 0, 2);
             RUN(T_Q3K, F16, 4, 96, 0, 2, 2, dyn == 0);
             RUN(T_Q3K, F16, 2, 96, 0, 2, 2, false);
