@@ -16,7 +16,9 @@
 //     order-independent; "first with greatest |.|" uses a lowest-lane-wins arg-max);
 //   * codes go through a per-warp shared-memory scratch and are assembled into the packed layout one 32-bit
 //     (Q2K / Q4K / Q5K) or 16-bit (Q3K / Q6K) unit per lane and iteration, then copied to global memory;
-//   * the rows of the next warp pass arrive by cp.async while this pass searches.
+//   * the launcher decides who hands out the warp passes (quant_k.cu): one pass per warp and the hardware's CTA
+//     scheduler (Q2K / Q4K / Q5K / Q6K), or a persistent grid whose passes are tickets of a launch-wide counter (Q3K);
+//     a warp that takes more than one pass has the rows of its next pass arrive by cp.async while this pass searches.
 // This path is COMPUTE-bound (~400 dependent flops per element for Q4K), not HBM-bound; see DESIGN.md.
 #pragma once
 #include <type_traits>

@@ -113,12 +113,16 @@ int main(int argc, char **argv) {
             RUNC(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1);   // shipped: packed affine, clamp as one VIMNMX.RELU
             RUNC(T_Q4K, F16, 4, 168, 0, 2, 2, 1, 0, 0, 1);   // 140 registers, three warps per scheduler, no spill
             RUNC(T_Q4K, F16, 2, 128, 0, 2, 2, 1, 0, 0, 1);   // two-warp CTAs
-            RUNC(T_Q4K, F16, 1, 128, 0, 2, 2, 1, 0, 0, 1);   // one-warp CTAs
+            RUNC(T_Q4K, F16, 1, 128, 0, 2, 2, 1, 0, 0, 1);   // one-warp CTAs (shipped)
+            RUNC(T_Q4K, F16, 1, 128, 0, 2, 2, 1, 0, 1, 1);   // + shared-divisor quotients (the one-warp build has no spill to double)
+            RUNC(T_Q4K, F16, 1, 136, 0, 2, 2, 1, 0, 0, 1);   // 136 registers: 15 one-warp CTAs per SM
+            RUNC(T_Q4K, F16, 1, 120, 0, 2, 2, 1, 0, 0, 1);   // 120 registers: 17
             RUNC(T_Q4K, F16, 4, 128, 0, 2, 2, 1, 2, 0, 1);   // alternate pairs round on the FP32 pipe
             RUNC(T_Q4K, F16, 4, 128, 0, 2, 1, 1, 0, 0, 1);   // one input stage (a one-shot CTA has no next pass to prefetch)
             RUN(T_Q5K, F16, 4, 128, 0, 2, 2, dyn == 0);
             RUNC(T_Q5K, F16, 4, 128, 0, 2, 2, 1, 0, 0, 1);
             RUNC(T_Q5K, F16, 1, 128, 0, 2, 2, 1, 0, 0, 1);
+            RUNC(T_Q5K, F16, 1, 128, 0, 2, 2, 1, 0, 1, 1);
             RUN(T_Q2K, F16, 4, 72, 0, 2, 2, dyn == 0);
             RUNC(T_Q2K, F16, 1, 64, 0, 2, 2, 1, 0, 0, 1);
             RUNC(T_Q2K, F16, 4, 64, 0, 2, 2, 1, 0, 0, 1);
