@@ -174,6 +174,48 @@ def test_concurrent_callers(ggq, oracle):
         assert np.array_equal(out[i], oracle.quantize(types[i], F16, xs[i], threads=4))
 
 
+def test_concurrent_kquant_launches_have_their_own_ticket_counter(ggq, oracle):
+    """Q3K's big launches hand their warp passes out through an 8-byte counter owned by (calling thread, device,
+    stream) and zeroed in stream order (quant_k.cu, work_slot).  Launches that can overlap — other host threads, other
+    streams of one thread — must not share one: every byte is compared with the oracle, a shared counter would skip or
+    repeat passes.  Inputs are big enough for the ticket path (more passes than resident warps)."""
+    import torch
+    Q3K, Q4K = 11, 12
+    n = 256 * 12288                      # 3.1 M elements: 6 144 Q3K passes against 2 960 resident warps
+    xs = [to_fdt(gaussian(n, 300 + i), F16) for i in range(4)]
+    want = [oracle.quantize(Q3K, F16, x, threads=16) for x in xs]
+    # (a) four host threads, each repeating its own tensor through the host API
+    out = [[None] * 3 for _ in range(4)]
+
+    def work(i):
+        for r in range(3):
+            out[i][r] = ggq.quantize(Q3K, xs[i], F16)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(4):
+        for r in range(3):
+            assert np.array_equal(out[i][r], want[i]), f"thread {i} repeat {r}"
+    # (b) one thread, four streams, launches queued back to back without a synchronize in between (a Q4K launch, which
+    # needs no counter, rides along on each stream)
+    _, b3 = oracle.block_info(Q3K)
+    _, b4 = oracle.block_info(Q4K)
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    dx = [torch.from_numpy(x.view(np.uint8)).cuda() for x in xs]
+    d3 = [torch.zeros(n // 256 * b3, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    d4 = [torch.zeros(n // 256 * b4, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    torch.cuda.synchronize()
+    for r in range(3):
+        for i, st in enumerate(streams):
+            ggq.quantize_slice_device(Q3K, F16, d3[i].data_ptr(), n // 256, dx[i].data_ptr(), n, st.cuda_stream)
+            ggq.quantize_slice_device(Q4K, F16, d4[i].data_ptr(), n // 256, dx[i].data_ptr(), n, st.cuda_stream)
+    torch.cuda.synchronize()
+    for i in range(4):
+        assert np.array_equal(d3[i].cpu().numpy(), want[i]), f"stream {i}"
+        assert np.array_equal(d4[i].cpu().numpy(), oracle.quantize(Q4K, F16, xs[i], threads=16)), f"stream {i} Q4K"
+
+
 @pytest.mark.parametrize("ty", [2, 8, 12, 14])
 def test_device_api_alignment_independence(ggq, oracle, ty):
     """Device pointers at odd 2-byte offsets take the byte-exact paths; results must not change."""
