@@ -94,7 +94,7 @@ static cudaError_t launch_quant_k(const void *src, void *dst, size_t nblocks, cu
     const size_t want = (ngroups + CFG::WARPS - 1) / CFG::WARPS;   // one pass per warp
     size_t grid = want;
     unsigned long long *work = nullptr;
-    if (KqGridOf<T>::value == KqGrid::Tickets) {
+    if constexpr (KqGridOf<T>::value == KqGrid::Tickets) {
         static std::atomic<int> occ_cache[MAX_DEVICES];
         int ctas_per_sm = 0;
         cudaError_t e = cached_occupancy(kern, CFG::THREADS, 0, dev.device, occ_cache, &ctas_per_sm);
