@@ -256,8 +256,10 @@ void *ggq_host_alloc(size_t bytes);
 void ggq_host_free(void *p);
 
 /* Releases the idle stream pipelines (device staging buffers, pinned bounce buffers, streams) the host
- * entry points keep pooled between calls, and the device memory cached by the stream-ordered allocator.  Safe at any time; pipelines in use are not touched and the
- * pool refills on demand. */
+ * entry points keep pooled between calls, the device memory cached by the stream-ordered allocator, and the 8-byte
+ * ticket counters the Q3_K quantizer keeps per (calling thread, device, stream).  Pipelines in use are not touched and
+ * everything is re-created on demand; do not call it while another thread has a `_device` quantize call in flight on a
+ * stream (the counter of that launch would be freed under it). */
 void ggq_shutdown(void);
 
 /* Number of kernel launches issued by this library since load (all threads); for harnesses. */
