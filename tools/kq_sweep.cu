@@ -2,6 +2,10 @@
 // on a 4096x14336 f16 (or f32) Gaussian tensor and checks that every configuration writes the same bytes as the first.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -fmad=false --ftz=false --prec-div=true --prec-sqrt=true \
 //        -I gguf_b200/csrc tools/kq_sweep.cu -o tools/kq_sweep
+// The library's Makefile refuses objects with a contracted packed multiply-add (an FFMA2 whose multiplier is not the uniform
+// register holding 1.0); this binary is not guarded, so a variant that invites the contraction shows up as "BYTES DIFFER"
+// here (it did: Q6K unclamped candidates rounded with the magic-number add).  The same check by hand:
+//   cuobjdump -sass tools/kq_sweep | grep FFMA2 | grep -v "UR[0-9]*\.F32"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
