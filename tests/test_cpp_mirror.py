@@ -38,6 +38,17 @@ def test_shared_divisor_division_is_correctly_rounded():
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_q6k_clamp_bounds_hold_for_every_candidate_group():
+    """tests/cpp/test_q6k_clamp_bounds.c: the Q6K search applies its clamp to [-32, 31] only where a candidate can reach a
+    bound (quant_k_kernel.cuh, make_qx_quants16, CS 1); the float expressions of the kernel, evaluated on the host for the
+    extreme ratios x = +-max over every exponent and adversarial significands, stay inside the claimed ranges."""
+    exe = os.path.join(ROOT, "tests", "cpp", "test_q6k_clamp_bounds")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_q6k_clamp_bounds.c"), "-lm"])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 bound violations" in r.stdout
+
+
 @pytest.mark.gpu
 def test_cpp_mirror_reference_unit_tests(ggq):
     build(ggq)
