@@ -38,6 +38,17 @@ def test_shared_divisor_division_is_correctly_rounded():
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_relu_clamp_equals_the_two_sided_float_clamp():
+    """tests/cpp/test_clamp_relu.c: `min.relu.s32` on the float's bits (the K-quant search's one-instruction clamp to
+    [0, nmax]) returns the value of fminf(fmaxf(v, 0), nmax) for every non-NaN float (every 13th pattern and the
+    neighbourhoods of the boundaries here; `test_clamp_relu all` walks all 2^32)."""
+    exe = os.path.join(ROOT, "tests", "cpp", "test_clamp_relu")
+    subprocess.check_call(["gcc", "-O2", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_clamp_relu.c"), "-lm"])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 differ" in r.stdout
+
+
 def test_q6k_clamp_bounds_hold_for_every_candidate_group():
     """tests/cpp/test_q6k_clamp_bounds.c: the Q6K search applies its clamp to [-32, 31] only where a candidate can reach a
     bound (quant_k_kernel.cuh, make_qx_quants16, CS 1); the float expressions of the kernel, evaluated on the host for the
